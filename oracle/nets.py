@@ -1,0 +1,244 @@
+"""Oracle: ResUNet generator + 3D PatchGAN discriminator (torch CPU, autograd).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Tensors are NDHWC at the
+interface, exactly like the reference's Keras `channels_last` models; weights are
+kept in Keras layout: Conv3D kernel (kd,kh,kw,Cin,Cout), bias (Cout), InstanceNorm
+gamma/beta (C).
+
+Follows
+  resunet_model.py:23-39   norm_act           resunet_model.py:42-66   conv_block
+  resunet_model.py:69-100  stem               resunet_model.py:103-143 residual_block
+  resunet_model.py:146-182 upsample_concat    resunet_model.py:185-249 ResUNet
+  discriminator.py:47-124  get_discriminator  building_blocks.py:126-196 downsample
+  building_blocks.py:15-39 ReflectionPadding3D
+with the arguments VanGan passes (vangan.py:112-122,151-162,167-192).
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+IN_EPS = 1e-3  # tfa.layers.InstanceNormalization default epsilon
+
+
+# --------------------------------------------------------------------------- helpers
+def _ncdhw(x):
+    return x.permute(0, 4, 1, 2, 3)
+
+
+def _ndhwc(x):
+    return x.permute(0, 2, 3, 4, 1)
+
+
+def reflect_pad(x, p=1):
+    """building_blocks.py:28-39 — tf.pad(..., mode='REFLECT') on the three spatial axes."""
+    return _ndhwc(F.pad(_ncdhw(x), (p, p, p, p, p, p), mode="reflect"))
+
+
+def conv3d(x, w, b=None, stride=1, padding="valid"):
+    """Keras Conv3D on NDHWC input with kernel (kd,kh,kw,Cin,Cout).
+
+    'same' follows TensorFlow: total = max((ceil(n/s)-1)*s + k - n, 0), before = total//2,
+    after = total - before (the extra voxel goes AFTER).
+    """
+    k = w.shape[0]
+    xt = _ncdhw(x)
+    if padding == "same":
+        pads = []
+        for n in x.shape[1:4][::-1]:  # F.pad wants last axis first
+            out = -(-n // stride)
+            total = max((out - 1) * stride + k - n, 0)
+            pads += [total // 2, total - total // 2]
+        xt = F.pad(xt, pads)
+    wt = w.permute(4, 3, 0, 1, 2)  # -> (Cout, Cin, kd, kh, kw)
+    return _ndhwc(F.conv3d(xt, wt, b, stride=stride))
+
+
+def instance_norm(x, gamma, beta):
+    """tfa InstanceNormalization (GroupNorm with groups=C): biased variance over D,H,W per (n,c)."""
+    mu = x.mean(dim=(1, 2, 3), keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=(1, 2, 3), keepdim=True)
+    return (x - mu) * torch.rsqrt(var + IN_EPS) * gamma + beta
+
+
+def upsample2(x):
+    """UpSampling3D(size=2): nearest repeat along the three spatial axes."""
+    return x.repeat_interleave(2, 1).repeat_interleave(2, 2).repeat_interleave(2, 3)
+
+
+# --------------------------------------------------------------------------- parameters
+def he_normal(rng, shape):
+    """Keras 'he_normal': truncated normal (|z|<=2), stddev = sqrt(2/fan_in)/0.87962566."""
+    fan_in = int(np.prod(shape[:-1]))
+    std = math.sqrt(2.0 / fan_in) / 0.87962566103423978
+    z = rng.standard_normal(size=shape)
+    bad = np.abs(z) > 2
+    while bad.any():
+        z[bad] = rng.standard_normal(size=int(bad.sum()))
+        bad = np.abs(z) > 2
+    return (z * std).astype(np.float32)
+
+
+def resunet_param_shapes(filters=16, num_layers=4, cin=1):
+    """Ordered {name: shape}.  Naming: '<block>.<layer>.{w,b,gamma,beta}'."""
+    f = [filters * (2 ** i) for i in range(num_layers + 1)]
+    P = OrderedDict()
+
+    def conv(name, k, ci, co):
+        P[name + ".w"] = (k, k, k, ci, co)
+        P[name + ".b"] = (co,)
+
+    def inorm(name, c):
+        P[name + ".gamma"] = (c,)
+        P[name + ".beta"] = (c,)
+
+    def resblock(name, ci, co):
+        inorm(name + ".cb1.in", ci); conv(name + ".cb1.conv", 3, ci, co)
+        inorm(name + ".cb2.in", co); conv(name + ".cb2.conv", 3, co, co)
+        conv(name + ".short.conv", 1, ci, co); inorm(name + ".short.in", co)
+
+    conv("stem.conv0", 3, cin, f[0])
+    inorm("stem.cb.in", f[0]); conv("stem.cb.conv", 3, f[0], f[0])
+    conv("stem.short.conv", 1, cin, f[0]); inorm("stem.short.in", f[0])
+    for e in range(1, num_layers + 1):
+        resblock("enc%d" % e, f[e - 1], f[e])
+    for i in (1, 2):
+        inorm("bridge%d.in" % i, f[-1]); conv("bridge%d.conv" % i, 3, f[-1], f[-1])
+    for d in reversed(range(num_layers)):
+        resblock("dec%d" % d, f[d + 1] + f[d], f[d])
+    conv("head", 1, f[0], 1)
+    return P
+
+
+def disc_param_shapes(filters=64, cin=1):
+    P = OrderedDict()
+    P["d0.conv.w"] = (4, 4, 4, cin, filters); P["d0.conv.b"] = (filters,)
+    P["d0.in.gamma"] = (filters,); P["d0.in.beta"] = (filters,)
+    c = filters
+    for i in (1, 2, 3):
+        P["d%d.conv.w" % i] = (4, 4, 4, c, 2 * c)  # use_bias=False (building_blocks.py:136)
+        P["d%d.in.gamma" % i] = (2 * c,); P["d%d.in.beta" % i] = (2 * c,)
+        c *= 2
+    P["dout.conv.w"] = (3, 3, 3, c, 1); P["dout.conv.b"] = (1,)
+    return P
+
+
+def init_params(shapes, seed, perturb=0.0):
+    """He-normal kernels, zero bias, gamma=1, beta=0 (Keras defaults).  `perturb` adds N(0,perturb)
+    to bias/gamma/beta so parity tests exercise them (all-zero biases hide bugs)."""
+    rng = np.random.default_rng(seed)
+    out = OrderedDict()
+    for name, shp in shapes.items():
+        if name.endswith(".w"):
+            out[name] = he_normal(rng, shp)
+        elif name.endswith(".gamma"):
+            out[name] = (1.0 + perturb * rng.standard_normal(shp)).astype(np.float32)
+        else:
+            out[name] = (perturb * rng.standard_normal(shp)).astype(np.float32)
+    return out
+
+
+def to_torch(params, dtype=torch.float32, requires_grad=True):
+    return OrderedDict((k, torch.tensor(v, dtype=dtype, requires_grad=requires_grad)) for k, v in params.items())
+
+
+# --------------------------------------------------------------------------- ResUNet
+def _norm_act(p, name, x, act=True):
+    y = instance_norm(x, p[name + ".gamma"], p[name + ".beta"])
+    return torch.relu(y) if act else y
+
+
+def _conv_block(p, name, x, stride=1):
+    y = _norm_act(p, name + ".in", x)
+    y = reflect_pad(y)
+    return conv3d(y, p[name + ".conv.w"], p[name + ".conv.b"], stride=stride)
+
+
+def _res_block(p, name, x, stride):
+    res = _conv_block(p, name + ".cb1", x, stride)
+    res = _conv_block(p, name + ".cb2", res, 1)
+    sc = conv3d(x, p[name + ".short.conv.w"], p[name + ".short.conv.b"], stride=stride, padding="same")
+    sc = _norm_act(p, name + ".short.in", sc, act=False)
+    return sc + res
+
+
+def resunet_forward(p, x, num_layers=4, taps=None):
+    """ResUNet(upsample_mode='simple', dropout_type='none', filters=16, num_layers=4, tanh head).
+    `taps`: optional dict that receives named intermediate tensors (for layer-wise parity tests)."""
+    conv = conv3d(reflect_pad(x), p["stem.conv0.w"], p["stem.conv0.b"])
+    conv = _conv_block(p, "stem.cb", conv)
+    sc = conv3d(x, p["stem.short.conv.w"], p["stem.short.conv.b"], padding="same")
+    sc = _norm_act(p, "stem.short.in", sc, act=False)
+    h = conv + sc
+    skips = [h]
+    if taps is not None:
+        taps["stem"] = h
+    for e in range(1, num_layers + 1):
+        h = _res_block(p, "enc%d" % e, h, 2)
+        skips.append(h)
+        if taps is not None:
+            taps["enc%d" % e] = h
+    h = _conv_block(p, "bridge1", h)
+    h = _conv_block(p, "bridge2", h)
+    if taps is not None:
+        taps["bridge"] = h
+    for d in reversed(range(num_layers)):
+        h = torch.cat([upsample2(h), skips[d]], dim=-1)
+        h = _res_block(p, "dec%d" % d, h, 1)
+        if taps is not None:
+            taps["dec%d" % d] = h
+    return torch.tanh(conv3d(h, p["head.w"], p["head.b"], padding="same"))
+
+
+# --------------------------------------------------------------------------- discriminator
+def disc_noise_shapes(n, s, filters=64):
+    """Shapes of the 5 GaussianNoise tensors and 3 SpatialDropout3D masks for an n x s^3 x 1 input."""
+    s1, s2, s3 = s // 2, s // 4, s // 8
+    noise = [(n, s + 2, s + 2, s + 2, 1), (n, s1 + 2, s1 + 2, s1 + 2, filters),
+             (n, s2 + 2, s2 + 2, s2 + 2, 2 * filters), (n, s3, s3, s3, 4 * filters),
+             (n, s3, s3, s3, 8 * filters)]
+    masks = [(n, 1, 1, 1, 2 * filters), (n, 1, 1, 1, 4 * filters), (n, 1, 1, 1, 8 * filters)]
+    return noise, masks
+
+
+def make_disc_rand(rng, n, s, filters=64, noise_std=0.1, rate=0.2, dtype=torch.float32):
+    """Explicit noise / dropout tensors (the reference draws them from TF's stateful RNG; parity
+    tests inject the same tensors into the oracle and the CUDA path)."""
+    ns, ms = disc_noise_shapes(n, s, filters)
+    noise = [torch.tensor(noise_std * rng.standard_normal(sh), dtype=dtype) for sh in ns]
+    masks = [torch.tensor((rng.random(sh) >= rate) / (1.0 - rate), dtype=dtype) for sh in ms]
+    return noise, masks
+
+
+def disc_forward(p, x, noise=None, masks=None, taps=None):
+    """get_discriminator(filters=64, use_dropout=True, dropout_rate=0.2, use_input_noise=True,
+    use_layer_noise=True, noise_std=0.1) in training mode when noise/masks are given; inference
+    mode (no noise, no dropout) when they are None."""
+    def nz(i, t):
+        return t if noise is None else t + noise[i]
+
+    def dr(i, t):
+        return t if masks is None else t * masks[i]
+
+    h = nz(0, reflect_pad(x))                                         # discriminator.py:50-52
+    h = conv3d(h, p["d0.conv.w"], p["d0.conv.b"], stride=2)           # :63-69
+    h = F.leaky_relu(instance_norm(h, p["d0.in.gamma"], p["d0.in.beta"]), 0.2)   # :70-72
+    if taps is not None:
+        taps["d0"] = h
+    for i in (1, 2):                                                  # :75-88 -> downsample()
+        h = nz(i, reflect_pad(h))
+        h = conv3d(h, p["d%d.conv.w" % i], None, stride=2)
+        h = F.leaky_relu(instance_norm(h, p["d%d.in.gamma" % i], p["d%d.in.beta" % i]), 0.2)
+        h = dr(i - 1, h)
+        if taps is not None:
+            taps["d%d" % i] = h
+    h = nz(3, h)                                                      # :90-103, padding='same'
+    h = conv3d(h, p["d3.conv.w"], None, stride=1, padding="same")
+    h = F.leaky_relu(instance_norm(h, p["d3.in.gamma"], p["d3.in.beta"]), 0.2)
+    h = dr(2, h)
+    if taps is not None:
+        taps["d3"] = h
+    h = nz(4, h)                                                      # :105-114
+    return conv3d(h, p["dout.conv.w"], p["dout.conv.b"], padding="same")
