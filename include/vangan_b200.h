@@ -1,0 +1,162 @@
+/* vangan_b200 — C ABI of the B200-native VAN-GAN volumetric hot path.
+ *
+ * Every entry point replaces a group of TensorFlow/Keras/tensorflow_addons op kernels that the
+ * reference (psweens/VAN-GAN) reaches from VanGan.train_step (vangan.py:380-440) or from
+ * GanMonitor.stitch_subvolumes (custom_callback.py:47-223).  The reference has no FFI of its own
+ * (it is pure Python over stock TF ops); these are the symbols a TF custom-op shim
+ * (OpKernel::Compute forwarding the op context's stream) or the ctypes binding in
+ * van-gan_b200/_lib.py binds.  See INTEGRATION.md.
+ *
+ * Conventions: plain pointers to DEVICE memory, sizes as ints / size_t, `stream` is a
+ * cudaStream_t passed as void*.  The caller owns every buffer (inputs, outputs, workspaces); the
+ * library allocates nothing, keeps no global state and never synchronises the host.  Return value:
+ * 0 = VG_OK, negative = error (no exceptions, no exit).  Activations are NDHWC (Keras
+ * channels_last); Conv3D kernels are (kd,kh,kw,Cin,Cout) fp32 exactly as Keras stores them.
+ */
+#ifndef VANGAN_B200_H
+#define VANGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { VG_OK = 0, VG_ERR_INVALID = -1, VG_ERR_UNSUPPORTED = -2, VG_ERR_WORKSPACE = -3, VG_ERR_CUDA = -4 };
+enum { VG_F32 = 0, VG_BF16 = 1 };
+enum { VG_ACT_NONE = 0, VG_ACT_RELU = 1, VG_ACT_LEAKY = 2, VG_ACT_TANH = 3 };
+enum { VG_PAD_ZERO = 0, VG_PAD_REFLECT = 1 };
+
+int vg_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Conv3D (valid convolution over an explicitly padded input; the padding itself — ReflectionPadding3D
+ * or TF 'same' zeros — is written by vg_instnorm_apply / vg_pad_noise, so it never costs a pass).
+ * Replaces keras.layers.Conv3D forward / Conv3DBackpropInputV2 / Conv3DBackpropFilterV2 at
+ * resunet_model.py:64-65,89-90,96,127,133-134,245; discriminator.py:63-69,108-114;
+ * building_blocks.py:182-189.
+ * x: [N, ID, IH, IW, Cin]   y: [N, OD, OH, OW, Cout],  O = (I - K)/stride + 1.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int N;
+    int ID, IH, IW; /* input spatial dims, padding included */
+    int Cin, Cout;
+    int K;          /* cubic kernel: 1, 3 or 4 */
+    int stride;     /* 1 or 2 */
+    int x_dtype;    /* VG_BF16, or VG_F32 when Cin == 1 */
+    int y_dtype;    /* VG_BF16, or VG_F32 when Cout == 1 */
+    int act;        /* VG_ACT_NONE or VG_ACT_TANH (forward epilogue) */
+} vg_conv3d_desc;
+
+/* bytes of the bf16 operand copies of one layer's weights: forward pack and dgrad pack */
+size_t vg_conv3d_packed_bytes(const vg_conv3d_desc* d, int for_dgrad);
+/* w_keras fp32 (K,K,K,Cin,Cout) -> packed bf16 operand layouts (call after every optimizer step) */
+int vg_conv3d_pack_weights(const vg_conv3d_desc* d, const float* w_keras, void* w_fwd, void* w_dgrad, void* stream);
+/* y = act(conv(x, w) + bias).  `w_fwd` is the packed buffer, or the fp32 Keras kernel when Cin == 1 */
+int vg_conv3d_fwd(const vg_conv3d_desc* d, const void* x, const void* w_fwd, const float* bias, void* y, void* stream);
+/* dx[N,ID,IH,IW,Cin] = conv_transpose(dy, w)  (gradient w.r.t. the PADDED input; fully overwritten).
+ * `w_dgrad` is the packed buffer, or the fp32 Keras kernel when Cout == 1.  dx dtype = x_dtype. */
+int vg_conv3d_dgrad(const vg_conv3d_desc* d, const void* dy, const void* w_dgrad, void* dx, void* stream);
+/* dw (fp32, Keras layout) += x^T * dy;  dbias (optional, fp32[Cout]) += sum dy */
+int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, float* dw, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * InstanceNormalization + activation + residual + dropout + noise + padding (tfa InstanceNormalization,
+ * Activation/LeakyReLU, Add, SpatialDropout3D, GaussianNoise, ReflectionPadding3D):
+ * resunet_model.py:23-39,96-100,133-143; discriminator.py:50-52,70-72,105-106;
+ * building_blocks.py:15-39,166-195.
+ *   y[pad(p)] = drop[n,c] * act(gamma*(x-mean)*rstd + beta) + residual  (+ noise)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int N, D, H, W, C; /* unpadded input dims */
+    int dtype;         /* storage type of x / residual / y / dy / dx */
+    int act;           /* VG_ACT_NONE / RELU / LEAKY */
+    float slope;       /* LeakyReLU slope */
+    int pad_lo, pad_hi, pad_mode; /* padding written around the output (0/0 = none) */
+    float noise_std;   /* >0 and noise==NULL: Philox noise generated in-kernel from `seed` */
+    unsigned long long seed;
+} vg_instnorm_desc;
+
+size_t vg_instnorm_workspace_bytes(int N, int D, int H, int W, int C);
+int vg_instnorm_stats(const void* x, int dtype, int N, int D, int H, int W, int C, float* mean, float* rstd, void* ws,
+                      size_t ws_bytes, void* stream);
+int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* residual, void* y, const float* mean,
+                      const float* rstd, const float* gamma, const float* beta, const float* drop, const float* noise,
+                      void* stream);
+int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, const float* drop, void* dx, int accumulate_dx, void* dres,
+                    float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout helpers around the convolutions: UpSampling3D(2)+concatenate (resunet_model.py:176,181),
+ * input ReflectionPadding3D+GaussianNoise of the discriminator (discriminator.py:50-52), gradient
+ * accumulation, tanh backward of the generator head (resunet_model.py:245).
+ * ------------------------------------------------------------------------------------------- */
+/* out[N,2D,2H,2W,C0+C1] = concat(upsample2(lo[N,D,H,W,C0]), skip[N,2D,2H,2W,C1]) (bf16) */
+int vg_upsample_concat(const void* lo, const void* skip, void* out, int N, int D, int H, int W, int C0, int C1, void* stream);
+/* dlo = 2x2x2 block-sum of dcat[..., :C0]; dskip (+)= dcat[..., C0:] */
+int vg_upsample_concat_bwd(const void* dcat, void* dlo, void* dskip, int accumulate_skip, int N, int D, int H, int W, int C0,
+                           int C1, void* stream);
+/* y[N,D+2,H+2,W+2] = reflect_pad(x) + noise  (fp32, one channel).  noise may be NULL (then noise_std/seed) */
+int vg_pad_noise(const float* x, float* y, int N, int D, int H, int W, const float* noise, float noise_std,
+                 unsigned long long seed, void* stream);
+/* dx[N,D,H,W] (+)= fold of dy[N,D+2,H+2,W+2] through the reflect padding */
+int vg_pad_fold(const float* dy, float* dx, int N, int D, int H, int W, int accumulate, void* stream);
+/* a += b  (dtype VG_BF16 or VG_F32) */
+int vg_accumulate(void* a, const void* b, size_t n, int dtype, void* stream);
+/* out = dy * (1 - y*y) */
+int vg_tanh_bwd(const float* dy, const float* y, float* out, size_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * clDice soft skeleton (clDice_func.py:8-80).  x: [N,D,H,W] fp32.
+ * E: [(iters+2)][N*D*H*W] erosion pyramid, S: [(iters+1)][N*D*H*W]; the skeleton is S[iters].
+ * ------------------------------------------------------------------------------------------- */
+int vg_soft_skel_fwd(const float* x, float* E, float* S, int N, int D, int H, int W, int iters, void* stream);
+size_t vg_soft_skel_bwd_workspace_bytes(int N, int D, int H, int W);
+int vg_soft_skel_bwd(const float* E, const float* S, const float* gskel, float* dx, void* workspace, size_t workspace_bytes,
+                     int N, int D, int H, int W, int iters, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loss arithmetic (loss_functions.py:7-22,56-68,86-117,163-226,255-322; clDice_func.py:83-149;
+ * utils.py:27-48).  Reductions accumulate (+=) into caller-zeroed double accumulators.
+ * ------------------------------------------------------------------------------------------- */
+int vg_minmax(const float* x, int N, size_t V, float* mm, void* enc_ws, void* stream);
+int vg_minmax_normalize(const float* x, const float* mm, float* out, int N, size_t V, void* stream);
+int vg_minmax_normalize_bwd(const float* x, const float* nrm, const float* mm, const float* g, float* dx, int N, size_t V,
+                            void* acc_ws, int accumulate, void* stream);
+int vg_sqdiff_sum(const float* a, const float* b, float target, size_t n, double* acc, void* stream);
+int vg_lincomb(float* out, size_t n, int accumulate, float c0, const float* x1, float c1, const float* x2, float c2,
+               const float* x3, float c3, void* stream);
+int vg_bce_sum(const float* y_true, const float* y_pred, size_t n, double* acc, void* stream);
+int vg_bce_bwd(const float* y_true, const float* y_pred, float coef, float* g, size_t n, int accumulate, void* stream);
+int vg_cldice_sums(const float* y_true, const float* y_pred, const float* skel_true, const float* skel_pred, size_t n,
+                   double* acc7, void* stream);
+int vg_ssim_fwd(const float* t, const float* p, int N, int D, int H, int W, double* acc, float* mA, float* mB, float* mC,
+                void* stream);
+int vg_ssim_bwd(const float* t, const float* p, const float* mA, const float* mB, const float* mC, int N, int D, int H, int W,
+                float coef, float* gp, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Keras OptimizerV2 Adam with per-variable clipnorm (vangan.py:220-235, applied by minimize at
+ * :426-438).  One flat fp32 buffer per network; seg_offsets[nseg+1] (device) delimits the variables,
+ * total = seg_offsets[nseg]; norm_ws: nseg doubles of scratch.
+ * ------------------------------------------------------------------------------------------- */
+int vg_clip_adam_step(float* w, const float* g, float* m, float* v, const long long* seg_offsets, int nseg, long long total,
+                      float lr_t, float beta1, float beta2, float eps, float clipnorm, double* norm_ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sliding-window stitching (custom_callback.py:123,165-166,177-183,192,202).
+ * pred/cnt: [H,W,D] fp32 volumes; win: [B,kH,kW,kD] generator outputs; starts: [B][3] window origins.
+ * ------------------------------------------------------------------------------------------- */
+int vg_stitch_accumulate(float* pred, float* cnt, int H, int W, int D, const float* win, const int* starts, int B, int kH,
+                         int kW, int kD, int pH, int pW, int pD, void* stream);
+/* out[oh,ow,od] = 255 * minmax_norm( (pred/cnt)[crop] ): two calls — divide+minmax, then scale */
+int vg_stitch_finalize(const float* pred, const float* cnt, int H, int W, int D, int x0, int y0, int z0, int oH, int oW, int oD,
+                       float* out, float* mm, void* enc_ws, void* stream);
+int vg_stitch_scale(float* out, size_t n, const float* mm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VANGAN_B200_H */

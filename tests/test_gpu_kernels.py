@@ -1,0 +1,263 @@
+"""GPU parity tests: every C-ABI kernel family against the CPU oracle on seeded inputs.
+
+Tolerances: fp32 elementwise / stencil / loss kernels 1e-5 relative (soft_skel forward: bit-exact);
+bf16 tensor-core convolutions: relative L2 <= 2e-2 against the fp32 oracle (in practice ~3e-3, the
+bf16 rounding of the operands)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a = a.double().flatten().cpu()
+    b = b.double().flatten().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _bf(t):  # round through bf16 like the device path does for operands
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+# ----------------------------------------------------------------------------- soft skeleton
+@pytest.mark.parametrize("shape,iters", [((1, 24, 20, 28), 6), ((2, 33, 17, 40), 3), ((1, 64, 64, 64), 15), ((1, 8, 8, 8), 0)])
+def test_soft_skel_forward_bit_exact(cuda, shape, iters):
+    from oracle import losses as OL
+    from van_gan_b200 import clDice_func as K
+    rng = np.random.default_rng(7)
+    x = torch.tensor(rng.random(shape + (1,)), dtype=torch.float32)
+    ref = OL.soft_skel(x, iters)
+    out = K.soft_skel(x.cuda(), iters).cpu()
+    assert torch.equal(out, ref)
+    assert torch.equal(K.soft_erode(x.cuda()).cpu(), OL.soft_erode(x))
+
+
+@pytest.mark.parametrize("shape,iters", [((1, 20, 24, 36), 5), ((2, 16, 16, 16), 2), ((1, 40, 40, 40), 15)])
+def test_soft_skel_backward(cuda, shape, iters):
+    from oracle import losses as OL
+    from van_gan_b200 import clDice_func as K
+    rng = np.random.default_rng(8)
+    x = torch.tensor(rng.random(shape + (1,)), dtype=torch.float32, requires_grad=True)
+    g = torch.tensor(rng.standard_normal(shape + (1,)), dtype=torch.float32)
+    OL.soft_skel(x, iters).backward(g)
+    skel, bwd = K.soft_skel_with_grad(x.detach().cuda(), iters)
+    dx = bwd(g.cuda()).cpu()
+    assert rel_l2(dx, x.grad) < 1e-5
+    assert float((dx - x.grad).abs().max()) < 1e-5 * float(x.grad.abs().max()) + 1e-6
+
+
+# ----------------------------------------------------------------------------- losses
+class _Cfg:
+    def __init__(self, G=2, nd=1):
+        self.global_batch_size, self.n_devices = G, nd
+        self.lambda_cycle, self.lambda_reconstruction, self.lambda_topology = 10.0, 5.0, 5.0
+        self.loss_ctx = None
+
+
+@pytest.mark.parametrize("S,N", [(24, 2), (32, 1)])
+def test_cycle_losses_forward_backward(cuda, S, N):
+    from oracle import losses as OL
+    from van_gan_b200 import engine as E, loss_functions as LF
+    rng = np.random.default_rng(11)
+    real = torch.tensor(rng.random((N, S, S, S, 1)) * 2 - 1, dtype=torch.float32)
+    cyc0 = torch.tensor(np.tanh(rng.standard_normal((N, S, S, S, 1))), dtype=torch.float32)
+    cfg = _Cfg(G=2 * N, nd=2)
+    ocfg = OL.make_cfg(2 * N, 2)
+    cases = {
+        "bce": (lambda c: OL.cycle_loss(ocfg, real, c, typ="bce"), lambda r, c: LF.cycle_loss(cfg, r, c, typ="bce")),
+        "mse": (lambda c: OL.cycle_loss(ocfg, real, c, typ="mse"), lambda r, c: LF.cycle_loss(cfg, r, c, typ="mse")),
+        "ssim": (lambda c: OL.cycle_reconstruction(ocfg, real, c), lambda r, c: LF.cycle_reconstruction(cfg, r, c)),
+        "seg": (lambda c: OL.cycle_seg_loss(ocfg, real, c, iters=5), lambda r, c: LF.cycle_seg_loss(cfg, r, c, iters=5)),
+    }
+    for name, (ofn, kfn) in cases.items():
+        c = cyc0.clone().requires_grad_(True)
+        lo = ofn(c)
+        lo.backward()
+        cfg.loss_ctx = LF.LossContext()
+        rv, cv = E.Var(real.cuda()), E.Var(cyc0.cuda())
+        s = kfn(rv, cv)
+        assert abs(float(s) - float(lo)) <= 1e-5 * abs(float(lo)) + 1e-7, name
+        seeds = s.seeds()
+        g = sum(gg for v, gg in seeds if v is cv).cpu()
+        assert rel_l2(g, c.grad) < 2e-5, (name, rel_l2(g, c.grad))
+
+
+def test_lsgan_losses(cuda):
+    from oracle import losses as OL
+    from van_gan_b200 import engine as E, loss_functions as LF
+    rng = np.random.default_rng(12)
+    a = torch.tensor(rng.standard_normal((2, 4, 4, 4, 1)), dtype=torch.float32)
+    b = torch.tensor(rng.standard_normal((2, 4, 4, 4, 1)), dtype=torch.float32)
+    cfg, ocfg = _Cfg(G=4), OL.make_cfg(4)
+    cfg.loss_ctx = LF.LossContext()
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    lo = OL.discriminator_loss_fn(ocfg, ar, br) + OL.generator_loss_fn(ocfg, br)
+    lo.backward()
+    av, bv = E.Var(a.cuda()), E.Var(b.cuda())
+    s = LF.discriminator_loss_fn(cfg, av, bv) + LF.generator_loss_fn(cfg, bv)
+    assert abs(float(s) - float(lo)) < 1e-6 * abs(float(lo))
+    seeds = s.seeds()
+    ga = sum(g for v, g in seeds if v is av).cpu()
+    gb = sum(g for v, g in seeds if v is bv).cpu()
+    assert rel_l2(ga, ar.grad) < 1e-6 and rel_l2(gb, br.grad) < 1e-6
+
+
+# ----------------------------------------------------------------------------- instance norm
+@pytest.mark.parametrize("C,S,act,pad,dt", [(16, 12, 1, (1, 1, 1), torch.float32), (48, 10, 0, (0, 0, 0), torch.float32),
+                                            (64, 8, 2, (1, 2, 0), torch.float32), (32, 9, 2, (1, 1, 1), torch.bfloat16),
+                                            (512, 4, 2, (1, 1, 0), torch.float32)])
+def test_instnorm_forward_backward(cuda, C, S, act, pad, dt):
+    import torch.nn.functional as F
+    from oracle import nets as ON
+    from van_gan_b200 import engine as E
+    from van_gan_b200.resunet_model import resunet_param_shapes  # noqa: F401
+    rng = np.random.default_rng(13)
+    N = 2
+    x = torch.tensor(rng.standard_normal((N, S, S + 1, S + 2, C)) * 1.5 + 0.7, dtype=torch.float32)
+    res = torch.tensor(rng.standard_normal(x.shape), dtype=torch.float32)
+    gamma = torch.tensor(1 + 0.2 * rng.standard_normal(C), dtype=torch.float32)
+    beta = torch.tensor(0.2 * rng.standard_normal(C), dtype=torch.float32)
+    drop = torch.tensor((rng.random((N, 1, 1, 1, C)) > 0.2) / 0.8, dtype=torch.float32)
+    if dt == torch.bfloat16:
+        x, res = _bf(x), _bf(res)
+    pshape = (N, S + pad[0] + pad[1], S + 1 + pad[0] + pad[1], S + 2 + pad[0] + pad[1], C)
+    noise_shape = pshape if pad[2] == 1 else x.shape
+    noise = torch.tensor(0.1 * rng.standard_normal(noise_shape), dtype=torch.float32)
+    gout = torch.tensor(rng.standard_normal(pshape), dtype=torch.float32)
+    if dt == torch.bfloat16:
+        gout = _bf(gout)
+
+    xr, rr = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = ON.instance_norm(xr, gr, br)
+    y = torch.relu(y) if act == 1 else (F.leaky_relu(y, 0.2) if act == 2 else y)
+    y = y * drop + rr
+    if pad[2] == 1 and pad[0]:
+        y = ON.reflect_pad(y) + noise
+    else:
+        y = y + noise
+        if pad[0] or pad[1]:
+            y = F.pad(y.permute(0, 4, 1, 2, 3), (pad[0], pad[1]) * 3).permute(0, 2, 3, 4, 1)
+    y.backward(gout)
+
+    class Net:
+        pass
+    from collections import OrderedDict
+    net = E.Network("t", OrderedDict([("n.gamma", (C,)), ("n.beta", (C,))]))
+    net.load({"n.gamma": gamma.numpy(), "n.beta": beta.numpy()})
+    layer = E.InstanceNorm(net, "n", C)
+    tape = E.Tape()
+    xv, rv = E.Var(x.to(dt).cuda()), E.Var(res.to(dt).cuda())
+    out = layer(tape, xv, act=act, residual=rv, pad=pad, drop=drop.reshape(-1).cuda(), noise=noise.cuda())
+    tol = 1e-5 if dt == torch.float32 else 1.5e-2
+    assert rel_l2(out.data.float(), y.detach()) < tol
+    tape.backward([(out, gout.to(dt).cuda())], net.trainable_variables, wrt_vars=[xv, rv])
+    tolb = 2e-5 if dt == torch.float32 else 2e-2
+    assert rel_l2(xv.grad.float(), xr.grad) < tolb
+    assert rel_l2(rv.grad.float(), rr.grad) < tolb
+    assert rel_l2(net.params["n.gamma"].grad, gr.grad) < tolb
+    assert rel_l2(net.params["n.beta"].grad, br.grad) < tolb
+
+
+# ----------------------------------------------------------------------------- convolutions
+CONV_CASES = [
+    # (Cin, Cout, K, stride, spatial(in, padded), N)
+    (16, 16, 3, 1, (10, 11, 14), 2), (48, 16, 3, 1, (9, 10, 18), 1), (16, 32, 3, 2, (13, 11, 19), 2),
+    (32, 32, 3, 1, (6, 6, 10), 1), (96, 32, 3, 1, (8, 8, 10), 1), (64, 128, 3, 2, (9, 9, 9), 1),
+    (256, 256, 3, 1, (4, 4, 4), 2), (384, 128, 3, 1, (6, 6, 6), 1), (192, 64, 3, 1, (7, 6, 10), 1),
+    (16, 32, 1, 2, (12, 12, 16), 1), (48, 16, 1, 1, (8, 8, 8), 2), (128, 256, 1, 2, (4, 4, 4), 1),
+    (64, 128, 4, 2, (10, 10, 18), 1), (128, 256, 4, 2, (10, 10, 10), 1), (256, 512, 4, 1, (7, 7, 7), 1),
+    (1, 16, 3, 1, (10, 10, 12), 2), (1, 64, 4, 2, (18, 18, 18), 1), (1, 16, 1, 1, (8, 8, 8), 1),
+    (512, 1, 3, 1, (6, 6, 6), 2), (16, 1, 1, 1, (8, 8, 9), 2),
+]
+
+
+@pytest.mark.parametrize("Cin,Cout,K,stride,sp,N", CONV_CASES)
+def test_conv3d_fwd_dgrad_wgrad(cuda, Cin, Cout, K, stride, sp, N):
+    from collections import OrderedDict
+    from oracle import nets as ON
+    from van_gan_b200 import engine as E
+    from van_gan_b200._lib import ACT_NONE, ACT_TANH
+    rng = np.random.default_rng(Cin * 1000 + Cout + K)
+    act = ACT_TANH if (Cout == 1 and K == 1) else ACT_NONE
+    x = torch.tensor(rng.standard_normal((N,) + sp + (Cin,)), dtype=torch.float32)
+    w = torch.tensor(ON.he_normal(rng, (K, K, K, Cin, Cout)), dtype=torch.float32)
+    b = torch.tensor(0.1 * rng.standard_normal(Cout), dtype=torch.float32)
+    xd = x if Cin == 1 else _bf(x)
+    wd = w if (Cin == 1 or Cout == 1) else _bf(w)
+    xr, wr, br = xd.clone().requires_grad_(True), wd.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = ON.conv3d(xr, wr, br, stride=stride)
+    if act == ACT_TANH:
+        y = torch.tanh(y)
+    gy = torch.tensor(rng.standard_normal(y.shape), dtype=torch.float32)
+    if Cout != 1:
+        gy = _bf(gy)
+    y.backward(gy)
+
+    net = E.Network("t", OrderedDict([("c.w", tuple(w.shape)), ("c.b", (Cout,))]))
+    net.load({"c.w": w.numpy(), "c.b": b.numpy()})
+    layer = E.Conv3D(net, "c", K, stride, Cin, Cout, act=act)
+    net.repack()
+    tape = E.Tape()
+    xv = E.Var(x.cuda() if Cin == 1 else x.to(torch.bfloat16).cuda())
+    out = layer(tape, xv)
+    assert out.shape == tuple(y.shape)
+    assert rel_l2(out.data.float(), y.detach()) < 1e-2
+    tape.backward([(out, gy.cuda() if Cout == 1 else gy.to(torch.bfloat16).cuda())], net.trainable_variables, wrt_vars=[xv])
+    assert rel_l2(xv.grad.float(), xr.grad) < 1e-2, "dgrad"
+    assert rel_l2(net.params["c.w"].grad, wr.grad) < 1e-2, "wgrad"
+    assert rel_l2(net.params["c.b"].grad, br.grad) < 1e-2, "bias grad"
+
+
+def test_upsample_concat_and_pad(cuda):
+    from oracle import nets as ON
+    from van_gan_b200 import engine as E
+    rng = np.random.default_rng(3)
+    lo = _bf(torch.tensor(rng.standard_normal((2, 3, 4, 5, 32)), dtype=torch.float32))
+    sk = _bf(torch.tensor(rng.standard_normal((2, 6, 8, 10, 16)), dtype=torch.float32))
+    lr, sr = lo.clone().requires_grad_(True), sk.clone().requires_grad_(True)
+    y = torch.cat([ON.upsample2(lr), sr], dim=-1)
+    g = _bf(torch.tensor(rng.standard_normal(y.shape), dtype=torch.float32))
+    y.backward(g)
+    tape = E.Tape()
+    lv, sv = E.Var(lo.to(torch.bfloat16).cuda()), E.Var(sk.to(torch.bfloat16).cuda())
+    out = E.upsample_concat(tape, lv, sv)
+    assert torch.equal(out.data.float().cpu(), y.detach())
+    tape.backward([(out, g.to(torch.bfloat16).cuda())], [], wrt_vars=[lv, sv])
+    assert rel_l2(lv.grad.float(), lr.grad) < 1e-2
+    assert torch.equal(sv.grad.float().cpu(), sr.grad)
+
+    x = torch.tensor(rng.standard_normal((2, 5, 6, 7, 1)), dtype=torch.float32)
+    nz = torch.tensor(rng.standard_normal((2, 7, 8, 9, 1)), dtype=torch.float32)
+    xr = x.clone().requires_grad_(True)
+    yp = ON.reflect_pad(xr) + nz
+    gp = torch.tensor(rng.standard_normal(yp.shape), dtype=torch.float32)
+    yp.backward(gp)
+    tape = E.Tape()
+    xv = E.Var(x.cuda())
+    o = E.pad_noise(tape, xv, noise=nz.cuda())
+    assert torch.allclose(o.data.cpu(), yp.detach(), atol=1e-6)
+    tape.backward([(o, gp.cuda())], [], wrt_vars=[xv])
+    assert torch.allclose(xv.grad.cpu(), xr.grad, atol=1e-5)
+
+
+def test_clip_adam(cuda):
+    from collections import OrderedDict
+    from oracle import step as OS
+    from van_gan_b200 import engine as E
+    rng = np.random.default_rng(5)
+    shapes = OrderedDict([("a.w", (3, 3, 3, 4, 8)), ("a.b", (8,)), ("b.gamma", (16,)), ("c.w", (1, 1, 1, 64, 64))])
+    net = E.Network("t", shapes)
+    init = {k: rng.standard_normal(s).astype(np.float32) for k, s in shapes.items()}
+    net.load(init)
+    P = OrderedDict((k, torch.tensor(v)) for k, v in init.items())
+    opt = OS.Adam(list(shapes))
+    for it in range(3):
+        g = {k: (rng.standard_normal(s) * (40.0 if k == "c.w" else 1.0)).astype(np.float32) for k, s in shapes.items()}
+        for k in shapes:
+            net.params[k].grad.copy_(torch.tensor(g[k]).cuda())
+        net.adam_step()
+        opt.apply(P, {k: torch.tensor(v) for k, v in g.items()})
+        for k in shapes:
+            assert torch.allclose(net.params[k].w.cpu(), P[k], rtol=1e-5, atol=1e-6), (it, k)

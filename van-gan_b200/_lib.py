@@ -1,0 +1,124 @@
+"""ctypes binding of libvangan_b200.so (the C ABI declared in include/vangan_b200.h).
+
+torch is used only for device memory (`tensor.data_ptr()`) and the current CUDA stream.  There is
+NO fallback: if the shared library is missing, fails to load, or a call returns an error code, an
+exception is raised.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvangan_b200.so")
+
+VG_F32, VG_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
+PAD_ZERO, PAD_REFLECT = 0, 1
+_ERR = {-1: "invalid argument", -2: "unsupported shape", -3: "workspace too small", -4: "CUDA error"}
+
+
+class VgError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("N", C.c_int), ("ID", C.c_int), ("IH", C.c_int), ("IW", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
+                ("K", C.c_int), ("stride", C.c_int), ("x_dtype", C.c_int), ("y_dtype", C.c_int), ("act", C.c_int)]
+
+
+class InDesc(C.Structure):
+    _fields_ = [("N", C.c_int), ("D", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("dtype", C.c_int),
+                ("act", C.c_int), ("slope", C.c_float), ("pad_lo", C.c_int), ("pad_hi", C.c_int), ("pad_mode", C.c_int),
+                ("noise_std", C.c_float), ("seed", C.c_ulonglong)]
+
+
+_P, _I, _F, _Z, _LL, _ULL = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong, C.c_ulonglong
+_CD, _ID = C.POINTER(ConvDesc), C.POINTER(InDesc)
+
+# name -> (restype, argtypes); must list every symbol of include/vangan_b200.h (tests/test_abi.py checks)
+SIGNATURES = {
+    "vg_abi_version": (_I, []),
+    "vg_conv3d_packed_bytes": (_Z, [_CD, _I]),
+    "vg_conv3d_pack_weights": (_I, [_CD, _P, _P, _P, _P]),
+    "vg_conv3d_fwd": (_I, [_CD, _P, _P, _P, _P, _P]),
+    "vg_conv3d_dgrad": (_I, [_CD, _P, _P, _P, _P]),
+    "vg_conv3d_wgrad": (_I, [_CD, _P, _P, _P, _P, _P]),
+    "vg_instnorm_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "vg_instnorm_stats": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "vg_instnorm_apply": (_I, [_ID, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vg_instnorm_bwd": (_I, [_ID, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    "vg_upsample_concat": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "vg_upsample_concat_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vg_pad_noise": (_I, [_P, _P, _I, _I, _I, _I, _P, _F, _ULL, _P]),
+    "vg_pad_fold": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "vg_accumulate": (_I, [_P, _P, _Z, _I, _P]),
+    "vg_tanh_bwd": (_I, [_P, _P, _P, _Z, _P]),
+    "vg_soft_skel_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vg_soft_skel_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "vg_soft_skel_bwd": (_I, [_P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _P]),
+    "vg_minmax": (_I, [_P, _I, _Z, _P, _P, _P]),
+    "vg_minmax_normalize": (_I, [_P, _P, _P, _I, _Z, _P]),
+    "vg_minmax_normalize_bwd": (_I, [_P, _P, _P, _P, _P, _I, _Z, _P, _I, _P]),
+    "vg_sqdiff_sum": (_I, [_P, _P, _F, _Z, _P, _P]),
+    "vg_lincomb": (_I, [_P, _Z, _I, _F, _P, _F, _P, _F, _P, _F, _P]),
+    "vg_bce_sum": (_I, [_P, _P, _Z, _P, _P]),
+    "vg_bce_bwd": (_I, [_P, _P, _F, _P, _Z, _I, _P]),
+    "vg_cldice_sums": (_I, [_P, _P, _P, _P, _Z, _P, _P]),
+    "vg_ssim_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "vg_ssim_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P]),
+    "vg_clip_adam_step": (_I, [_P, _P, _P, _P, _P, _I, _LL, _F, _F, _F, _F, _F, _P, _P]),
+    "vg_stitch_accumulate": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vg_stitch_finalize": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "vg_stitch_scale": (_I, [_P, _Z, _P, _P]),
+}
+
+_lib = None
+LAUNCHES = 0  # number of ABI compute calls issued (bench.py reports kernel launches from this)
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it is missing — there is no CPU fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VgError("libvangan_b200.so not built: run `python van-gan_b200/build.py` (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    assert t.is_cuda and t.is_contiguous(), "ABI buffers must be contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke an int-returning ABI function; tensors are converted to raw device pointers and the
+    current torch stream is appended as the last argument."""
+    global LAUNCHES
+    conv = [(_ptr(a) if (a is None or torch.is_tensor(a)) else a) for a in args]
+    rc = getattr(lib(), name)(*conv, _stream())
+    LAUNCHES += 1
+    if rc != 0:
+        raise VgError("%s failed: %s (%d)" % (name, _ERR.get(rc, "?"), rc))
+
+
+def dtype_code(t):
+    if t.dtype == torch.bfloat16:
+        return VG_BF16
+    if t.dtype == torch.float32:
+        return VG_F32
+    raise VgError("unsupported dtype %s" % t.dtype)

@@ -1,0 +1,137 @@
+// Shared device helpers for the VAN-GAN B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vangan_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+#define VG_CHECK_LAUNCH()                                   \
+    do {                                                    \
+        cudaError_t e__ = cudaGetLastError();               \
+        if (e__ != cudaSuccess) return VG_ERR_CUDA;         \
+    } while (0)
+
+#define VG_REQUIRE(cond)                      \
+    do {                                      \
+        if (!(cond)) return VG_ERR_INVALID;   \
+    } while (0)
+
+static inline int vg_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// grid sizing: a multiple of the SM count (148 on B200), capped by the work available
+static inline int vg_grid_for(long long work_items, int per_block, int waves = 8) {
+    long long blocks = (work_items + per_block - 1) / per_block;
+    long long cap = 148LL * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide sum of a double; result valid in thread 0.  `sh` must hold >= 32 doubles.
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+    v = warp_sum_d(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        v = lane < nw ? sh[lane] : 0.0;
+        v = warp_sum_d(v);
+    }
+    return v;
+}
+
+// reflect index for pad-1 REFLECT padding: -1 -> 1, n -> n-2
+__device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+// 8 x bf16 <-> 8 x float through one 128-bit access
+struct __align__(16) bf16x8 {
+    __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float2 t = __bfloat1622float2(p.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+    bf16x8 p;
+#pragma unroll
+    for (int i = 0; i < 4; i++) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return p;
+}
+
+// generic 8-wide load/store on either float or bf16 storage
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float* f);
+template <>
+__device__ __forceinline__ void load8<bf16>(const bf16* p, float* f) {
+    bf16x8 v = *reinterpret_cast<const bf16x8*>(p);
+    unpack8(v, f);
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float* f) {
+    float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float* f);
+template <>
+__device__ __forceinline__ void store8<bf16>(bf16* p, const float* f) {
+    *reinterpret_cast<bf16x8*>(p) = pack8(f);
+}
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float* f) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// Philox-4x32-10 counter RNG (one call -> 4 uniform u32); key = (seed_lo, seed_hi)
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+// two standard normals from two u32 (Box-Muller)
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+    float u1 = (a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+    float u2 = b * 2.3283064365386963e-10f;
+    float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(6.283185307179586f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+}

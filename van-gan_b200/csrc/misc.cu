@@ -1,0 +1,343 @@
+// Layout helpers, optimizer and sliding-window stitching kernels (all HBM-bound streaming passes).
+//
+// Replaces: UpSampling3D(2)+concatenate (resunet_model.py:176,181) and its gradient; the
+// discriminator's input ReflectionPadding3D+GaussianNoise (discriminator.py:50-52); gradient
+// accumulation done by tf.GradientTape; Keras OptimizerV2 Adam with clipnorm (vangan.py:220-235,
+// 426-438); the numpy accumulate / divide / min-max of GanMonitor.stitch_subvolumes
+// (custom_callback.py:165-166,177-183,192,202).
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+__global__ void __launch_bounds__(NT) upsample_concat_kernel(const bf16* __restrict__ lo, const bf16* __restrict__ skip,
+                                                             bf16* __restrict__ out, int N, int D, int H, int W, int C0, int C1) {
+    const int C = C0 + C1, cg = C / 8, cg0 = C0 / 8;
+    const int D2 = 2 * D, H2 = 2 * H, W2 = 2 * W;
+    size_t total = (size_t)N * D2 * H2 * W2 * cg;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        int c8 = (int)(i % cg);
+        size_t v = i / cg;
+        int w = (int)(v % W2), h = (int)((v / W2) % H2), d = (int)((v / ((size_t)W2 * H2)) % D2);
+        int n = (int)(v / ((size_t)W2 * H2 * D2));
+        bf16x8 val;
+        if (c8 < cg0)
+            val = *reinterpret_cast<const bf16x8*>(lo + ((((size_t)n * D + (d >> 1)) * H + (h >> 1)) * W + (w >> 1)) * C0 + c8 * 8);
+        else
+            val = *reinterpret_cast<const bf16x8*>(skip + v * C1 + (c8 - cg0) * 8);
+        *reinterpret_cast<bf16x8*>(out + i * 8) = val;
+    }
+}
+
+__global__ void __launch_bounds__(NT) upsample_concat_bwd_lo_kernel(const bf16* __restrict__ dcat, bf16* __restrict__ dlo, int N,
+                                                                    int D, int H, int W, int C0, int C1) {
+    const int C = C0 + C1, cg0 = C0 / 8;
+    const int H2 = 2 * H, W2 = 2 * W, D2 = 2 * D;
+    size_t total = (size_t)N * D * H * W * cg0;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        int c8 = (int)(i % cg0);
+        size_t v = i / cg0;
+        int w = (int)(v % W), h = (int)((v / W) % H), d = (int)((v / ((size_t)W * H)) % D);
+        int n = (int)(v / ((size_t)W * H * D));
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = 0.f;
+#pragma unroll
+        for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+            for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+                for (int dx = 0; dx < 2; dx++) {
+                    float f[8];
+                    load8<bf16>(dcat + ((((size_t)n * D2 + 2 * d + dz) * H2 + 2 * h + dy) * W2 + 2 * w + dx) * C + c8 * 8, f);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) a[k] += f[k];
+                }
+        store8<bf16>(dlo + i * 8, a);
+    }
+}
+
+__global__ void __launch_bounds__(NT) upsample_concat_bwd_skip_kernel(const bf16* __restrict__ dcat, bf16* __restrict__ dskip,
+                                                                      size_t V2, int C0, int C1, int accumulate) {
+    const int C = C0 + C1, cg1 = C1 / 8;
+    size_t total = V2 * cg1;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        int c8 = (int)(i % cg1);
+        size_t v = i / cg1;
+        float f[8];
+        load8<bf16>(dcat + v * C + C0 + c8 * 8, f);
+        if (accumulate) {
+            float o[8];
+            load8<bf16>(dskip + i * 8, o);
+#pragma unroll
+            for (int k = 0; k < 8; k++) f[k] += o[k];
+        }
+        store8<bf16>(dskip + i * 8, f);
+    }
+}
+
+__global__ void __launch_bounds__(NT) pad_noise_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int D, int H,
+                                                       int W, const float* __restrict__ noise, float noise_std,
+                                                       unsigned long long seed) {
+    const int PD = D + 2, PH = H + 2, PW = W + 2;
+    size_t total = (size_t)N * PD * PH * PW;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        int pw = (int)(i % PW), ph = (int)((i / PW) % PH), pd = (int)((i / ((size_t)PW * PH)) % PD);
+        int n = (int)(i / ((size_t)PW * PH * PD));
+        int d = reflect1(pd - 1, D), h = reflect1(ph - 1, H), w = reflect1(pw - 1, W);
+        float v = x[(((size_t)n * D + d) * H + h) * W + w];
+        if (noise) {
+            v += noise[i];
+        } else if (noise_std > 0.f) {
+            uint4 r = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 2u, 0x56414e47u),
+                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            v += noise_std * box_muller(r.x, r.y).x;
+        }
+        y[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(NT) pad_fold_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int D, int H,
+                                                      int W, int accumulate) {
+    const int PH = H + 2, PW = W + 2, PD = D + 2;
+    size_t total = (size_t)N * D * H * W;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        int w = (int)(i % W), h = (int)((i / W) % H), d = (int)((i / ((size_t)W * H)) % D);
+        int n = (int)(i / ((size_t)W * H * D));
+        int dd[3], hh[3], ww[3], nd = 1, nh = 1, nw = 1;
+        dd[0] = d + 1; if (d == 1) dd[nd++] = 0; if (d == D - 2) dd[nd++] = D + 1;
+        hh[0] = h + 1; if (h == 1) hh[nh++] = 0; if (h == H - 2) hh[nh++] = H + 1;
+        ww[0] = w + 1; if (w == 1) ww[nw++] = 0; if (w == W - 2) ww[nw++] = W + 1;
+        float s = 0.f;
+        for (int a = 0; a < nd; a++)
+            for (int b = 0; b < nh; b++)
+                for (int c = 0; c < nw; c++) s += dy[(((size_t)n * PD + dd[a]) * PH + hh[b]) * PW + ww[c]];
+        dx[i] = accumulate ? dx[i] + s : s;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) accumulate_kernel(T* __restrict__ a, const T* __restrict__ b, size_t n8, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n8; i += (size_t)gridDim.x * NT) {
+        float fa[8], fb[8];
+        load8<T>(a + i * 8, fa);
+        load8<T>(b + i * 8, fb);
+#pragma unroll
+        for (int k = 0; k < 8; k++) fa[k] += fb[k];
+        store8<T>(a + i * 8, fa);
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = n8 * 8 + threadIdx.x; i < n; i += NT) a[i] = (T)((float)a[i] + (float)b[i]);
+}
+
+__global__ void __launch_bounds__(NT) tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                      float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n; i += (size_t)gridDim.x * NT) {
+        float t = y[i];
+        out[i] = dy[i] * (1.f - t * t);
+    }
+}
+
+// ------------------------------------------------------------------ clip-by-norm + Adam
+__global__ void __launch_bounds__(NT) seg_sqnorm_kernel(const float* __restrict__ g, const long long* __restrict__ off, int nseg,
+                                                        double* __restrict__ norms, int blocks_per_seg) {
+    int seg = blockIdx.x / blocks_per_seg, sub = blockIdx.x % blocks_per_seg;
+    long long a = off[seg], b = off[seg + 1];
+    double s = 0;
+    for (long long i = a + (long long)sub * NT + threadIdx.x; i < b; i += (long long)blocks_per_seg * NT) {
+        float v = g[i];
+        s += (double)v * v;
+    }
+    __shared__ double sh[32];
+    s = block_sum_d(s, sh);
+    if (threadIdx.x == 0 && s != 0.0) atomicAdd(norms + seg, s);
+}
+
+__global__ void __launch_bounds__(NT) clip_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, const long long* __restrict__ off, int nseg,
+                                                       const double* __restrict__ norms, float lr_t, float b1, float b2,
+                                                       float eps, float clip, long long total) {
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        // binary search of the segment containing i
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (off[mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        float nrm = (float)sqrt(norms[lo]);
+        float scale = clip / fmaxf(nrm, clip);   // tf.clip_by_norm
+        float gi = g[i] * scale;
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+// ------------------------------------------------------------------ stitching
+__global__ void __launch_bounds__(NT) stitch_accumulate_kernel(float* __restrict__ pred, float* __restrict__ cnt, int H, int W,
+                                                               int D, const float* __restrict__ win, const int* __restrict__ starts,
+                                                               int B, int kH, int kW, int kD, int pH, int pW, int pD) {
+    const int iH = kH - 2 * pH, iW = kW - 2 * pW, iD = kD - 2 * pD;
+    size_t per = (size_t)iH * iW * iD, total = per * B;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        int b = (int)(i / per);
+        size_t r = i % per;
+        int z = (int)(r % iD) + pD, y = (int)((r / iD) % iW) + pW, x = (int)(r / ((size_t)iD * iW)) + pH;
+        float v = win[(((size_t)b * kH + x) * kW + y) * kD + z];
+        size_t o = (((size_t)(starts[3 * b] + x)) * W + starts[3 * b + 1] + y) * D + starts[3 * b + 2] + z;
+        // windows of one batch may overlap -> atomics (fp32 add order is the only nondeterminism)
+        atomicAdd(pred + o, v);
+        atomicAdd(cnt + o, 1.0f);
+    }
+}
+
+__device__ __forceinline__ uint32_t enc_f(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void stitch_init_kernel(uint32_t* enc) { enc[0] = 0xffffffffu; enc[1] = 0u; }
+
+__global__ void __launch_bounds__(NT) stitch_divide_kernel(const float* __restrict__ pred, const float* __restrict__ cnt, int H,
+                                                           int W, int D, int x0, int y0, int z0, int oH, int oW, int oD,
+                                                           float* __restrict__ out, uint32_t* enc) {
+    size_t total = (size_t)oH * oW * oD;
+    float mn = INFINITY, mx = -INFINITY;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        int z = (int)(i % oD), y = (int)((i / oD) % oW), x = (int)(i / ((size_t)oD * oW));
+        size_t s = (((size_t)(x + x0)) * W + y + y0) * D + z + z0;
+        float v = __fdiv_rn(pred[s], cnt[s]);   // np.true_divide
+        out[i] = v;
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(enc, enc_f(mn));
+        atomicMax(enc + 1, enc_f(mx));
+    }
+}
+
+__global__ void stitch_decode_kernel(const uint32_t* enc, float* mm) {
+    mm[0] = dec_f(enc[0]);
+    mm[1] = dec_f(enc[1]);
+}
+
+__global__ void __launch_bounds__(NT) stitch_scale_kernel(float* __restrict__ out, size_t n, const float* __restrict__ mm) {
+    float mn = mm[0], r = __fsub_rn(mm[1], mn);
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n; i += (size_t)gridDim.x * NT)
+        out[i] = __fmul_rn(255.f, __fdiv_rn(__fsub_rn(out[i], mn), r));   // 255 * (data - dmin) / (dmax - dmin)
+}
+
+}  // namespace
+
+extern "C" {
+
+int vg_upsample_concat(const void* lo, const void* skip, void* out, int N, int D, int H, int W, int C0, int C1, void* stream) {
+    VG_REQUIRE(lo && skip && out && C0 % 8 == 0 && C1 % 8 == 0 && N > 0);
+    size_t total = (size_t)N * 8 * D * H * W * ((C0 + C1) / 8);
+    upsample_concat_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>((const bf16*)lo, (const bf16*)skip, (bf16*)out,
+                                                                                       N, D, H, W, C0, C1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_upsample_concat_bwd(const void* dcat, void* dlo, void* dskip, int accumulate_skip, int N, int D, int H, int W, int C0,
+                           int C1, void* stream) {
+    VG_REQUIRE(dcat && dlo && dskip && C0 % 8 == 0 && C1 % 8 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t t0 = (size_t)N * D * H * W * (C0 / 8), V2 = (size_t)N * 8 * D * H * W;
+    upsample_concat_bwd_lo_kernel<<<vg_grid_for(t0, NT, 16), NT, 0, st>>>((const bf16*)dcat, (bf16*)dlo, N, D, H, W, C0, C1);
+    upsample_concat_bwd_skip_kernel<<<vg_grid_for(V2 * (C1 / 8), NT, 16), NT, 0, st>>>((const bf16*)dcat, (bf16*)dskip, V2, C0, C1,
+                                                                                      accumulate_skip);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_pad_noise(const float* x, float* y, int N, int D, int H, int W, const float* noise, float noise_std,
+                 unsigned long long seed, void* stream) {
+    VG_REQUIRE(x && y && D >= 2 && H >= 2 && W >= 2);
+    size_t total = (size_t)N * (D + 2) * (H + 2) * (W + 2);
+    pad_noise_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(x, y, N, D, H, W, noise, noise_std, seed);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_pad_fold(const float* dy, float* dx, int N, int D, int H, int W, int accumulate, void* stream) {
+    VG_REQUIRE(dy && dx);
+    size_t total = (size_t)N * D * H * W;
+    pad_fold_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(dy, dx, N, D, H, W, accumulate);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_accumulate(void* a, const void* b, size_t n, int dtype, void* stream) {
+    VG_REQUIRE(a && b);
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t n8 = n / 8;
+    if (dtype == VG_BF16)
+        accumulate_kernel<bf16><<<vg_grid_for(n8 + 1, NT, 16), NT, 0, st>>>((bf16*)a, (const bf16*)b, n8, n);
+    else if (dtype == VG_F32)
+        accumulate_kernel<float><<<vg_grid_for(n8 + 1, NT, 16), NT, 0, st>>>((float*)a, (const float*)b, n8, n);
+    else
+        return VG_ERR_INVALID;
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_tanh_bwd(const float* dy, const float* y, float* out, size_t n, void* stream) {
+    VG_REQUIRE(dy && y && out);
+    tanh_bwd_kernel<<<vg_grid_for(n, NT * 2, 8), NT, 0, (cudaStream_t)stream>>>(dy, y, out, n);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+// norm_ws: nseg doubles (zeroed here)
+int vg_clip_adam_step(float* w, const float* g, float* m, float* v, const long long* seg_offsets, int nseg, long long total,
+                      float lr_t, float beta1, float beta2, float eps, float clipnorm, double* norm_ws, void* stream) {
+    VG_REQUIRE(w && g && m && v && seg_offsets && nseg > 0 && total > 0 && norm_ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(norm_ws, 0, (size_t)nseg * sizeof(double), st) != cudaSuccess) return VG_ERR_CUDA;
+    const int bps = 8;
+    seg_sqnorm_kernel<<<nseg * bps, NT, 0, st>>>(g, seg_offsets, nseg, norm_ws, bps);
+    clip_adam_kernel<<<vg_grid_for(total, NT, 16), NT, 0, st>>>(w, g, m, v, seg_offsets, nseg, norm_ws, lr_t, beta1, beta2, eps,
+                                                               clipnorm, total);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_stitch_accumulate(float* pred, float* cnt, int H, int W, int D, const float* win, const int* starts, int B, int kH,
+                         int kW, int kD, int pH, int pW, int pD, void* stream) {
+    VG_REQUIRE(pred && cnt && win && starts && B > 0);
+    size_t total = (size_t)B * (kH - 2 * pH) * (kW - 2 * pW) * (kD - 2 * pD);
+    stitch_accumulate_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(pred, cnt, H, W, D, win, starts, B, kH, kW,
+                                                                                         kD, pH, pW, pD);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_stitch_finalize(const float* pred, const float* cnt, int H, int W, int D, int x0, int y0, int z0, int oH, int oW, int oD,
+                       float* out, float* mm, void* enc_ws, void* stream) {
+    VG_REQUIRE(pred && cnt && out && mm && enc_ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    stitch_init_kernel<<<1, 1, 0, st>>>((uint32_t*)enc_ws);
+    stitch_divide_kernel<<<vg_grid_for((size_t)oH * oW * oD, NT, 16), NT, 0, st>>>(pred, cnt, H, W, D, x0, y0, z0, oH, oW, oD, out,
+                                                                                  (uint32_t*)enc_ws);
+    stitch_decode_kernel<<<1, 1, 0, st>>>((const uint32_t*)enc_ws, mm);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_stitch_scale(float* out, size_t n, const float* mm, void* stream) {
+    VG_REQUIRE(out && mm);
+    stitch_scale_kernel<<<vg_grid_for(n, NT, 16), NT, 0, (cudaStream_t)stream>>>(out, n, mm);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,325 @@
+"""Host-side execution engine: a persistent gradient tape over the C-ABI kernels.
+
+Plays the role tf.GradientTape(persistent=True) + Keras layers play in the reference
+(vangan.py:394-438): every op records a node; `Tape.backward` runs one reverse sweep for ONE loss
+w.r.t. ONE network's variables (what each `optimizer.minimize(loss, var_list, tape)` call does),
+visiting only nodes that lie between the seeds and the requested variables.
+
+All device arithmetic happens inside libvangan_b200.so; torch supplies allocation and streams.
+Activations are NDHWC, bf16 for multi-channel feature maps, fp32 for single-channel volumes.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH, PAD_REFLECT, PAD_ZERO, ConvDesc, InDesc, call, dtype_code
+
+DEV = "cuda"
+
+
+# ----------------------------------------------------------------------------- tape
+class Var:
+    """A tensor on the tape.  `data`: torch CUDA tensor; `grad`: accumulated gradient or None."""
+    __slots__ = ("data", "grad", "src")
+
+    def __init__(self, data, src=None):
+        self.data = data
+        self.grad = None
+        self.src = src
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+
+class Node:
+    __slots__ = ("inputs", "outputs", "params", "bwd", "name")
+
+    def __init__(self, inputs, outputs, params, bwd, name):
+        self.inputs, self.outputs, self.params, self.bwd, self.name = inputs, outputs, params, bwd, name
+
+
+def accumulate(var, g):
+    """var.grad += g (takes ownership of g when it is the first contribution)."""
+    if var.grad is None:
+        var.grad = g
+    else:
+        call("vg_accumulate", var.grad, g, g.numel(), dtype_code(g))
+
+
+class Tape:
+    def __init__(self, enabled=True):
+        self.nodes = []
+        self.enabled = enabled
+
+    def record(self, inputs, outputs, params, bwd, name):
+        if self.enabled:
+            node = Node(inputs, outputs, params, bwd, name)
+            for o in outputs:
+                o.src = node
+            self.nodes.append(node)
+
+    def backward(self, seeds, wrt_params, wrt_vars=()):
+        """seeds: list of (Var, grad tensor).  wrt_params: Param objects whose .grad views receive
+        (+=) the gradients; wrt_vars: leaf Vars whose .grad is wanted as well (kept after the sweep).
+        One reverse sweep; gradients of intermediate Vars are released as soon as they are consumed."""
+        wrt = set(id(p) for p in wrt_params)
+        needs = set(id(v) for v in wrt_vars)
+        keep = set(needs)
+        for node in self.nodes:
+            if any(id(p) in wrt for p in node.params) or any(id(v) in needs for v in node.inputs):
+                for o in node.outputs:
+                    needs.add(id(o))
+        for v, g in seeds:
+            accumulate(v, g)
+        for node in reversed(self.nodes):
+            outs = node.outputs
+            if all(o.grad is None for o in outs):
+                continue
+            if id(outs[0]) not in needs:
+                for o in outs:
+                    o.grad = None
+                continue
+            in_needs = [id(v) in needs for v in node.inputs]
+            p_needs = any(id(p) in wrt for p in node.params)
+            node.bwd(in_needs, p_needs)
+            for o in outs:
+                o.grad = None
+        # inputs that are leaves keep their grads; clear everything else that may linger
+        for node in self.nodes:
+            for v in node.inputs:
+                if v.src is None and id(v) not in keep:
+                    v.grad = None
+
+
+# ----------------------------------------------------------------------------- parameters
+class Param:
+    """A trainable variable: fp32 views into its network's flat weight / gradient buffers."""
+    __slots__ = ("name", "shape", "offset", "size", "w", "grad")
+
+    def __init__(self, name, shape, offset):
+        self.name, self.shape, self.offset = name, tuple(shape), offset
+        self.size = int(np.prod(shape))
+        self.w = None
+        self.grad = None
+
+
+class Network:
+    """Owns the flat fp32 master weights, gradients and Adam slots of one Keras model, in the
+    model's trainable_variables order (Keras layouts, so a TF checkpoint maps 1:1)."""
+
+    def __init__(self, name, shapes):
+        self.name = name
+        self.params = {}
+        off = 0
+        for n, shp in shapes.items():
+            self.params[n] = Param(n, shp, off)
+            off += self.params[n].size
+        self.total = off
+        self.w = torch.zeros(off, dtype=torch.float32, device=DEV)
+        self.g = torch.zeros(off, dtype=torch.float32, device=DEV)
+        self.m = torch.zeros(off, dtype=torch.float32, device=DEV)
+        self.v = torch.zeros(off, dtype=torch.float32, device=DEV)
+        offs = [p.offset for p in self.params.values()] + [off]
+        self.seg = torch.tensor(offs, dtype=torch.int64, device=DEV)
+        self.norm_ws = torch.zeros(len(self.params), dtype=torch.float64, device=DEV)
+        for p in self.params.values():
+            p.w = self.w[p.offset:p.offset + p.size].view(p.shape)
+            p.grad = self.g[p.offset:p.offset + p.size].view(p.shape)
+        self.convs = []
+        self.step_count = 0
+
+    @property
+    def trainable_variables(self):
+        return list(self.params.values())
+
+    def load(self, arrays):
+        """arrays: {name: numpy array in Keras layout}."""
+        for n, p in self.params.items():
+            a = np.asarray(arrays[n], dtype=np.float32)
+            assert a.shape == p.shape, (n, a.shape, p.shape)
+            p.w.copy_(torch.from_numpy(a).to(DEV))
+        self.repack()
+
+    def export(self):
+        return {n: p.w.detach().cpu().numpy().copy() for n, p in self.params.items()}
+
+    def export_grads(self):
+        return {n: p.grad.detach().cpu().numpy().copy() for n, p in self.params.items()}
+
+    def repack(self):
+        for c in self.convs:
+            c.repack()
+
+    def zero_grad(self):
+        self.g.zero_()
+
+    def adam_step(self, lr=2e-4, beta_1=0.5, beta_2=0.9, eps=1e-7, clipnorm=100.0):
+        """Keras OptimizerV2 Adam: per-variable clip_by_norm, lr_t = lr*sqrt(1-b2^t)/(1-b1^t)."""
+        self.step_count += 1
+        t = self.step_count
+        lr_t = lr * math.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t)
+        call("vg_clip_adam_step", self.w, self.g, self.m, self.v, self.seg, len(self.params), self.total, lr_t, beta_1,
+             beta_2, eps, clipnorm, self.norm_ws)
+        self.repack()
+
+
+def he_normal(rng, shape):
+    """Keras 'he_normal' (truncated normal, stddev sqrt(2/fan_in)/0.8796...)."""
+    fan_in = int(np.prod(shape[:-1]))
+    std = math.sqrt(2.0 / fan_in) / 0.87962566103423978
+    z = rng.standard_normal(size=shape)
+    bad = np.abs(z) > 2
+    while bad.any():
+        z[bad] = rng.standard_normal(size=int(bad.sum()))
+        bad = np.abs(z) > 2
+    return (z * std).astype(np.float32)
+
+
+def default_init(shapes, seed):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for n, shp in shapes.items():
+        if n.endswith(".w"):
+            out[n] = he_normal(rng, shp)
+        elif n.endswith(".gamma"):
+            out[n] = np.ones(shp, np.float32)
+        else:
+            out[n] = np.zeros(shp, np.float32)
+    return out
+
+
+# ----------------------------------------------------------------------------- layers
+class Conv3D:
+    """keras.layers.Conv3D(filters, k, strides, padding='valid') over an explicitly padded input."""
+
+    def __init__(self, net, name, k, stride, cin, cout, use_bias=True, act=ACT_NONE):
+        self.w = net.params[name + ".w"]
+        self.b = net.params[name + ".b"] if use_bias else None
+        self.k, self.stride, self.cin, self.cout, self.act = k, stride, cin, cout, act
+        self.x_dtype = _lib.VG_F32 if cin == 1 else _lib.VG_BF16
+        self.y_dtype = _lib.VG_F32 if cout == 1 else _lib.VG_BF16
+        d = self.desc(1, 8, 8, 8)
+        nb_f = _lib.lib().vg_conv3d_packed_bytes(d, 0)
+        nb_d = _lib.lib().vg_conv3d_packed_bytes(d, 1)
+        self.wf = torch.empty(max(nb_f, 2) // 2, dtype=torch.bfloat16, device=DEV) if nb_f else None
+        self.wd = torch.empty(max(nb_d, 2) // 2, dtype=torch.bfloat16, device=DEV) if nb_d else None
+        net.convs.append(self)
+
+    def desc(self, n, d, h, w):
+        return ConvDesc(n, d, h, w, self.cin, self.cout, self.k, self.stride, self.x_dtype, self.y_dtype, self.act)
+
+    def repack(self):
+        if self.wf is not None or self.wd is not None:
+            call("vg_conv3d_pack_weights", self.desc(1, 8, 8, 8), self.w.w, self.wf, self.wd)
+
+    def __call__(self, tape, x):
+        n, d, h, w, c = x.shape
+        assert c == self.cin, (c, self.cin)
+        desc = self.desc(n, d, h, w)
+        od, oh, ow = [(s - self.k) // self.stride + 1 for s in (d, h, w)]
+        y = torch.empty((n, od, oh, ow, self.cout), device=DEV,
+                        dtype=torch.float32 if self.cout == 1 else torch.bfloat16)
+        call("vg_conv3d_fwd", desc, x.data, self.w.w if self.cin == 1 else self.wf, self.b.w if self.b else None, y)
+        out = Var(y)
+
+        def bwd(in_needs, p_needs):
+            dy = out.grad
+            if self.act == ACT_TANH:
+                t = torch.empty_like(dy)
+                call("vg_tanh_bwd", dy, out.data, t, dy.numel())
+                dy = t
+            if p_needs:
+                call("vg_conv3d_wgrad", desc, x.data, dy, self.w.grad, self.b.grad if self.b else None)
+            if in_needs[0]:
+                dx = torch.empty_like(x.data)
+                call("vg_conv3d_dgrad", desc, dy, self.w.w if self.cout == 1 else self.wd, dx)
+                accumulate(x, dx)
+
+        tape.record([x], [out], [self.w] + ([self.b] if self.b else []), bwd, "conv")
+        return out
+
+
+class InstanceNorm:
+    """tfa.layers.InstanceNormalization followed by the activation / residual Add / SpatialDropout3D /
+    GaussianNoise / padding that the reference applies before the next convolution."""
+
+    def __init__(self, net, name, c):
+        self.gamma = net.params[name + ".gamma"]
+        self.beta = net.params[name + ".beta"]
+        self.c = c
+
+    def __call__(self, tape, x, act=ACT_NONE, slope=0.2, residual=None, pad=(0, 0, PAD_ZERO), drop=None, noise=None,
+                 noise_std=0.0, seed=0):
+        n, d, h, w, c = x.shape
+        assert c == self.c
+        dt = dtype_code(x.data)
+        ws_bytes = _lib.lib().vg_instnorm_workspace_bytes(n, d, h, w, c)
+        ws = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
+        mean = torch.empty(n * c, dtype=torch.float32, device=DEV)
+        rstd = torch.empty(n * c, dtype=torch.float32, device=DEV)
+        call("vg_instnorm_stats", x.data, dt, n, d, h, w, c, mean, rstd, ws, ws_bytes)
+        desc = InDesc(n, d, h, w, c, dt, act, slope, pad[0], pad[1], pad[2], noise_std if noise is None else 0.0, seed)
+        pp = pad[0] + pad[1]
+        y = torch.empty((n, d + pp, h + pp, w + pp, c), dtype=x.data.dtype, device=DEV)
+        call("vg_instnorm_apply", desc, x.data, residual.data if residual is not None else None, y, mean, rstd,
+             self.gamma.w, self.beta.w, drop, noise)
+        out = Var(y)
+        ins = [x] + ([residual] if residual is not None else [])
+
+        def bwd(in_needs, p_needs):
+            dy = out.grad
+            dx = torch.empty_like(x.data)
+            need_res = residual is not None and in_needs[1]
+            dres = torch.empty_like(x.data) if need_res else None
+            ws2 = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
+            call("vg_instnorm_bwd", desc, dy, x.data, mean, rstd, self.gamma.w, self.beta.w, drop, dx, 0, dres,
+                 self.gamma.grad if p_needs else None, self.beta.grad if p_needs else None, ws2, ws_bytes)
+            if in_needs[0]:
+                accumulate(x, dx)
+            if need_res:
+                accumulate(residual, dres)
+
+        tape.record(ins, [out], [self.gamma, self.beta], bwd, "instnorm")
+        return out
+
+
+def upsample_concat(tape, lo, skip):
+    """UpSampling3D(2) + concatenate([x, xskip]) (resunet_model.py:176,181)."""
+    n, d, h, w, c0 = lo.shape
+    c1 = skip.shape[-1]
+    y = torch.empty((n, 2 * d, 2 * h, 2 * w, c0 + c1), dtype=torch.bfloat16, device=DEV)
+    call("vg_upsample_concat", lo.data, skip.data, y, n, d, h, w, c0, c1)
+    out = Var(y)
+
+    def bwd(in_needs, p_needs):
+        dlo = torch.empty_like(lo.data)
+        dsk = torch.empty_like(skip.data)
+        call("vg_upsample_concat_bwd", out.grad, dlo, dsk, 0, n, d, h, w, c0, c1)
+        if in_needs[0]:
+            accumulate(lo, dlo)
+        if in_needs[1]:
+            accumulate(skip, dsk)
+
+    tape.record([lo, skip], [out], [], bwd, "upcat")
+    return out
+
+
+def pad_noise(tape, x, noise=None, noise_std=0.0, seed=0):
+    """ReflectionPadding3D + GaussianNoise on a single-channel fp32 volume (discriminator.py:50-52)."""
+    n, d, h, w, c = x.shape
+    assert c == 1 and x.data.dtype == torch.float32
+    y = torch.empty((n, d + 2, h + 2, w + 2, 1), dtype=torch.float32, device=DEV)
+    call("vg_pad_noise", x.data, y, n, d, h, w, noise, noise_std if noise is None else 0.0, seed)
+    out = Var(y)
+
+    def bwd(in_needs, p_needs):
+        if in_needs[0]:
+            dx = torch.empty_like(x.data)
+            call("vg_pad_fold", out.grad, dx, n, d, h, w, 0)
+            accumulate(x, dx)
+
+    tape.record([x], [out], [], bwd, "pad_noise")
+    return out

@@ -1,0 +1,213 @@
+"""VanGan — the reference's trainer class (vangan.py:20-508) re-backed by the B200 kernels.
+
+Kept from the reference: the constructor signature, the attribute names the loss functions read,
+`compute_losses`, `train_step`, `test_step`, `distributed_train_step`, `distributed_test_step`,
+`reduce_dict`, the ten result-dict keys (vangan.py:338-351) and the order of the four optimizer
+updates (vangan.py:426-438).  Only the LSGAN / resUnet configuration that main.py runs
+(main.py:196-200) is built; the other branches raise.
+"""
+import numpy as np
+import torch
+
+from . import engine as E
+from .discriminator import get_discriminator
+from .distribute import Strategy
+from .loss_functions import (LossContext, cycle_loss, cycle_reconstruction, cycle_seg_loss, discriminator_loss_fn,
+                             generator_loss_fn)
+from .resunet_model import ResUNet
+
+RESULT_KEYS = ("total_IS_loss", "total_SI_loss", "D_I_loss", "D_S_loss", "gen_IS_loss", "gen_SI_loss",
+               "cycle_gen_SIS_loss", "cycle_gen_ISI_loss", "seg_loss", "reconstruction_loss_I")
+
+
+class VanGan:
+    def __init__(self, args, strategy=None, lambda_cycle=10.0, lambda_identity=5, lambda_reconstruction=5,
+                 lambda_topology=5, gen_i2s='resnet', gen_s2i='resnet', semi_supervised=False, wasserstein=False,
+                 ncritic=5, gp_weight=10.0, seed=1234):
+        self.strategy = strategy if strategy is not None else Strategy()
+        self.n_devices = args.N_DEVICES
+        self.img_size = args.INPUT_IMG_SIZE
+        self.lambda_cycle = lambda_cycle
+        self.lambda_identity = lambda_identity
+        self.lambda_reconstruction = lambda_reconstruction
+        self.lambda_topology = lambda_topology
+        self.channels = args.CHANNELS
+        self.gen_i2s_typ, self.gen_s2i_typ = gen_i2s, gen_s2i
+        self.semi_supervised = semi_supervised
+        self.global_batch_size = args.GLOBAL_BATCH_SIZE
+        self.dims = args.DIMENSIONS
+        if self.dims != 3:
+            raise NotImplementedError("only DIMENSIONS=3 is built (main.py:80)")
+        sp = args.SUBVOL_PATCH_SIZE
+        self.subvol_patch_size = (sp[0], sp[1], sp[2], self.channels)
+        self.seg_subvol_patch_size = (sp[0], sp[1], sp[2], 1)
+        self.train_steps = getattr(args, "train_steps", None)
+        self.batch_size = getattr(args, "BATCH_SIZE", None)
+        self.wasserstein = wasserstein
+        if wasserstein:
+            raise NotImplementedError("Wasserstein/GP branch (vangan.py:355-378,400-423) is out of scope")
+        self.cycle_loss_fn = cycle_loss
+        self.generator_loss_fn = generator_loss_fn
+        self.discriminator_loss_fn = discriminator_loss_fn
+        self.seg_loss_fn = cycle_seg_loss
+        self.reconstruction_loss = cycle_reconstruction
+        self.layer_noise = 0.1
+        self.cldice_iters = 15
+        self.step = 0
+        self.loss_ctx = None
+
+        with self.strategy.scope():
+            if gen_i2s != 'resUnet' or gen_s2i != 'resUnet':
+                raise NotImplementedError("generators: only 'resUnet' (what main.py:196-200 selects) is built; "
+                                          "'resnet'/'vnet' are listed under next steps in DESIGN.md")
+            self.gen_IS = ResUNet(input_shape=self.subvol_patch_size, upsample_mode='simple', dropout=0.1,
+                                  dropout_change_per_layer=0.1, dropout_type='none', use_attention_gate=False,
+                                  filters=16, num_layers=4, name='generator_IS', seed=seed)
+            self.gen_SI = ResUNet(input_shape=self.seg_subvol_patch_size, upsample_mode='simple', dropout=0.1,
+                                  dropout_change_per_layer=0.1, dropout_type='none', use_attention_gate=False,
+                                  filters=16, num_layers=4, use_input_noise=False, name='generator_SI', seed=seed + 1)
+            common = dict(filters=64, use_dropout=True, dropout_rate=0.2, wasserstein=False, use_SN=False,
+                          use_input_noise=True, use_layer_noise=True, noise_std=self.layer_noise)
+            self.disc_I = get_discriminator(input_img_size=self.subvol_patch_size, batch_size=self.global_batch_size,
+                                            name='discriminator_I', seed=seed + 2, **common)
+            self.disc_S = get_discriminator(input_img_size=self.seg_subvol_patch_size, batch_size=self.global_batch_size,
+                                            name='discriminator_S', seed=seed + 3, **common)
+            # tf.keras.optimizers.Adam(2e-4, beta_1=0.5, beta_2=0.9, clipnorm=100) x4 (vangan.py:220-235)
+            self.opt = dict(lr=2e-4, beta_1=0.5, beta_2=0.9, eps=1e-7, clipnorm=100.0)
+        self.networks = {"gen_IS": self.gen_IS, "gen_SI": self.gen_SI, "disc_I": self.disc_I, "disc_S": self.disc_S}
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _as_var(x):
+        if isinstance(x, E.Var):
+            return x
+        t = torch.as_tensor(x)
+        if t.device.type != "cuda":
+            t = t.to(E.DEV, non_blocking=True)
+        return E.Var(t.to(torch.float32).contiguous())
+
+    def _disc(self, net, tape, x, training, rand, key, app):
+        noise, masks = (None, None) if rand is None else rand[key]
+        return net.forward(tape, x, training=training, noise=noise, masks=masks, seed=self.step * 4 + app)
+
+    # ------------------------------------------------------------------ reference API
+    def compute_losses(self, real_I, real_S, result, training=True, rand=None, tape=None):
+        """vangan.py:270-353.  Returns (result, total_loss_I, total_loss_S, disc_I_loss, disc_S_loss, fake_I, fake_S);
+        the losses are `Scalar`s (float() for the value).  `rand`: optional explicit discriminator noise / dropout
+        tensors {'S_real','S_fake','I_real','I_fake': (noise list, mask list)} for parity tests."""
+        tape = tape if tape is not None else E.Tape(enabled=training)
+        self.tape = tape
+        self.loss_ctx = LossContext()
+        real_I, real_S = self._as_var(real_I), self._as_var(real_S)
+        fake_S = self.gen_IS.forward(tape, real_I)
+        fake_I = self.gen_SI.forward(tape, real_S)
+        cycled_S = self.gen_IS.forward(tape, fake_I)
+        cycle_loss_I = self.cycle_loss_fn(self, real_S, cycled_S, typ="bce")
+        seg_loss = self.seg_loss_fn(self, real_S, cycled_S, iters=self.cldice_iters)
+        cycled_I = self.gen_SI.forward(tape, fake_S)
+        cycle_loss_S = self.cycle_loss_fn(self, real_I, cycled_I, typ='mse')
+        reconstruction_loss = self.reconstruction_loss(self, real_I, cycled_I)
+
+        disc_real_S = self._disc(self.disc_S, tape, real_S, training, rand, "S_real", 0)
+        disc_fake_S = self._disc(self.disc_S, tape, fake_S, training, rand, "S_fake", 1)
+        disc_real_I = self._disc(self.disc_I, tape, real_I, training, rand, "I_real", 2)
+        disc_fake_I = self._disc(self.disc_I, tape, fake_I, training, rand, "I_fake", 3)
+
+        gen_IS_loss = self.generator_loss_fn(self, disc_fake_S, from_logits=True)
+        gen_SI_loss = self.generator_loss_fn(self, disc_fake_I, from_logits=True)
+        disc_I_loss = self.discriminator_loss_fn(self, disc_real_I, disc_fake_I, from_logits=True)
+        disc_S_loss = self.discriminator_loss_fn(self, disc_real_S, disc_fake_S, from_logits=True)
+
+        total_loss_I = gen_IS_loss + cycle_loss_I + seg_loss
+        total_loss_S = gen_SI_loss + cycle_loss_S + reconstruction_loss
+        result.update({
+            'total_IS_loss': total_loss_I, 'total_SI_loss': total_loss_S, 'D_I_loss': disc_I_loss,
+            'D_S_loss': disc_S_loss, 'gen_IS_loss': gen_IS_loss, 'gen_SI_loss': gen_SI_loss,
+            'cycle_gen_SIS_loss': cycle_loss_I, 'cycle_gen_ISI_loss': cycle_loss_S, 'seg_loss': seg_loss,
+            'reconstruction_loss_I': reconstruction_loss})
+        self.last = dict(fake_S=fake_S, fake_I=fake_I, cycled_S=cycled_S, cycled_I=cycled_I, disc_real_S=disc_real_S,
+                         disc_fake_S=disc_fake_S, disc_real_I=disc_real_I, disc_fake_I=disc_fake_I)
+        return result, total_loss_I, total_loss_S, disc_I_loss, disc_S_loss, fake_I, fake_S
+
+    def train_step(self, real_I, real_S, rand=None, apply=True):
+        """vangan.py:380-440: persistent tape around compute_losses, then one minimize per network
+        (gen_IS on total_loss_I, gen_SI on total_loss_S, disc_I, disc_S).  Each network's gradient
+        all-reduce (MirroredStrategy's, hidden inside `minimize`) is launched as soon as its sweep ends."""
+        result = {}
+        result, total_I, total_S, dI, dS, _fI, _fS = self.compute_losses(real_I, real_S, result, training=True, rand=rand)
+        plan = ((self.gen_IS, total_I), (self.gen_SI, total_S), (self.disc_I, dI), (self.disc_S, dS))
+        handles = []
+        for net, loss in plan:
+            net.zero_grad()
+            self.tape.backward(loss.seeds(), net.trainable_variables)
+            handles.append(self.strategy.all_reduce_async(net.g))
+        if apply:
+            for (net, _), h in zip(plan, handles):
+                if h is not None:
+                    h.wait()
+                net.adam_step(**self.opt)
+        else:
+            for h in handles:
+                if h is not None:
+                    h.wait()
+        self.step += 1
+        self.tape = None
+        vals = self.loss_ctx.values()
+        return {k: float(v.value_fn(vals)) for k, v in result.items()}
+
+    def test_step(self, real_I, real_S):
+        """vangan.py:442-457."""
+        result = {}
+        result, *_ = self.compute_losses(real_I, real_S, result, training=False)
+        vals = self.loss_ctx.values()
+        return {k: float(v.value_fn(vals)) for k, v in result.items()}
+
+    def reduce_dict(self, d):
+        """vangan.py:459-473: SUM over replicas of every entry (one 10-float all-reduce)."""
+        keys = list(d.keys())
+        if self.strategy.num_replicas_in_sync > 1:
+            t = torch.tensor([d[k] for k in keys], dtype=torch.float64, device=E.DEV)
+            self.strategy.reduce("SUM", t, axis=None)
+            vals = t.cpu().tolist()
+            for k, v in zip(keys, vals):
+                d[k] = v
+
+    def distributed_train_step(self, x, y, rand=None):
+        """vangan.py:475-490.  x, y: this replica's shard of the global batch."""
+        results = self.strategy.run(self.train_step, args=(x, y), kwargs=dict(rand=rand))
+        self.reduce_dict(results)
+        return results
+
+    def distributed_test_step(self, x, y):
+        results = self.strategy.run(self.test_step, args=(x, y))
+        self.reduce_dict(results)
+        return results
+
+    # ------------------------------------------------------------------ checkpoints (numpy .npz, Keras layouts)
+    def save_checkpoint(self, path):
+        arrays = {}
+        for nn, net in self.networks.items():
+            for k, v in net.export().items():
+                arrays[nn + "/" + k] = v
+        np.savez(path, **arrays)
+
+    def load_checkpoint(self, path):
+        z = np.load(path)
+        for nn, net in self.networks.items():
+            net.load({k: z[nn + "/" + k] for k in net.params})
+
+
+def train(ds, gan, summary, epoch, steps=None, desc=None, training=True):
+    """vangan.py:510-550: loops the dataset, appends the per-step result dicts."""
+    from .utils import append_dict
+    results, cntr = {}, 0
+    for x, y in ds:
+        if cntr == steps:
+            break
+        cntr += 1
+        result = gan.distributed_train_step(x, y) if training else gan.distributed_test_step(x, y)
+        append_dict(results, result)
+    if summary is not None:
+        for key, value in results.items():
+            summary.scalar(key, float(np.mean(value)), epoch=epoch, training=training)
+    return results
