@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py — VAN-GAN 128^3 train-step throughput (volumes/s) on N B200s of one node.
+
+Workload (BASELINE.json configs[1]): full VanGan.train_step — 2 ResUNet generators + 2 3D-PatchGAN
+discriminators, all ten losses (LSGAN, BCE/MSE cycle, SSIM reconstruction, clDice iters=15), four backward
+sweeps, gradient all-reduce, clip+Adam — on synthetic 128^3 single-channel volumes, GLOBAL batch 8, sharded
+b = 8/N per GPU (strong scaling), one process per GPU over NCCL.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # the CPU oracle port of the reference, host cores
+  torchrun ... bench.py --gpus N ...                       # N > 1 (driver-launched)
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_step_volumes_per_s_128cubed"
+UNIT = "volumes/s"
+
+
+class Args:
+    """The attributes VanGan reads from the reference's `args` namespace (main.py:62-105)."""
+
+    def __init__(self, S, G, nd):
+        self.N_DEVICES, self.GLOBAL_BATCH_SIZE = nd, G
+        self.INPUT_IMG_SIZE = (G, S, S, S, 1)
+        self.CHANNELS, self.DIMENSIONS = 1, 3
+        self.SUBVOL_PATCH_SIZE = (S, S, S)
+        self.train_steps, self.BATCH_SIZE, self.output_dir = 1, G // nd, "/tmp"
+
+
+def synth_batch(n, S, seed):
+    """Synthetic photoacoustic-like imaging volumes and vessel-like segmentation volumes in [-1,1]
+    (SURVEY.md 8d config 2): smoothed noise; union of random soft-edged tubes."""
+    import numpy as np
+    from scipy import ndimage
+    rng = np.random.default_rng(seed)
+    I = np.empty((n, S, S, S, 1), np.float32)
+    Sg = np.empty((n, S, S, S, 1), np.float32)
+    ax = np.arange(S, dtype=np.float32)
+    zz, yy, xx = np.meshgrid(ax, ax, ax, indexing="ij")
+    for i in range(n):
+        v = ndimage.gaussian_filter(rng.standard_normal((S, S, S)).astype(np.float32), 2.0)
+        I[i, ..., 0] = 2 * (v - v.min()) / (v.max() - v.min()) - 1
+        t = np.zeros((S, S, S), np.float32)
+        for _ in range(24):
+            p0, d = rng.random(3) * S, rng.standard_normal(3)
+            d /= np.linalg.norm(d)
+            rz, ry, rx = zz - p0[0], yy - p0[1], xx - p0[2]
+            along = rz * d[0] + ry * d[1] + rx * d[2]
+            dist = np.sqrt(np.maximum(rz * rz + ry * ry + rx * rx - along * along, 0))
+            t = np.maximum(t, 1.0 / (1.0 + np.exp((dist - (1.5 + 2.5 * rng.random())) * 2.0)))
+        Sg[i, ..., 0] = 2 * t - 1 + 1e-3 * rng.standard_normal((S, S, S)).astype(np.float32)
+    return I, Sg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nme, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1375.8), d.get("hbm_gbs", 6551.7), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+def cpu_oracle_sample(S=64, steps=1, warmup=0):
+    """Times the oracle port of the reference's train_step (torch CPU fp32, all host cores) on a bounded
+    sample: one 1 x S^3 step; converted to 128^3-volumes/s by the voxel ratio.  Returns (value, seconds/step, cores)."""
+    import numpy as np
+    import torch
+    from oracle import losses as OL, nets as ON, step as OS
+    cores = torch.get_num_threads()
+    rng = np.random.default_rng(0)
+    I, Sg = synth_batch(1, S, 11)
+    real_I, real_S = torch.tensor(I), torch.tensor(Sg)
+    P = {"gen_IS": ON.to_torch(ON.init_params(ON.resunet_param_shapes(), 1234)),
+         "gen_SI": ON.to_torch(ON.init_params(ON.resunet_param_shapes(), 1235)),
+         "disc_I": ON.to_torch(ON.init_params(ON.disc_param_shapes(), 1236)),
+         "disc_S": ON.to_torch(ON.init_params(ON.disc_param_shapes(), 1237))}
+    opts = {k: OS.Adam(list(v.keys())) for k, v in P.items()}
+    cfg = OL.make_cfg(1, 1)
+    times = []
+    for it in range(warmup + steps):
+        rand = {k: ON.make_disc_rand(rng, 1, S) for k in ("S_real", "S_fake", "I_real", "I_fake")}
+        t0 = time.perf_counter()
+        OS.train_step_dp(cfg, P, opts, real_I, real_S, [rand])
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    vol_ratio = (128.0 / S) ** 3
+    return 1.0 / (sec * vol_ratio), sec, cores, sum(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S = 64
+    value, sec, cores, total = cpu_oracle_sample(S=S, steps=args.steps, warmup=args.warmup)
+    sample = "one oracle train_step on 1x%d^3 per step (%.2fs/step), scaled by (128/%d)^3 to 128^3 volumes" % (S, sec, S)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "VanGan.train_step 2xResUNet+2xPatchGAN, 128^3x1, global batch 8 (CPU arm: bounded sample)",
+                       "note": "TensorFlow is not installable here; the reference arm is the oracle port (torch CPU fp32) "
+                               "of the reference's train_step on the host cores"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from van_gan_b200 import _lib
+    from van_gan_b200.distribute import Strategy, init_from_env
+    from van_gan_b200.vangan import VanGan
+
+    rank, world, local = init_from_env()
+    torch.cuda.set_device(local)
+    _lib.lib()
+    G, S = args.global_batch, args.size
+    assert G % world == 0, "global batch must divide over the ranks"
+    b = G // world
+    strategy = Strategy()
+    gan = VanGan(Args(S, G, world), strategy, gen_i2s='resUnet', gen_s2i='resUnet', seed=1234)
+
+    # host-resident (pinned) shard of the synthetic global batch
+    I, Sg = synth_batch(b, S, 100 + rank)
+    hI, hS = torch.from_numpy(I).pin_memory(), torch.from_numpy(Sg).pin_memory()
+    dI, dS = hI.cuda(), hS.cuda()
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, prof=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.PROFILER = prof
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        _lib.PROFILER = None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        l2_flush.zero_()          # flush L2 between timed iterations (inputs are << L2 at b=1)
+        gan.distributed_train_step(dI, dS)
+
+    def step_e2e():
+        l2_flush.zero_()
+        gan.distributed_train_step(hI, hS)    # H2D of the shard inside; the result dict is read back (D2H)
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    prof = _lib.Profiler(["vg_conv3d_fwd", "vg_conv3d_dgrad", "vg_conv3d_wgrad", "vg_instnorm_stats", "vg_instnorm_apply",
+                          "vg_instnorm_bwd", "vg_soft_skel_fwd", "vg_soft_skel_bwd", "vg_upsample_concat", "vg_upsample_concat_bwd"])
+    l0 = _lib.lib().vg_launch_count()
+    ms = timed(step_resident, args.steps, prof)
+    launches = _lib.lib().vg_launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    fam = prof.summary()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        return
+    tf_peak, hbm_peak, peak_src = measured_peaks()
+    value = G * args.steps / (ms / 1e3)
+    e2e = G * args.steps / (ms_e2e / 1e3)
+    convs = [fam[k] for k in ("vg_conv3d_fwd", "vg_conv3d_dgrad", "vg_conv3d_wgrad") if k in fam]
+    conv_ms = sum(c["ms"] for c in convs)
+    conv_flops = sum(c["work"] for c in convs)
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
+    roofline = {"kernel": "conv3d implicit-GEMM family (fwd+dgrad+wgrad)", "bound": "tensor", "achieved": achieved,
+                "peak": tf_peak, "unit": "TFLOP/s", "frac": (achieved / tf_peak) if achieved else None, "traffic": None,
+                "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peak_src,
+                "share_of_step": conv_ms / ms if ms > 0 else None,
+                "families_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(fam.items())}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "VanGan.train_step 2xResUNet(f16,L4)+2xPatchGAN(f64), %d^3x1 volumes, global batch %d "
+                                   "(b=%d per GPU), clDice iters 15, LSGAN, Adam+clipnorm" % (S, G, b),
+                       "parallelism": "dp%d" % world, "l2": "256 MiB flush write between timed steps"},
+            "clocks": clk, "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * b * S ** 3 * 4 * world),
+                                   "d2h_bytes_per_step": int(64 * 8 * world), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    if world == 1 and not args.no_cpu_baseline:
+        v, sec, cores, _tot = cpu_oracle_sample(S=64, steps=1, warmup=0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "one oracle (torch CPU fp32) train_step on 1x64^3 (%.1fs), scaled by 8 to 128^3 volumes" % sec}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--global-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

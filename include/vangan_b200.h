@@ -29,6 +29,8 @@ enum { VG_ACT_NONE = 0, VG_ACT_RELU = 1, VG_ACT_LEAKY = 2, VG_ACT_TANH = 3 };
 enum { VG_PAD_ZERO = 0, VG_PAD_REFLECT = 1 };
 
 int vg_abi_version(void);
+/* kernels launched by this library so far (monotonic counter, for bench accounting) */
+unsigned long long vg_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Conv3D (valid convolution over an explicitly padded input; the padding itself — ReflectionPadding3D

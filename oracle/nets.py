@@ -44,6 +44,8 @@ def conv3d(x, w, b=None, stride=1, padding="valid"):
     after = total - before (the extra voxel goes AFTER).
     """
     k = w.shape[0]
+    if w.shape[3] > 1:          # Cin == 1 layers run in fp32 on CUDA cores
+        w = _qw(w)
     xt = _ncdhw(x)
     if padding == "same":
         pads = []
@@ -53,7 +55,8 @@ def conv3d(x, w, b=None, stride=1, padding="valid"):
             pads += [total // 2, total - total // 2]
         xt = F.pad(xt, pads)
     wt = w.permute(4, 3, 0, 1, 2)  # -> (Cout, Cin, kd, kh, kw)
-    return _ndhwc(F.conv3d(xt, wt, b, stride=stride))
+    y = _ndhwc(F.conv3d(xt, wt, b, stride=stride))
+    return _qa(y) if w.shape[4] > 1 else y      # single-channel outputs (head, logits) stay fp32
 
 
 def instance_norm(x, gamma, beta):
@@ -66,6 +69,49 @@ def instance_norm(x, gamma, beta):
 def upsample2(x):
     """UpSampling3D(size=2): nearest repeat along the three spatial axes."""
     return x.repeat_interleave(2, 1).repeat_interleave(2, 2).repeat_interleave(2, 3)
+
+
+# --------------------------------------------------------------------------- bf16 storage emulation
+class _RoundBoth(torch.autograd.Function):
+    """Rounds a tensor to bf16 in the forward pass AND its gradient in the backward pass: models an
+    activation that the CUDA path stores in bf16 (its gradient tensor is stored in bf16 too)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundFwd(torch.autograd.Function):
+    """bf16 operand copy of an fp32 master weight (straight-through gradient)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class Emu:
+    """Switch for the optional bf16-storage emulation.  With `Emu.on = True` the oracle rounds at
+    exactly the points where the CUDA path stores bf16 (conv outputs, normalised+padded activations,
+    tensor-core weight operands, and the matching gradient tensors).  Used by the graph-level parity
+    test: it separates "is the wiring of the four backward sweeps right" from "how much does bf16
+    cost against the fp32 reference"."""
+    on = False
+
+
+def _qa(t):
+    return _RoundBoth.apply(t) if Emu.on else t
+
+
+def _qw(w):
+    return _RoundFwd.apply(w) if Emu.on else w
 
 
 # --------------------------------------------------------------------------- parameters
@@ -151,7 +197,7 @@ def _norm_act(p, name, x, act=True):
 
 
 def _conv_block(p, name, x, stride=1):
-    y = _norm_act(p, name + ".in", x)
+    y = _qa(_norm_act(p, name + ".in", x))
     y = reflect_pad(y)
     return conv3d(y, p[name + ".conv.w"], p[name + ".conv.b"], stride=stride)
 
@@ -161,7 +207,7 @@ def _res_block(p, name, x, stride):
     res = _conv_block(p, name + ".cb2", res, 1)
     sc = conv3d(x, p[name + ".short.conv.w"], p[name + ".short.conv.b"], stride=stride, padding="same")
     sc = _norm_act(p, name + ".short.in", sc, act=False)
-    return sc + res
+    return _qa(sc + res)
 
 
 def resunet_forward(p, x, num_layers=4, taps=None):
@@ -171,7 +217,7 @@ def resunet_forward(p, x, num_layers=4, taps=None):
     conv = _conv_block(p, "stem.cb", conv)
     sc = conv3d(x, p["stem.short.conv.w"], p["stem.short.conv.b"], padding="same")
     sc = _norm_act(p, "stem.short.in", sc, act=False)
-    h = conv + sc
+    h = _qa(conv + sc)
     skips = [h]
     if taps is not None:
         taps["stem"] = h
@@ -228,17 +274,17 @@ def disc_forward(p, x, noise=None, masks=None, taps=None):
     if taps is not None:
         taps["d0"] = h
     for i in (1, 2):                                                  # :75-88 -> downsample()
-        h = nz(i, reflect_pad(h))
+        h = _qa(nz(i, reflect_pad(h)))
         h = conv3d(h, p["d%d.conv.w" % i], None, stride=2)
         h = F.leaky_relu(instance_norm(h, p["d%d.in.gamma" % i], p["d%d.in.beta" % i]), 0.2)
         h = dr(i - 1, h)
         if taps is not None:
             taps["d%d" % i] = h
-    h = nz(3, h)                                                      # :90-103, padding='same'
+    h = _qa(nz(3, h))                                                 # :90-103, padding='same'
     h = conv3d(h, p["d3.conv.w"], None, stride=1, padding="same")
     h = F.leaky_relu(instance_norm(h, p["d3.in.gamma"], p["d3.in.beta"]), 0.2)
     h = dr(2, h)
     if taps is not None:
         taps["d3"] = h
-    h = nz(4, h)                                                      # :105-114
+    h = _qa(nz(4, h))                                                 # :105-114
     return conv3d(h, p["dout.conv.w"], p["dout.conv.b"], padding="same")

@@ -185,7 +185,7 @@ def test_conv3d_fwd_dgrad_wgrad(cuda, Cin, Cout, K, stride, sp, N):
     w = torch.tensor(ON.he_normal(rng, (K, K, K, Cin, Cout)), dtype=torch.float32)
     b = torch.tensor(0.1 * rng.standard_normal(Cout), dtype=torch.float32)
     xd = x if Cin == 1 else _bf(x)
-    wd = w if (Cin == 1 or Cout == 1) else _bf(w)
+    wd = w if Cin == 1 else _bf(w)      # tensor-core layers use the bf16 operand copy of the weights
     xr, wr, br = xd.clone().requires_grad_(True), wd.clone().requires_grad_(True), b.clone().requires_grad_(True)
     y = ON.conv3d(xr, wr, br, stride=stride)
     if act == ACT_TANH:
@@ -196,18 +196,23 @@ def test_conv3d_fwd_dgrad_wgrad(cuda, Cin, Cout, K, stride, sp, N):
     y.backward(gy)
 
     net = E.Network("t", OrderedDict([("c.w", tuple(w.shape)), ("c.b", (Cout,))]))
-    net.load({"c.w": w.numpy(), "c.b": b.numpy()})
+    net.load({"c.w": wd.numpy(), "c.b": b.numpy()})
     layer = E.Conv3D(net, "c", K, stride, Cin, Cout, act=act)
     net.repack()
     tape = E.Tape()
     xv = E.Var(x.cuda() if Cin == 1 else x.to(torch.bfloat16).cuda())
     out = layer(tape, xv)
     assert out.shape == tuple(y.shape)
-    assert rel_l2(out.data.float(), y.detach()) < 1e-2
+    # operands are bf16-exact, so the only differences are fp32 summation order and the final bf16 store:
+    # compare against the oracle rounded the same way (a wrong tap / border / stride shows up as >> 1e-3)
+    yref = y.detach() if Cout == 1 else _bf(y.detach())
+    assert rel_l2(out.data.float(), yref) < 1e-3, "fwd"
+    assert rel_l2(out.data.float(), y.detach()) < 2e-2          # north_star tolerance vs the fp32 oracle
     tape.backward([(out, gy.cuda() if Cout == 1 else gy.to(torch.bfloat16).cuda())], net.trainable_variables, wrt_vars=[xv])
-    assert rel_l2(xv.grad.float(), xr.grad) < 1e-2, "dgrad"
-    assert rel_l2(net.params["c.w"].grad, wr.grad) < 1e-2, "wgrad"
-    assert rel_l2(net.params["c.b"].grad, br.grad) < 1e-2, "bias grad"
+    dxref = xr.grad if Cin == 1 else _bf(xr.grad)
+    assert rel_l2(xv.grad.float(), dxref) < (5e-3 if Cin == 1 else 1e-3), "dgrad"   # Cin==1: dgrad runs on bf16 weights
+    assert rel_l2(net.params["c.w"].grad, wr.grad) < 1e-5, "wgrad"
+    assert rel_l2(net.params["c.b"].grad, br.grad) < 1e-5, "bias grad"
 
 
 def test_upsample_concat_and_pad(cuda):

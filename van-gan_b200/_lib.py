@@ -39,6 +39,7 @@ _CD, _ID = C.POINTER(ConvDesc), C.POINTER(InDesc)
 # name -> (restype, argtypes); must list every symbol of include/vangan_b200.h (tests/test_abi.py checks)
 SIGNATURES = {
     "vg_abi_version": (_I, []),
+    "vg_launch_count": (_ULL, []),
     "vg_conv3d_packed_bytes": (_Z, [_CD, _I]),
     "vg_conv3d_pack_weights": (_I, [_CD, _P, _P, _P, _P]),
     "vg_conv3d_fwd": (_I, [_CD, _P, _P, _P, _P, _P]),
@@ -74,7 +75,27 @@ SIGNATURES = {
 }
 
 _lib = None
-LAUNCHES = 0  # number of ABI compute calls issued (bench.py reports kernel launches from this)
+LAUNCHES = 0  # number of ABI compute calls issued
+
+
+class Profiler:
+    """Optional per-family device timing (CUDA events on the launching stream) used by bench.py to
+    report the dominant kernel's achieved FLOP/s / bytes/s.  `track`: set of ABI names."""
+
+    def __init__(self, track):
+        self.track = set(track)
+        self.records = {}
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+            out[name] = dict(calls=len(recs), ms=ms, work=sum(w for _, _, w in recs))
+        return out
+
+
+PROFILER = None
 
 
 def lib():
@@ -105,12 +126,21 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args):
+def call(name, *args, work=0.0):
     """Invoke an int-returning ABI function; tensors are converted to raw device pointers and the
-    current torch stream is appended as the last argument."""
+    current torch stream is appended as the last argument.  `work`: algorithmic FLOPs (or bytes) of
+    this call, only used when a Profiler is attached."""
     global LAUNCHES
     conv = [(_ptr(a) if (a is None or torch.is_tensor(a)) else a) for a in args]
-    rc = getattr(lib(), name)(*conv, _stream())
+    prof = PROFILER
+    if prof is not None and name in prof.track:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*conv, _stream())
+        e1.record()
+        prof.records.setdefault(name, []).append((e0, e1, work))
+    else:
+        rc = getattr(lib(), name)(*conv, _stream())
     LAUNCHES += 1
     if rc != 0:
         raise VgError("%s failed: %s (%d)" % (name, _ERR.get(rc, "?"), rc))

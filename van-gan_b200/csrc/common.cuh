@@ -14,6 +14,10 @@ typedef __nv_bfloat16 bf16;
         if (e__ != cudaSuccess) return VG_ERR_CUDA;         \
     } while (0)
 
+// launch accounting (read by bench.py through vg_launch_count): every kernel launch goes through VG_LAUNCHED(n)
+extern unsigned long long g_vg_launches;
+#define VG_LAUNCHED(n) (g_vg_launches += (unsigned long long)(n))
+
 #define VG_REQUIRE(cond)                      \
     do {                                      \
         if (!(cond)) return VG_ERR_INVALID;   \

@@ -262,7 +262,7 @@ int launch_gconv_t(const GConv& p, const GCfg& c, cudaStream_t st) {
     }
     const int gtw = (p.GW + BW - 1) / BW, gth = (p.GH + BH - 1) / BH, gtd = (p.GD + BD - 1) / BD;
     dim3 grid((unsigned)((size_t)gtw * gth * gtd * p.N), (unsigned)((p.Cy + 8 * NTW - 1) / (8 * NTW)));
-    gconv_kernel<CK, NTW><<<grid, 128, c.smem, st>>>(p);
+    gconv_kernel<CK, NTW><<<grid, 128, c.smem, st>>>(p); VG_LAUNCHED(1);
     return VG_OK;
 }
 
@@ -425,7 +425,7 @@ int launch_wgrad_t(const WGrad& p, cudaStream_t st) {
     if (nsplit > p.nbricks) nsplit = p.nbricks;
     if (nsplit < 1) nsplit = 1;
     dim3 grid(nsplit, p.Cx / 16, p.Cy / (8 * NCW));
-    wgrad_kernel<TPW, NCW><<<grid, 256, 2 * stage, st>>>(p);
+    wgrad_kernel<TPW, NCW><<<grid, 256, 2 * stage, st>>>(p); VG_LAUNCHED(1);
     return VG_OK;
 }
 
@@ -504,35 +504,49 @@ __global__ void __launch_bounds__(256) cin1_fwd_kernel(const float* __restrict__
 }
 
 // wgrad, Cin == 1: dw[t][co] += sum_o x[o*s+t] * dy[o][co]
+// A task is (tap, 8 output channels); thread = (task, voxel lane).  Per voxel a thread issues one scalar
+// load of x, one 128-bit load of dy and 8 FMAs; lanes are reduced through shared memory and each block
+// finishes with one atomicAdd per output.
 __global__ void __launch_bounds__(256) cin1_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
                                                          float* __restrict__ dw, int N, int ID, int IH, int IW, int OD, int OH,
                                                          int OW, int Cout, int K, int stride, int per_block) {
-    const int T = K * K * K, TC = T * Cout;
-    size_t V = (size_t)N * OD * OH * OW;
-    size_t v0 = (size_t)blockIdx.x * per_block, v1 = v0 + per_block < V ? v0 + per_block : V;
-    constexpr int MAXO = 16;  // outputs per thread (T*Cout <= 4096)
-    float acc[MAXO];
+    extern __shared__ float sred[];   // [lanes][ntasks_pass * 8]
+    const int T = K * K * K, cg = Cout / 8, ntasks = T * cg;
+    const size_t V = (size_t)N * OD * OH * OW;
+    const size_t v0 = (size_t)blockIdx.x * per_block, v1 = v0 + per_block < V ? v0 + per_block : V;
+    for (int task0 = 0; task0 < ntasks; task0 += 256) {
+        const int tp = ntasks - task0 < 256 ? ntasks - task0 : 256;   // tasks in this pass
+        const int lanes = 256 / tp;
+        const int task = task0 + (int)threadIdx.x % tp, lane = (int)threadIdx.x / tp;
+        float acc[8];
 #pragma unroll
-    for (int k = 0; k < MAXO; k++) acc[k] = 0.f;
-    for (size_t v = v0; v < v1; v++) {
-        int ow = (int)(v % OW), oh = (int)((v / OW) % OH), od = (int)((v / ((size_t)OW * OH)) % OD);
-        int n = (int)(v / ((size_t)OW * OH * OD));
-        const float* xb = x + (((size_t)n * ID + od * stride) * IH + oh * stride) * IW + ow * stride;
-        const bf16* dr = dy + v * Cout;
+        for (int k = 0; k < 8; k++) acc[k] = 0.f;
+        if (lane < lanes) {
+            const int t = task / cg, c8 = task % cg;
+            const int kw = t % K, kh = (t / K) % K, kd = t / (K * K);
+            size_t v = v0 + lane;
+            int ow = (int)(v % OW), oh = (int)((v / OW) % OH), od = (int)((v / ((size_t)OW * OH)) % OD);
+            int n = (int)(v / ((size_t)OW * OH * OD));
+            for (; v < v1; v += lanes) {
+                const float xv = __ldg(x + (((size_t)n * ID + od * stride + kd) * IH + oh * stride + kh) * IW + ow * stride + kw);
+                float f[8];
+                load8<bf16>(dy + v * Cout + c8 * 8, f);
 #pragma unroll
-        for (int k = 0; k < MAXO; k++) {
-            int o = threadIdx.x + k * 256;
-            if (o < TC) {
-                int t = o / Cout, co = o % Cout;
-                int kw = t % K, kh = (t / K) % K, kd = t / (K * K);
-                acc[k] = fmaf(__ldg(xb + ((size_t)kd * IH + kh) * IW + kw), __bfloat162float(dr[co]), acc[k]);
+                for (int k = 0; k < 8; k++) acc[k] = fmaf(xv, f[k], acc[k]);
+                ow += lanes;
+                while (ow >= OW) { ow -= OW; if (++oh == OH) { oh = 0; if (++od == OD) { od = 0; n++; } } }
             }
-        }
-    }
 #pragma unroll
-    for (int k = 0; k < MAXO; k++) {
-        int o = threadIdx.x + k * 256;
-        if (o < TC) atomicAdd(dw + o, acc[k]);
+            for (int k = 0; k < 8; k++) sred[((size_t)lane * tp + (threadIdx.x % tp)) * 8 + k] = acc[k];
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < tp * 8; o += 256) {
+            float sum = 0.f;
+            for (int l = 0; l < lanes; l++) sum += sred[(size_t)l * tp * 8 + o];
+            int tk = task0 + o / 8;
+            atomicAdd(dw + (size_t)(tk / cg) * Cout + (tk % cg) * 8 + (o % 8), sum);
+        }
+        __syncthreads();
     }
 }
 
@@ -685,12 +699,12 @@ int vg_conv3d_pack_weights(const vg_conv3d_desc* d, const float* w, void* w_fwd,
     int T = d->K * d->K * d->K;
     if (w_fwd && d->Cin != 1) {
         int Np = rup(d->Cout, NPAD);
-        pack_fwd_kernel<<<vg_grid_for((long long)T * Np * d->Cin, 256, 4), 256, 0, st>>>(w, (bf16*)w_fwd, T, d->Cin, d->Cout, Np);
+        pack_fwd_kernel<<<vg_grid_for((long long)T * Np * d->Cin, 256, 4), 256, 0, st>>>(w, (bf16*)w_fwd, T, d->Cin, d->Cout, Np); VG_LAUNCHED(1);
     }
     if (w_dgrad && d->Cout != 1) {
         int NpI = rup(d->Cin, NPAD);
         pack_dgrad_kernel<<<vg_grid_for((long long)T * NpI * d->Cout, 256, 4), 256, 0, st>>>(w, (bf16*)w_dgrad, d->K, d->stride,
-                                                                                          d->Cin, d->Cout, NpI);
+                                                                                          d->Cin, d->Cout, NpI); VG_LAUNCHED(1);
     }
     VG_CHECK_LAUNCH();
     return VG_OK;
@@ -706,7 +720,7 @@ int vg_conv3d_fwd(const vg_conv3d_desc* d, const void* x, const void* w_fwd, con
         size_t smem = ((size_t)T * d->Cout + d->Cout) * sizeof(float);
         size_t total = (size_t)d->N * OD * OH * OW * (d->Cout / 8);
         cin1_fwd_kernel<<<vg_grid_for(total, 256, 16), 256, smem, st>>>((const float*)x, (const float*)w_fwd, bias, (bf16*)y, d->N,
-                                                                       d->ID, d->IH, d->IW, OD, OH, OW, d->Cout, d->K, d->stride);
+                                                                       d->ID, d->IH, d->IW, OD, OH, OW, d->Cout, d->K, d->stride); VG_LAUNCHED(1);
         VG_CHECK_LAUNCH();
         return VG_OK;
     }
@@ -733,7 +747,7 @@ int vg_conv3d_dgrad(const vg_conv3d_desc* d, const void* dy, const void* w_dgrad
         VG_REQUIRE(d->stride == 1 && d->Cin % 8 == 0);
         size_t total = (size_t)d->N * d->ID * d->IH * d->IW * (d->Cin / 8);
         cout1_dgrad_kernel<<<vg_grid_for(total, 256, 16), 256, 0, st>>>((const float*)dy, (const float*)w_dgrad, (bf16*)dx, d->N,
-                                                                       d->ID, d->IH, d->IW, OD, OH, OW, d->Cin, d->K);
+                                                                       d->ID, d->IH, d->IW, OD, OH, OW, d->Cin, d->K); VG_LAUNCHED(1);
         VG_CHECK_LAUNCH();
         return VG_OK;
     }
@@ -773,18 +787,20 @@ int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, floa
     const int OD = odim(d->ID, d->K, d->stride), OH = odim(d->IH, d->K, d->stride), OW = odim(d->IW, d->K, d->stride);
     const size_t rows = (size_t)d->N * OD * OH * OW;
     if (dbias) {
-        if (d->Cout == 1)
-            channel_sum_kernel<float><<<vg_grid_for(rows, 256, 2), 256, 32 * sizeof(float), st>>>((const float*)dy, rows, 1, dbias);
-        else
+        if (d->Cout == 1) {
+            channel_sum_kernel<float><<<vg_grid_for(rows, 256, 2), 256, 32 * sizeof(float), st>>>((const float*)dy, rows, 1, dbias); VG_LAUNCHED(1);
+        }
+        else {
             channel_sum_kernel<bf16><<<vg_grid_for(rows, 32, 2), 256, (size_t)(256 / (d->Cout / 8)) * d->Cout * sizeof(float), st>>>(
-                (const bf16*)dy, rows, d->Cout, dbias);
+                (const bf16*)dy, rows, d->Cout, dbias); VG_LAUNCHED(1);
+        }
     }
     if (d->Cin == 1) {
-        VG_REQUIRE(d->K * d->K * d->K * d->Cout <= 4096);
+        VG_REQUIRE(d->Cout % 8 == 0);
         int per_block = (int)((rows + 148 * 8 - 1) / (148 * 8));
-        if (per_block < 64) per_block = 64;
-        cin1_wgrad_kernel<<<vg_cdiv(rows, per_block), 256, 0, st>>>((const float*)x, (const bf16*)dy, dw, d->N, d->ID, d->IH, d->IW,
-                                                                   OD, OH, OW, d->Cout, d->K, d->stride, per_block);
+        if (per_block < 256) per_block = 256;
+        cin1_wgrad_kernel<<<vg_cdiv(rows, per_block), 256, 256 * 8 * sizeof(float), st>>>((const float*)x, (const bf16*)dy, dw, d->N, d->ID, d->IH, d->IW,
+                                                                   OD, OH, OW, d->Cout, d->K, d->stride, per_block); VG_LAUNCHED(1);
         VG_CHECK_LAUNCH();
         return VG_OK;
     }
@@ -796,7 +812,7 @@ int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, floa
         if (per_block < 32) per_block = 32;
         size_t smem = (size_t)(256 / (d->Cin / 8)) * d->Cin * sizeof(float);
         cout1_wgrad_kernel<<<dim3(vg_cdiv(rows, per_block), T), 256, smem, st>>>((const bf16*)x, (const float*)dy, dw, d->N, d->ID,
-                                                                                d->IH, d->IW, OD, OH, OW, d->Cin, d->K, per_block);
+                                                                                d->IH, d->IW, OD, OH, OW, d->Cin, d->K, per_block); VG_LAUNCHED(1);
         VG_CHECK_LAUNCH();
         return VG_OK;
     }

@@ -72,24 +72,30 @@ __global__ void __launch_bounds__(NT) in_stats_partial_kernel(const T* __restric
     }
 }
 
+// one warp per (n,c): lanes stride over the block partials, shuffle-reduce in double
 template <typename T>
-__global__ void in_stats_final_kernel(const T* __restrict__ x, const float* __restrict__ partial, size_t V, int C, int nblk,
-                                      int N, float* __restrict__ mean, float* __restrict__ rstd) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) in_stats_final_kernel(const T* __restrict__ x, const float* __restrict__ partial,
+                                                             size_t V, int C, int nblk, int N, float* __restrict__ mean,
+                                                             float* __restrict__ rstd) {
+    int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= N * C) return;
     int n = i / C, c = i % C;
     double s1 = 0, s2 = 0;
-    for (int b = 0; b < nblk; b++) {
+    for (int b = lane; b < nblk; b += 32) {
         const float* p = partial + (((size_t)n * nblk + b) * C + c) * 2;
         s1 += p[0];
         s2 += p[1];
     }
-    double shift = (double)(float)x[(size_t)n * V * C + c];
-    double m = s1 / (double)V;
-    double var = s2 / (double)V - m * m;
-    if (var < 0) var = 0;
-    mean[i] = (float)(shift + m);
-    rstd[i] = (float)(1.0 / sqrt(var + (double)IN_EPS));
+    s1 = warp_sum_d(s1);
+    s2 = warp_sum_d(s2);
+    if (lane == 0) {
+        double shift = (double)(float)x[(size_t)n * V * C + c];
+        double m = s1 / (double)V;
+        double var = s2 / (double)V - m * m;
+        if (var < 0) var = 0;
+        mean[i] = (float)(shift + m);
+        rstd[i] = (float)(1.0 / sqrt(var + (double)IN_EPS));
+    }
 }
 
 // ------------------------------------------------------------------ forward apply
@@ -246,26 +252,27 @@ __global__ void __launch_bounds__(NT) in_bwd_partial_kernel(const T* __restrict_
     }
 }
 
-// sums[(n*C+c)*2+{0,1}] = S1, S2; dgamma[c] += sum_n S2, dbeta[c] += sum_n S1  (one thread per channel)
-__global__ void in_bwd_final_kernel(const float* __restrict__ partial, int nblk, int N, int C, float* __restrict__ sums,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double g1 = 0, g2 = 0;
-    for (int n = 0; n < N; n++) {
-        double s1 = 0, s2 = 0;
-        for (int b = 0; b < nblk; b++) {
-            const float* p = partial + (((size_t)n * nblk + b) * C + c) * 2;
-            s1 += p[0];
-            s2 += p[1];
-        }
-        sums[((size_t)n * C + c) * 2] = (float)s1;
-        sums[((size_t)n * C + c) * 2 + 1] = (float)s2;
-        g1 += s1;
-        g2 += s2;
+// sums[(n*C+c)*2+{0,1}] = S1, S2; dgamma[c] += S2, dbeta[c] += S1  (one warp per (n,c); N <= a few atomics per channel)
+__global__ void __launch_bounds__(256) in_bwd_final_kernel(const float* __restrict__ partial, int nblk, int N, int C,
+                                                           float* __restrict__ sums, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta) {
+    int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= N * C) return;
+    int n = i / C, c = i % C;
+    double s1 = 0, s2 = 0;
+    for (int b = lane; b < nblk; b += 32) {
+        const float* p = partial + (((size_t)n * nblk + b) * C + c) * 2;
+        s1 += p[0];
+        s2 += p[1];
     }
-    if (dgamma) dgamma[c] += (float)g2;
-    if (dbeta) dbeta[c] += (float)g1;
+    s1 = warp_sum_d(s1);
+    s2 = warp_sum_d(s2);
+    if (lane == 0) {
+        sums[(size_t)i * 2] = (float)s1;
+        sums[(size_t)i * 2 + 1] = (float)s2;
+        if (dgamma) atomicAdd(dgamma + c, (float)s2);
+        if (dbeta) atomicAdd(dbeta + c, (float)s1);
+    }
 }
 
 // dx = gamma*rstd*(g - S1/V - xhat*S2/V); dres = fold(dy) (optional)
@@ -317,8 +324,8 @@ int stats_impl(const T* x, int N, size_t V, int C, float* mean, float* rstd, voi
     if (ws_bytes < need) return VG_ERR_WORKSPACE;
     int cg = C / 8, nvl = NT / cg;
     size_t smem = (size_t)nvl * C * 2 * sizeof(float);
-    in_stats_partial_kernel<T><<<dim3(nblk, N), NT, smem, st>>>(x, V, C, nblk, (float*)ws);
-    in_stats_final_kernel<T><<<vg_cdiv(N * C, 128), 128, 0, st>>>(x, (const float*)ws, V, C, nblk, N, mean, rstd);
+    in_stats_partial_kernel<T><<<dim3(nblk, N), NT, smem, st>>>(x, V, C, nblk, (float*)ws); VG_LAUNCHED(1);
+    in_stats_final_kernel<T><<<vg_cdiv(N * C, 8), 256, 0, st>>>(x, (const float*)ws, V, C, nblk, N, mean, rstd); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -355,10 +362,12 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
     size_t total = (size_t)d->N * P * (d->C / 8);
     int grid = vg_grid_for(total, NT, 16);
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->dtype == VG_BF16)
-        in_apply_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, g, a);
-    else if (d->dtype == VG_F32)
-        in_apply_kernel<float><<<grid, NT, 0, st>>>((const float*)x, (const float*)residual, (float*)y, g, a);
+    if (d->dtype == VG_BF16) {
+        in_apply_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, g, a); VG_LAUNCHED(1);
+    }
+    else if (d->dtype == VG_F32) {
+        in_apply_kernel<float><<<grid, NT, 0, st>>>((const float*)x, (const float*)residual, (float*)y, g, a); VG_LAUNCHED(1);
+    }
     else
         return VG_ERR_INVALID;
     VG_CHECK_LAUNCH();
@@ -386,15 +395,15 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
     int grid = vg_grid_for(total, NT, 16);
     cudaStream_t st = (cudaStream_t)stream;
     if (d->dtype == VG_BF16) {
-        in_bwd_partial_kernel<bf16><<<dim3(nblk, d->N), NT, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, nblk, partial);
-        in_bwd_final_kernel<<<vg_cdiv(d->C, 64), 64, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta);
+        in_bwd_partial_kernel<bf16><<<dim3(nblk, d->N), NT, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, nblk, partial); VG_LAUNCHED(1);
+        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta); VG_LAUNCHED(1);
         in_bwd_apply_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres,
-                                                      accumulate_dx);
+                                                      accumulate_dx); VG_LAUNCHED(1);
     } else if (d->dtype == VG_F32) {
-        in_bwd_partial_kernel<float><<<dim3(nblk, d->N), NT, smem, st>>>((const float*)dy, (const float*)x, g, a, nblk, partial);
-        in_bwd_final_kernel<<<vg_cdiv(d->C, 64), 64, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta);
+        in_bwd_partial_kernel<float><<<dim3(nblk, d->N), NT, smem, st>>>((const float*)dy, (const float*)x, g, a, nblk, partial); VG_LAUNCHED(1);
+        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta); VG_LAUNCHED(1);
         in_bwd_apply_kernel<float><<<grid, NT, 0, st>>>((const float*)dy, (const float*)x, g, a, sums, (float*)dx, (float*)dres,
-                                                       accumulate_dx);
+                                                       accumulate_dx); VG_LAUNCHED(1);
     } else {
         return VG_ERR_INVALID;
     }

@@ -329,16 +329,16 @@ int vg_minmax(const float* x, int N, size_t V, float* mm, void* enc_ws, void* st
     VG_REQUIRE(x && mm && enc_ws && N > 0 && V > 0);
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* enc = (uint32_t*)enc_ws;
-    minmax_init_kernel<<<vg_cdiv(N, 128), 128, 0, st>>>(enc, N);
-    minmax_kernel<<<grid2(V, N), NT, 0, st>>>(x, V, enc);
-    minmax_decode_kernel<<<vg_cdiv(2 * N, 128), 128, 0, st>>>(enc, mm, N);
+    minmax_init_kernel<<<vg_cdiv(N, 128), 128, 0, st>>>(enc, N); VG_LAUNCHED(1);
+    minmax_kernel<<<grid2(V, N), NT, 0, st>>>(x, V, enc); VG_LAUNCHED(1);
+    minmax_decode_kernel<<<vg_cdiv(2 * N, 128), 128, 0, st>>>(enc, mm, N); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
 
 int vg_minmax_normalize(const float* x, const float* mm, float* out, int N, size_t V, void* stream) {
     VG_REQUIRE(x && mm && out && N > 0);
-    normalize_kernel<<<grid2(V, N), NT, 0, (cudaStream_t)stream>>>(x, mm, out, V);
+    normalize_kernel<<<grid2(V, N), NT, 0, (cudaStream_t)stream>>>(x, mm, out, V); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -349,15 +349,15 @@ int vg_minmax_normalize_bwd(const float* x, const float* nrm, const float* mm, c
     VG_REQUIRE(x && nrm && mm && g && dx && acc_ws);
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(acc_ws, 0, (size_t)N * 4 * sizeof(double), st) != cudaSuccess) return VG_ERR_CUDA;
-    mmnorm_bwd_reduce_kernel<<<grid2(V, N), NT, 0, st>>>(x, nrm, mm, g, V, (double*)acc_ws);
-    mmnorm_bwd_apply_kernel<<<grid2(V, N), NT, 0, st>>>(x, mm, g, (const double*)acc_ws, dx, V, accumulate);
+    mmnorm_bwd_reduce_kernel<<<grid2(V, N), NT, 0, st>>>(x, nrm, mm, g, V, (double*)acc_ws); VG_LAUNCHED(1);
+    mmnorm_bwd_apply_kernel<<<grid2(V, N), NT, 0, st>>>(x, mm, g, (const double*)acc_ws, dx, V, accumulate); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
 
 int vg_sqdiff_sum(const float* a, const float* b, float target, size_t n, double* acc, void* stream) {
     VG_REQUIRE(a && acc);
-    sqdiff_sum_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(a, b, target, n, acc);
+    sqdiff_sum_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(a, b, target, n, acc); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -365,21 +365,21 @@ int vg_sqdiff_sum(const float* a, const float* b, float target, size_t n, double
 int vg_lincomb(float* out, size_t n, int accumulate, float c0, const float* x1, float c1, const float* x2, float c2,
                const float* x3, float c3, void* stream) {
     VG_REQUIRE(out);
-    lincomb_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(out, n, accumulate, c0, x1, c1, x2, c2, x3, c3);
+    lincomb_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(out, n, accumulate, c0, x1, c1, x2, c2, x3, c3); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
 
 int vg_bce_sum(const float* y_true, const float* y_pred, size_t n, double* acc, void* stream) {
     VG_REQUIRE(y_true && y_pred && acc);
-    bce_sum_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(y_true, y_pred, n, acc);
+    bce_sum_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(y_true, y_pred, n, acc); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
 
 int vg_bce_bwd(const float* y_true, const float* y_pred, float coef, float* g, size_t n, int accumulate, void* stream) {
     VG_REQUIRE(y_true && y_pred && g);
-    bce_bwd_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(y_true, y_pred, coef, g, n, accumulate);
+    bce_bwd_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(y_true, y_pred, coef, g, n, accumulate); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -387,7 +387,7 @@ int vg_bce_bwd(const float* y_true, const float* y_pred, float coef, float* g, s
 int vg_cldice_sums(const float* y_true, const float* y_pred, const float* skel_true, const float* skel_pred, size_t n,
                    double* acc7, void* stream) {
     VG_REQUIRE(y_true && y_pred && skel_true && skel_pred && acc7);
-    cldice_sums_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(y_true, y_pred, skel_true, skel_pred, n, acc7);
+    cldice_sums_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(y_true, y_pred, skel_true, skel_pred, n, acc7); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -398,7 +398,7 @@ int vg_ssim_fwd(const float* t, const float* p, int N, int D, int H, int W, doub
     VG_REQUIRE(t && p && acc && N > 0);
     VG_REQUIRE((mA && mB && mC) || (!mA && !mB && !mC));
     int tx = vg_cdiv(W, SX), ty = vg_cdiv(H, SY), tz = vg_cdiv(D, SZ);
-    ssim_fwd_kernel<<<tx * ty * tz * N, NT, 0, (cudaStream_t)stream>>>(t, p, D, H, W, make_taps(), acc, mA, mB, mC, tx, ty, tz);
+    ssim_fwd_kernel<<<tx * ty * tz * N, NT, 0, (cudaStream_t)stream>>>(t, p, D, H, W, make_taps(), acc, mA, mB, mC, tx, ty, tz); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -409,7 +409,7 @@ int vg_ssim_bwd(const float* t, const float* p, const float* mA, const float* mB
     VG_REQUIRE(t && p && mA && mB && mC && gp);
     int tx = vg_cdiv(W, SX), ty = vg_cdiv(H, SY), tz = vg_cdiv(D, SZ);
     ssim_bwd_kernel<<<tx * ty * tz * N, NT, 0, (cudaStream_t)stream>>>(t, p, mA, mB, mC, D, H, W, make_taps(), coef, gp,
-                                                                      accumulate, tx, ty, tz);
+                                                                      accumulate, tx, ty, tz); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }

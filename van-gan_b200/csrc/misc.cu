@@ -7,6 +7,8 @@
 // (custom_callback.py:165-166,177-183,192,202).
 #include "common.cuh"
 
+unsigned long long g_vg_launches = 0;
+
 namespace {
 
 constexpr int NT = 256;
@@ -140,18 +142,37 @@ __global__ void __launch_bounds__(NT) tanh_bwd_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------ clip-by-norm + Adam
-__global__ void __launch_bounds__(NT) seg_sqnorm_kernel(const float* __restrict__ g, const long long* __restrict__ off, int nseg,
-                                                        double* __restrict__ norms, int blocks_per_seg) {
-    int seg = blockIdx.x / blocks_per_seg, sub = blockIdx.x % blocks_per_seg;
-    long long a = off[seg], b = off[seg + 1];
-    double s = 0;
-    for (long long i = a + (long long)sub * NT + threadIdx.x; i < b; i += (long long)blocks_per_seg * NT) {
-        float v = g[i];
-        s += (double)v * v;
+__device__ __forceinline__ int find_seg(const long long* __restrict__ off, int nseg, long long i) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid - 1;
     }
-    __shared__ double sh[32];
-    s = block_sum_d(s, sh);
-    if (threadIdx.x == 0 && s != 0.0) atomicAdd(norms + seg, s);
+    return lo;
+}
+
+// per-variable squared norms: flat grid-stride pass; a warp that sits inside one variable issues one atomic
+__global__ void __launch_bounds__(NT) seg_sqnorm_kernel(const float* __restrict__ g, const long long* __restrict__ off, int nseg,
+                                                        double* __restrict__ norms, long long total) {
+    for (long long base = ((long long)blockIdx.x * NT + (threadIdx.x & ~31)) * 4; base < total; base += (long long)gridDim.x * NT * 4) {
+        // each warp owns 128 consecutive elements
+        int s0 = find_seg(off, nseg, base);
+        long long end = base + 128 < total ? base + 128 : total;
+        bool uniform = off[s0 + 1] >= end;
+        double acc = 0;
+        for (int k = 0; k < 4; k++) {
+            long long i = base + k * 32 + (threadIdx.x & 31);
+            if (i < total) {
+                float v = g[i];
+                if (uniform) acc += (double)v * v;
+                else atomicAdd(norms + find_seg(off, nseg, i), (double)v * v);
+            }
+        }
+        if (uniform) {
+            acc = warp_sum_d(acc);
+            if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(norms + s0, acc);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(NT) clip_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
@@ -159,12 +180,7 @@ __global__ void __launch_bounds__(NT) clip_adam_kernel(float* __restrict__ w, co
                                                        const double* __restrict__ norms, float lr_t, float b1, float b2,
                                                        float eps, float clip, long long total) {
     for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        // binary search of the segment containing i
-        int lo = 0, hi = nseg - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (off[mid] <= i) lo = mid; else hi = mid - 1;
-        }
+        int lo = find_seg(off, nseg, i);
         float nrm = (float)sqrt(norms[lo]);
         float scale = clip / fmaxf(nrm, clip);   // tf.clip_by_norm
         float gi = g[i] * scale;
@@ -238,11 +254,14 @@ __global__ void __launch_bounds__(NT) stitch_scale_kernel(float* __restrict__ ou
 
 extern "C" {
 
+// number of kernels this library has launched so far (monotonic; bench.py reports the difference)
+unsigned long long vg_launch_count(void) { return g_vg_launches; }
+
 int vg_upsample_concat(const void* lo, const void* skip, void* out, int N, int D, int H, int W, int C0, int C1, void* stream) {
     VG_REQUIRE(lo && skip && out && C0 % 8 == 0 && C1 % 8 == 0 && N > 0);
     size_t total = (size_t)N * 8 * D * H * W * ((C0 + C1) / 8);
     upsample_concat_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>((const bf16*)lo, (const bf16*)skip, (bf16*)out,
-                                                                                       N, D, H, W, C0, C1);
+                                                                                       N, D, H, W, C0, C1); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -252,9 +271,9 @@ int vg_upsample_concat_bwd(const void* dcat, void* dlo, void* dskip, int accumul
     VG_REQUIRE(dcat && dlo && dskip && C0 % 8 == 0 && C1 % 8 == 0);
     cudaStream_t st = (cudaStream_t)stream;
     size_t t0 = (size_t)N * D * H * W * (C0 / 8), V2 = (size_t)N * 8 * D * H * W;
-    upsample_concat_bwd_lo_kernel<<<vg_grid_for(t0, NT, 16), NT, 0, st>>>((const bf16*)dcat, (bf16*)dlo, N, D, H, W, C0, C1);
+    upsample_concat_bwd_lo_kernel<<<vg_grid_for(t0, NT, 16), NT, 0, st>>>((const bf16*)dcat, (bf16*)dlo, N, D, H, W, C0, C1); VG_LAUNCHED(1);
     upsample_concat_bwd_skip_kernel<<<vg_grid_for(V2 * (C1 / 8), NT, 16), NT, 0, st>>>((const bf16*)dcat, (bf16*)dskip, V2, C0, C1,
-                                                                                      accumulate_skip);
+                                                                                      accumulate_skip); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -263,7 +282,7 @@ int vg_pad_noise(const float* x, float* y, int N, int D, int H, int W, const flo
                  unsigned long long seed, void* stream) {
     VG_REQUIRE(x && y && D >= 2 && H >= 2 && W >= 2);
     size_t total = (size_t)N * (D + 2) * (H + 2) * (W + 2);
-    pad_noise_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(x, y, N, D, H, W, noise, noise_std, seed);
+    pad_noise_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(x, y, N, D, H, W, noise, noise_std, seed); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -271,7 +290,7 @@ int vg_pad_noise(const float* x, float* y, int N, int D, int H, int W, const flo
 int vg_pad_fold(const float* dy, float* dx, int N, int D, int H, int W, int accumulate, void* stream) {
     VG_REQUIRE(dy && dx);
     size_t total = (size_t)N * D * H * W;
-    pad_fold_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(dy, dx, N, D, H, W, accumulate);
+    pad_fold_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(dy, dx, N, D, H, W, accumulate); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -280,10 +299,12 @@ int vg_accumulate(void* a, const void* b, size_t n, int dtype, void* stream) {
     VG_REQUIRE(a && b);
     cudaStream_t st = (cudaStream_t)stream;
     size_t n8 = n / 8;
-    if (dtype == VG_BF16)
-        accumulate_kernel<bf16><<<vg_grid_for(n8 + 1, NT, 16), NT, 0, st>>>((bf16*)a, (const bf16*)b, n8, n);
-    else if (dtype == VG_F32)
-        accumulate_kernel<float><<<vg_grid_for(n8 + 1, NT, 16), NT, 0, st>>>((float*)a, (const float*)b, n8, n);
+    if (dtype == VG_BF16) {
+        accumulate_kernel<bf16><<<vg_grid_for(n8 + 1, NT, 16), NT, 0, st>>>((bf16*)a, (const bf16*)b, n8, n); VG_LAUNCHED(1);
+    }
+    else if (dtype == VG_F32) {
+        accumulate_kernel<float><<<vg_grid_for(n8 + 1, NT, 16), NT, 0, st>>>((float*)a, (const float*)b, n8, n); VG_LAUNCHED(1);
+    }
     else
         return VG_ERR_INVALID;
     VG_CHECK_LAUNCH();
@@ -292,7 +313,7 @@ int vg_accumulate(void* a, const void* b, size_t n, int dtype, void* stream) {
 
 int vg_tanh_bwd(const float* dy, const float* y, float* out, size_t n, void* stream) {
     VG_REQUIRE(dy && y && out);
-    tanh_bwd_kernel<<<vg_grid_for(n, NT * 2, 8), NT, 0, (cudaStream_t)stream>>>(dy, y, out, n);
+    tanh_bwd_kernel<<<vg_grid_for(n, NT * 2, 8), NT, 0, (cudaStream_t)stream>>>(dy, y, out, n); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -303,10 +324,9 @@ int vg_clip_adam_step(float* w, const float* g, float* m, float* v, const long l
     VG_REQUIRE(w && g && m && v && seg_offsets && nseg > 0 && total > 0 && norm_ws);
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(norm_ws, 0, (size_t)nseg * sizeof(double), st) != cudaSuccess) return VG_ERR_CUDA;
-    const int bps = 8;
-    seg_sqnorm_kernel<<<nseg * bps, NT, 0, st>>>(g, seg_offsets, nseg, norm_ws, bps);
+    seg_sqnorm_kernel<<<vg_grid_for(total / 4 + 1, NT, 8), NT, 0, st>>>(g, seg_offsets, nseg, norm_ws, total); VG_LAUNCHED(1);
     clip_adam_kernel<<<vg_grid_for(total, NT, 16), NT, 0, st>>>(w, g, m, v, seg_offsets, nseg, norm_ws, lr_t, beta1, beta2, eps,
-                                                               clipnorm, total);
+                                                               clipnorm, total); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -316,7 +336,7 @@ int vg_stitch_accumulate(float* pred, float* cnt, int H, int W, int D, const flo
     VG_REQUIRE(pred && cnt && win && starts && B > 0);
     size_t total = (size_t)B * (kH - 2 * pH) * (kW - 2 * pW) * (kD - 2 * pD);
     stitch_accumulate_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(pred, cnt, H, W, D, win, starts, B, kH, kW,
-                                                                                         kD, pH, pW, pD);
+                                                                                         kD, pH, pW, pD); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -325,17 +345,17 @@ int vg_stitch_finalize(const float* pred, const float* cnt, int H, int W, int D,
                        float* out, float* mm, void* enc_ws, void* stream) {
     VG_REQUIRE(pred && cnt && out && mm && enc_ws);
     cudaStream_t st = (cudaStream_t)stream;
-    stitch_init_kernel<<<1, 1, 0, st>>>((uint32_t*)enc_ws);
+    stitch_init_kernel<<<1, 1, 0, st>>>((uint32_t*)enc_ws); VG_LAUNCHED(1);
     stitch_divide_kernel<<<vg_grid_for((size_t)oH * oW * oD, NT, 16), NT, 0, st>>>(pred, cnt, H, W, D, x0, y0, z0, oH, oW, oD, out,
-                                                                                  (uint32_t*)enc_ws);
-    stitch_decode_kernel<<<1, 1, 0, st>>>((const uint32_t*)enc_ws, mm);
+                                                                                  (uint32_t*)enc_ws); VG_LAUNCHED(1);
+    stitch_decode_kernel<<<1, 1, 0, st>>>((const uint32_t*)enc_ws, mm); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
 
 int vg_stitch_scale(float* out, size_t n, const float* mm, void* stream) {
     VG_REQUIRE(out && mm);
-    stitch_scale_kernel<<<vg_grid_for(n, NT, 16), NT, 0, (cudaStream_t)stream>>>(out, n, mm);
+    stitch_scale_kernel<<<vg_grid_for(n, NT, 16), NT, 0, (cudaStream_t)stream>>>(out, n, mm); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }

@@ -241,7 +241,7 @@ int vg_soft_skel_fwd(const float* x, float* E, float* S, int N, int D, int H, in
     for (int j = 0; j <= iters; j++) {
         skel_level_fwd_kernel<<<blocks, NTHREADS, 0, st>>>(E + (size_t)j * nv, E + (size_t)(j + 1) * nv,
                                                           j ? S + (size_t)(j - 1) * nv : nullptr, S + (size_t)j * nv, v,
-                                                          tx, ty, tz, j == 0);
+                                                          tx, ty, tz, j == 0); VG_LAUNCHED(1);
     }
     VG_CHECK_LAUNCH();
     return VG_OK;
@@ -271,21 +271,21 @@ int vg_soft_skel_bwd(const float* E, const float* S, const float* gskel, float* 
     // a_j lives in Ab[j&1]; G_{j} (for j<k) in Gb[j&1]; D_j in Db[j&1]
     const float* Gcur = gskel;
     skel_bwd_coeff_kernel<<<blocks, NTHREADS, 0, st>>>(Gcur, k ? S + (size_t)(k - 1) * nv : nullptr, Ej(k), Ej(k + 1),
-                                                       Ab[k & 1], Gb[(k + 1) & 1], v, tx, ty, tz, k == 0);
+                                                       Ab[k & 1], Gb[(k + 1) & 1], v, tx, ty, tz, k == 0); VG_LAUNCHED(1);
     Gcur = Gb[(k + 1) & 1];  // now holds G_{k-1}
     skel_bwd_route_kernel<<<blocks, NTHREADS, ROUTE_SMEM, st>>>(Ej(k + 1), nullptr, nullptr, Ab[k & 1], Db[(k + 1) & 1], v, tx, ty,
-                                                       tz);
+                                                       tz); VG_LAUNCHED(1);
     for (int j = k; j >= 0; j--) {
         if (j >= 1) {
             int jj = j - 1;
             skel_bwd_coeff_kernel<<<blocks, NTHREADS, 0, st>>>(Gcur, jj ? S + (size_t)(jj - 1) * nv : nullptr, Ej(jj),
                                                                Ej(jj + 1), Ab[jj & 1], Gb[(jj + 1) & 1], v, tx, ty, tz,
-                                                               jj == 0);
+                                                               jj == 0); VG_LAUNCHED(1);
             Gcur = Gb[(jj + 1) & 1];
         }
         float* out = j == 0 ? dx : Db[j & 1];
         skel_bwd_route_kernel<<<blocks, NTHREADS, ROUTE_SMEM, st>>>(Ej(j), Ab[j & 1], Db[(j + 1) & 1], j >= 1 ? Ab[(j - 1) & 1] : nullptr,
-                                                           out, v, tx, ty, tz);
+                                                           out, v, tx, ty, tz); VG_LAUNCHED(1);
     }
     VG_CHECK_LAUNCH();
     return VG_OK;

@@ -61,6 +61,17 @@ class Tape:
                 o.src = node
             self.nodes.append(node)
 
+    def clear(self):
+        """Break the Var <-> Node reference cycles so the step's activations are released immediately
+        (by reference counting, without waiting for Python's cyclic GC)."""
+        for node in self.nodes:
+            for o in node.outputs:
+                o.src = None
+                o.grad = None
+            node.bwd = None
+            node.inputs = node.outputs = node.params = ()
+        self.nodes = []
+
     def backward(self, seeds, wrt_params, wrt_vars=()):
         """seeds: list of (Var, grad tensor).  wrt_params: Param objects whose .grad views receive
         (+=) the gradients; wrt_vars: leaf Vars whose .grad is wanted as well (kept after the sweep).
@@ -222,7 +233,9 @@ class Conv3D:
         od, oh, ow = [(s - self.k) // self.stride + 1 for s in (d, h, w)]
         y = torch.empty((n, od, oh, ow, self.cout), device=DEV,
                         dtype=torch.float32 if self.cout == 1 else torch.bfloat16)
-        call("vg_conv3d_fwd", desc, x.data, self.w.w if self.cin == 1 else self.wf, self.b.w if self.b else None, y)
+        flops = 2.0 * self.k ** 3 * self.cin * self.cout * n * od * oh * ow
+        call("vg_conv3d_fwd", desc, x.data, self.w.w if self.cin == 1 else self.wf, self.b.w if self.b else None, y,
+             work=flops)
         out = Var(y)
 
         def bwd(in_needs, p_needs):
@@ -232,10 +245,10 @@ class Conv3D:
                 call("vg_tanh_bwd", dy, out.data, t, dy.numel())
                 dy = t
             if p_needs:
-                call("vg_conv3d_wgrad", desc, x.data, dy, self.w.grad, self.b.grad if self.b else None)
+                call("vg_conv3d_wgrad", desc, x.data, dy, self.w.grad, self.b.grad if self.b else None, work=flops)
             if in_needs[0]:
                 dx = torch.empty_like(x.data)
-                call("vg_conv3d_dgrad", desc, dy, self.w.w if self.cout == 1 else self.wd, dx)
+                call("vg_conv3d_dgrad", desc, dy, self.w.w if self.cout == 1 else self.wd, dx, work=flops)
                 accumulate(x, dx)
 
         tape.record([x], [out], [self.w] + ([self.b] if self.b else []), bwd, "conv")

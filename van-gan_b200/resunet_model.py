@@ -83,21 +83,30 @@ class ResUNetModel(E.Network):
         if seed is not None:
             self.load(E.default_init({n: p.shape for n, p in self.params.items()}, seed))
 
-    def forward(self, tape, x):
-        """x: Var holding an (N,D,H,W,1) fp32 volume.  Returns the (N,D,H,W,1) fp32 tanh output."""
+    def forward(self, tape, x, taps=None):
+        """x: Var holding an (N,D,H,W,1) fp32 volume.  Returns the (N,D,H,W,1) fp32 tanh output.
+        `taps`: optional dict receiving the block outputs (layer-wise parity tests)."""
         conv = self.stem_conv0(tape, E.pad_noise(tape, x))           # stem(), resunet_model.py:87-91
         conv = self.stem_cb(tape, conv)
         sc = self.stem_short(tape, x)
         h = self.stem_short_norm(tape, sc, act=ACT_NONE, residual=conv)
         skips = [h]
-        for blk in self.enc:
+        if taps is not None:
+            taps["stem"] = h
+        for e, blk in enumerate(self.enc):
             h = blk(tape, h)
             skips.append(h)
+            if taps is not None:
+                taps["enc%d" % (e + 1)] = h
         for blk in self.bridge:
             h = blk(tape, h)
+        if taps is not None:
+            taps["bridge"] = h
         for d in reversed(range(self.num_layers)):
             h = E.upsample_concat(tape, h, skips[d])
             h = self.dec[d](tape, h)
+            if taps is not None:
+                taps["dec%d" % d] = h
         return self.head(tape, h)
 
     def __call__(self, x, training=False):

@@ -55,6 +55,9 @@ class VanGan:
         self.cldice_iters = 15
         self.step = 0
         self.loss_ctx = None
+        self.tape = None
+        self.last = None
+        self.keep_last = False   # tests set this to inspect fake/cycled volumes after a step
 
         with self.strategy.scope():
             if gen_i2s != 'resUnet' or gen_s2i != 'resUnet':
@@ -151,16 +154,28 @@ class VanGan:
                 if h is not None:
                     h.wait()
         self.step += 1
-        self.tape = None
         vals = self.loss_ctx.values()
-        return {k: float(v.value_fn(vals)) for k, v in result.items()}
+        out = {k: float(v.value_fn(vals)) for k, v in result.items()}
+        self._release()
+        return out
+
+    def _release(self):
+        """Drop the step's tape, loss scratch and (unless keep_last) the generated volumes."""
+        if self.tape is not None:
+            self.tape.clear()
+        self.tape = None
+        self.loss_ctx = None
+        if not self.keep_last:
+            self.last = None
 
     def test_step(self, real_I, real_S):
         """vangan.py:442-457."""
         result = {}
         result, *_ = self.compute_losses(real_I, real_S, result, training=False)
         vals = self.loss_ctx.values()
-        return {k: float(v.value_fn(vals)) for k, v in result.items()}
+        out = {k: float(v.value_fn(vals)) for k, v in result.items()}
+        self._release()
+        return out
 
     def reduce_dict(self, d):
         """vangan.py:459-473: SUM over replicas of every entry (one 10-float all-reduce)."""
