@@ -31,6 +31,8 @@ enum { VG_PAD_ZERO = 0, VG_PAD_REFLECT = 1 };
 int vg_abi_version(void);
 /* kernels launched by this library so far (monotonic counter, for bench accounting) */
 unsigned long long vg_launch_count(void);
+/* of those, launches of the tcgen05/TMEM/TMA convolution kernel */
+unsigned long long vg_tc_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Conv3D (valid convolution over an explicitly padded input; the padding itself — ReflectionPadding3D

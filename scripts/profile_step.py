@@ -14,3 +14,5 @@ for i in range(steps):
     r = gan.train_step(dI, dS)
     torch.cuda.synchronize()
 print(r)
+from van_gan_b200 import _lib
+print('kernel launches', _lib.lib().vg_launch_count(), 'tcgen05 conv launches', _lib.lib().vg_tc_launch_count())

@@ -40,6 +40,7 @@ _CD, _ID = C.POINTER(ConvDesc), C.POINTER(InDesc)
 SIGNATURES = {
     "vg_abi_version": (_I, []),
     "vg_launch_count": (_ULL, []),
+    "vg_tc_launch_count": (_ULL, []),
     "vg_conv3d_packed_bytes": (_Z, [_CD, _I]),
     "vg_conv3d_pack_weights": (_I, [_CD, _P, _P, _P, _P]),
     "vg_conv3d_fwd": (_I, [_CD, _P, _P, _P, _P, _P]),

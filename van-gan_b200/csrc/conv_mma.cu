@@ -18,6 +18,8 @@
 //
 // The tcgen05/TMEM path for the wide-channel layers lives in conv_tc.cu; this file is the
 // general-shape path and the numerical cross-check for it.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -674,6 +676,37 @@ inline bool desc_ok(const vg_conv3d_desc* d) {
 inline int odim(int I, int K, int s) { return (I - K) / s + 1; }
 inline int rup(int a, int b) { return (a + b - 1) / b * b; }
 
+// VG_CONV_PATH=mma forces the warp-level mma.sync kernels everywhere (A/B testing and cross-checks)
+inline bool tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VG_CONV_PATH");
+        v = (e && e[0] == 'm') ? 0 : 1;
+    }
+    return v == 1;
+}
+inline size_t mma_fwd_elems(const vg_conv3d_desc* d) {
+    return d->Cin == 1 ? 0 : (size_t)d->K * d->K * d->K * rup(d->Cout, NPAD) * d->Cin;
+}
+inline size_t mma_dgrad_elems(const vg_conv3d_desc* d) {
+    if (d->Cout == 1) return 0;
+    size_t tot = 0;
+    for (int a = 0; a < d->stride; a++)
+        for (int b = 0; b < d->stride; b++)
+            for (int c = 0; c < d->stride; c++)
+                tot += (size_t)class_taps(d->K, d->stride, a) * class_taps(d->K, d->stride, b) * class_taps(d->K, d->stride, c);
+    return tot * rup(d->Cin, NPAD) * d->Cout;
+}
+inline bool tc_fwd_ok(const vg_conv3d_desc* d) {
+    return d->stride == 1 && d->Cin % 16 == 0 && d->Cout % 16 == 0 && vg_tc_ncta(d->Cout, d->K * d->K * d->K) > 0;
+}
+inline bool tc_dgrad_ok(const vg_conv3d_desc* d) { return d->Cin % 16 == 0 && d->Cout % 16 == 0; }
+inline size_t tc_dgrad_class_elems(const vg_conv3d_desc* d, int a, int b, int c) {
+    int T = class_taps(d->K, d->stride, a) * class_taps(d->K, d->stride, b) * class_taps(d->K, d->stride, c);
+    return T ? vg_tc_pack_elems(d->Cin, d->Cout, T) : 0;
+}
+inline size_t rup256(size_t x) { return (x + 255) & ~(size_t)255; }
+
 }  // namespace
 
 extern "C" {
@@ -682,15 +715,18 @@ int vg_abi_version(void) { return 1; }
 
 size_t vg_conv3d_packed_bytes(const vg_conv3d_desc* d, int for_dgrad) {
     if (!desc_ok(d)) return 0;
-    size_t T = (size_t)d->K * d->K * d->K;
-    if (!for_dgrad) return d->Cin == 1 ? 0 : T * rup(d->Cout, NPAD) * d->Cin * 2;
-    if (d->Cout == 1) return 0;
-    size_t tot = 0;
-    for (int a = 0; a < d->stride; a++)
-        for (int b = 0; b < d->stride; b++)
-            for (int c = 0; c < d->stride; c++)
-                tot += (size_t)class_taps(d->K, d->stride, a) * class_taps(d->K, d->stride, b) * class_taps(d->K, d->stride, c);
-    return tot * rup(d->Cin, NPAD) * d->Cout * 2;
+    // layout: [ mma.sync operand pack | (256-byte aligned) tcgen05 operand pack ]
+    if (!for_dgrad) {
+        size_t bytes = rup256(mma_fwd_elems(d) * 2);
+        if (tc_fwd_ok(d)) bytes += vg_tc_pack_elems(d->Cout, d->Cin, d->K * d->K * d->K) * 2;
+        return bytes;
+    }
+    size_t bytes = rup256(mma_dgrad_elems(d) * 2);
+    if (tc_dgrad_ok(d))
+        for (int a = 0; a < d->stride; a++)
+            for (int b = 0; b < d->stride; b++)
+                for (int c = 0; c < d->stride; c++) bytes += rup256(tc_dgrad_class_elems(d, a, b, c) * 2);
+    return bytes;
 }
 
 int vg_conv3d_pack_weights(const vg_conv3d_desc* d, const float* w, void* w_fwd, void* w_dgrad, void* stream) {
@@ -705,6 +741,24 @@ int vg_conv3d_pack_weights(const vg_conv3d_desc* d, const float* w, void* w_fwd,
         int NpI = rup(d->Cin, NPAD);
         pack_dgrad_kernel<<<vg_grid_for((long long)T * NpI * d->Cout, 256, 4), 256, 0, st>>>(w, (bf16*)w_dgrad, d->K, d->stride,
                                                                                           d->Cin, d->Cout, NpI); VG_LAUNCHED(1);
+    }
+    if (w_fwd && tc_fwd_ok(d)) {
+        bf16* dst = (bf16*)((char*)w_fwd + rup256(mma_fwd_elems(d) * 2));
+        if (vg_tc_pack(w, dst, d->K, 1, d->Cin, d->Cout, 0, 0, 0, 0, d->K, d->K, d->K, st) != VG_OK) return VG_ERR_CUDA;
+    }
+    if (w_dgrad && tc_dgrad_ok(d)) {
+        char* dst = (char*)w_dgrad + rup256(mma_dgrad_elems(d) * 2);
+        const int s_ = d->stride;
+        for (int a = 0; a < s_; a++)
+            for (int b = 0; b < s_; b++)
+                for (int c = 0; c < s_; c++) {
+                    size_t el = tc_dgrad_class_elems(d, a, b, c);
+                    if (!el) continue;
+                    if (vg_tc_pack(w, (bf16*)dst, d->K, s_, d->Cin, d->Cout, 1, a, b, c, class_taps(d->K, s_, a), class_taps(d->K, s_, b),
+                                   class_taps(d->K, s_, c), st) != VG_OK)
+                        return VG_ERR_CUDA;
+                    dst += rup256(el * 2);
+                }
     }
     VG_CHECK_LAUNCH();
     return VG_OK;
@@ -723,6 +777,13 @@ int vg_conv3d_fwd(const vg_conv3d_desc* d, const void* x, const void* w_fwd, con
                                                                        d->ID, d->IH, d->IW, OD, OH, OW, d->Cout, d->K, d->stride); VG_LAUNCHED(1);
         VG_CHECK_LAUNCH();
         return VG_OK;
+    }
+    if (tc_enabled() && tc_fwd_ok(d) && d->y_dtype == VG_BF16) {
+        const bf16* wt = (const bf16*)((const char*)w_fwd + rup256(mma_fwd_elems(d) * 2));
+        int rc = vg_tc_launch((const bf16*)x, d->N, d->ID, d->IH, d->IW, d->Cin, wt, y, bias, OD, OH, OW, d->Cout, OD, OH, OW, d->K, d->K,
+                              d->K, +1, 1, 0, 0, 0, d->act, st);
+        if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
+        if (rc != VG_ERR_UNSUPPORTED) return rc;
     }
     GConv p{};
     p.x = (const bf16*)x; p.w = (const bf16*)w_fwd; p.y = y; p.bias = bias;
@@ -758,12 +819,23 @@ int vg_conv3d_dgrad(const vg_conv3d_desc* d, const void* dy, const void* w_dgrad
     }
     const int NpI = rup(d->Cin, NPAD);
     size_t woff = 0;
+    const bool use_tc = tc_enabled() && tc_dgrad_ok(d) && d->x_dtype == VG_BF16;
+    const char* wtc = (const char*)w_dgrad + rup256(mma_dgrad_elems(d) * 2);
     for (int ad = 0; ad < s; ad++)
         for (int ah = 0; ah < s; ah++)
             for (int aw = 0; aw < s; aw++) {
                 int td = class_taps(d->K, s, ad), th = class_taps(d->K, s, ah), tw = class_taps(d->K, s, aw);
                 size_t cnt = (size_t)td * th * tw * NpI * d->Cout;
                 if (cnt == 0) continue;
+                if (use_tc) {
+                    const bf16* wt = (const bf16*)wtc;
+                    wtc += rup256(tc_dgrad_class_elems(d, ad, ah, aw) * 2);
+                    int rc = vg_tc_launch((const bf16*)dy, d->N, OD, OH, OW, d->Cout, wt, dx, nullptr, d->ID, d->IH, d->IW, d->Cin,
+                                          (d->ID - ad + s - 1) / s, (d->IH - ah + s - 1) / s, (d->IW - aw + s - 1) / s, td, th, tw, -1, s,
+                                          ad, ah, aw, VG_ACT_NONE, st);
+                    if (rc == VG_OK) { woff += cnt; continue; }
+                    if (rc != VG_ERR_UNSUPPORTED) return rc;
+                }
                 GConv p{};
                 p.x = (const bf16*)dy; p.w = (const bf16*)w_dgrad + woff; p.y = dx; p.bias = nullptr;
                 p.N = d->N; p.XD = OD; p.XH = OH; p.XW = OW; p.Cx = d->Cout;

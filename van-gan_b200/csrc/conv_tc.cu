@@ -1,0 +1,512 @@
+// Conv3D forward (stride 1) and dgrad (all strides) on the 5th-generation tensor cores:
+// TMA halo bricks -> shared memory -> tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32)
+// with accumulators in TMEM, warp-specialised and persistent.
+//
+// Replaces the same reference call sites as conv_mma.cu (cuDNN Conv3D / Conv3DBackpropInputV2 behind
+// resunet_model.py:64-65,89-90,96,133-134; discriminator.py:91-114; building_blocks.py:182-189).
+//
+// Mapping.  Every convolution here is a VALID gather over an explicitly padded NDHWC bf16 tensor:
+//   out[g][n] = sum_{tap t, channel k} src[g + sigma*t][k] * W[t][k][n]      (sigma = +1 fwd, -1 dgrad)
+// A CTA owns a brick of BD x 16 x 8 output voxels = BD MMA tiles of M = 128 rows.  For one chunk of
+// 16 source channels the (BD+T-1) x (16+T-1) x (8+T-1) halo brick is fetched ONCE by two TMA tile
+// loads (one per 8-channel half; 5-D tensor map C,W,H,D,N; out-of-range coordinates are zero-filled
+// by the TMA unit, which is exactly the dgrad boundary condition), landing as two planes of 16-byte
+// voxel cells.  In that layout the A operand of ANY tap is a canonical K-major no-swizzle UMMA tile:
+// 8 consecutive w-voxels are one 8x16B core matrix, the 16 h-rows are 16 row groups at a constant
+// stride (SBO = halo row pitch), and the two K halves are the two planes (LBO = plane pitch).  So a
+// tap costs nothing but a different descriptor start address: 27 (or 64) tensor-core instructions per
+// tile re-use one staged brick, and the activation tensor is read from L2 ~2x instead of 27x.
+// Weights of the chunk ([tap][K half][N][8], pre-packed) arrive with one cp.async.bulk per stage.
+//
+// Two brick loaders produce that layout (VG_TC_LOADER=tma|gather, default gather):
+//   tma    : the two TMA tile loads described above.  Measured on B200 (profiles/): with NDHWC storage
+//            the box rows are only 16 bytes, the TMA unit retires ~1 row / 8 cycles, and the kernel is
+//            load-bound at ~120 TFLOP/s for the 16-channel layers -> kept for reference only.
+//   gather : four producer warps read each halo voxel's 32 contiguous bytes (one full L2 sector) with
+//            128-bit loads and store the two halves into the planes (conflict-free), then
+//            fence.proxy.async + mbarrier arrive.  This is also where InstanceNorm-apply / ReLU /
+//            reflect padding can be folded into the load (norm-on-load) in a later round.
+//
+// Roles (288 threads): warps 0-3 = brick producers (warp 0 lane 0 also issues the weight bulk copy and,
+// in tma mode, the tensor loads), warp 4 = MMA issuer (one elected lane) + TMEM allocator, warps 5-8 =
+// epilogue (tcgen05.ld 32x32b -> bias/act -> bf16 -> global).  Rings: shared-memory stages (full/empty
+// mbarriers, released by tcgen05.commit) and two TMEM accumulator buffers (tmem_full/tmem_empty) so
+// the epilogue of brick i overlaps the MMAs of brick i+1.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_THREADS = 288;
+constexpr int NPROD = 128;   // producer threads (warps 0-3)
+constexpr int MH = 16, MW = 8;
+
+struct TcParams {
+    const bf16* w;   // packed [nblk][nchunks][T][2][NCTA][8]
+    void* y;
+    const float* bias;
+    int Nb, nchunks;
+    int YD, YH, YW, Cy;
+    int GD, GH, GW;
+    int TD, TH, TW, st;
+    int oso, ood, ooh, oow;
+    int BD, NCTA, nblk;
+    int ED, EH, EW;
+    int stages, act, use_tma, dbg;   // dbg: bit0 = skip brick/weight loads, bit1 = skip MMA issue (timing experiments only)
+    const bf16* x;        // source tensor (gather loader)
+    int XD, XH, XW, Cx;
+    int bd_tiles, bh_tiles, bw_tiles, nwork;
+    uint32_t plane_bytes, plane_box_bytes, wstage_bytes, stage_bytes, tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 bytes (contiguous); LBO = byte offset between the two
+// K-halves, SBO = byte offset between 8-row groups; version = 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        // load + wait in ONE asm statement so no consumer of v[] can be scheduled before the wait
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int BD>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* bar_base = smem + (size_t)p.stages * p.stage_bytes;
+    const uint32_t full0 = s_addr(bar_base), empty0 = full0 + 8 * p.stages;
+    const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_base + 16 * p.stages + 32);
+    const uint32_t sbase = s_addr(smem);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(full0 + 8 * s, p.use_tma ? 1 : NPROD + 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(tfull0 + 8 * b, 1);
+            mbar_init(tempty0 + 8 * b, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_addr(tmem_slot)), "r"(p.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int T = p.TD * p.TH * p.TW;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------------ brick producers
+        int stage = 0;
+        uint32_t phase = 0;
+        const size_t wstage_elems = p.wstage_bytes / 2;
+        const int EV = p.ED * p.EH * p.EW, EHW = p.EH * p.EW;
+        const int tid = threadIdx.x;
+        if (p.use_tma && tid != 0) goto producers_done;
+        for (int wk = blockIdx.x; wk < p.nwork; wk += gridDim.x) {
+            const int nb = wk % p.nblk;
+            int brick = wk / p.nblk;
+            const int bw = brick % p.bw_tiles; brick /= p.bw_tiles;
+            const int bh = brick % p.bh_tiles; brick /= p.bh_tiles;
+            const int bd = brick % p.bd_tiles;
+            const int n = brick / p.bd_tiles;
+            const int sd0 = bd * BD - (p.st < 0 ? p.TD - 1 : 0);
+            const int sh0 = bh * MH - (p.st < 0 ? p.TH - 1 : 0);
+            const int sw0 = bw * MW - (p.st < 0 ? p.TW - 1 : 0);
+            const bf16* xn = p.x + (size_t)n * p.XD * p.XH * p.XW * p.Cx;
+            for (int c = 0; c < p.nchunks; c++) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t full = full0 + 8 * stage;
+                const uint32_t dst = sbase + stage * p.stage_bytes;
+                if (p.dbg & 1) {
+                    mbar_arrive(full);
+                    if (tid == 0 && !p.use_tma) mbar_arrive(full);
+                } else {
+                if (tid == 0) {
+                    mbar_expect_tx(full, p.wstage_bytes + (p.use_tma ? 2 * p.plane_box_bytes : 0));
+                    bulk_load(dst + 2 * p.plane_bytes, p.w + ((size_t)nb * p.nchunks + c) * wstage_elems, p.wstage_bytes, full);
+                }
+                if (p.use_tma) {
+                    tma_load_5d(dst, &tmap, c * 16, sw0, sh0, sd0, n, full);
+                    tma_load_5d(dst + p.plane_bytes, &tmap, c * 16 + 8, sw0, sh0, sd0, n, full);
+                } else {
+                    // each thread: voxels tid, tid+128, ...; 4 voxels (8 x 128-bit loads) in flight
+                    for (int v0 = tid; v0 < EV; v0 += 4 * NPROD) {
+                        uint4 lo[4], hi[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int v = v0 + u * NPROD;
+                            lo[u] = make_uint4(0, 0, 0, 0);
+                            hi[u] = lo[u];
+                            if (v < EV) {
+                                const int ld = v / EHW, rem = v - ld * EHW;
+                                const int lh = rem / p.EW, lw = rem - lh * p.EW;
+                                const int sd = sd0 + ld, sh = sh0 + lh, sw = sw0 + lw;
+                                if ((unsigned)sd < (unsigned)p.XD && (unsigned)sh < (unsigned)p.XH && (unsigned)sw < (unsigned)p.XW) {
+                                    const uint4* src = reinterpret_cast<const uint4*>(xn + (((size_t)sd * p.XH + sh) * p.XW + sw) * p.Cx + c * 16);
+                                    lo[u] = __ldg(src);
+                                    hi[u] = __ldg(src + 1);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int v = v0 + u * NPROD;
+                            if (v < EV) {
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + (uint32_t)v * 16), "r"(lo[u].x), "r"(lo[u].y),
+                                             "r"(lo[u].z), "r"(lo[u].w) : "memory");
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + p.plane_bytes + (uint32_t)v * 16), "r"(hi[u].x),
+                                             "r"(hi[u].y), "r"(hi[u].z), "r"(hi[u].w) : "memory");
+                            }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to tcgen05.mma
+                    mbar_arrive(full);
+                }
+                }
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    producers_done:;
+    } else if (warp == 4) {
+        // ------------------------------------------------------------------ MMA issuer
+        // The whole warp runs the (warp-uniform) loops so that descriptors live in uniform registers; one
+        // elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors are built incrementally: a tap or a
+        // tile only changes the 14-bit start-address field, i.e. one integer add on the low word.
+        // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both,
+        // N>>3 at bits 17-22, M>>4 at bits 24-28
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NCTA >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(leader));
+        int stage = 0, it = 0;
+        uint32_t phase = 0;
+        const uint32_t lbo_b = (uint32_t)p.NCTA * 16;
+        const uint32_t a_hi = (((uint32_t)p.EW * 16) >> 4) | (1u << 14);          // SBO | version
+        const uint32_t b_hi = (128u >> 4) | (1u << 14);
+        const uint32_t a_lo_lbo = ((p.plane_bytes >> 4) & 0x3fffu) << 16;
+        const uint32_t b_lo_lbo = ((lbo_b >> 4) & 0x3fffu) << 16;
+        const int tile_step = p.EH * p.EW;                                        // 16-byte units between d-slices
+        const uint32_t b_step = (2 * lbo_b) >> 4;
+        const int sgn = p.st > 0 ? 1 : -1;
+        const int aoff0 = p.st > 0 ? 0 : ((p.TD - 1) * p.EH + (p.TH - 1)) * p.EW + (p.TW - 1);
+        for (int wk = blockIdx.x; wk < p.nwork; wk += gridDim.x, it++) {
+            const int buf = it & 1;
+            mbar_wait(tempty0 + 8 * buf, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + (uint32_t)(buf * BD) * p.NCTA;
+            for (int c = 0; c < p.nchunks; c++) {
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t a_base = (sbase + stage * p.stage_bytes) >> 4;
+                uint32_t b_addr = a_base + ((2 * p.plane_bytes) >> 4);
+                int aoff = aoff0;
+                uint32_t acc = c ? 1u : 0u;
+                for (int td = 0; td < p.TD; td++) {
+                    for (int th = 0; th < p.TH; th++) {
+                        for (int tw = 0; tw < p.TW; tw++) {
+                            if (leader && !(p.dbg & 2)) {
+                                const uint64_t bdesc = ((uint64_t)b_hi << 32) | (b_lo_lbo | b_addr);
+#pragma unroll
+                                for (int m = 0; m < BD; m++) {
+                                    const uint64_t adesc = ((uint64_t)a_hi << 32) | (a_lo_lbo | (a_base + (uint32_t)(aoff + m * tile_step)));
+                                    tc_mma(d0 + (uint32_t)m * p.NCTA, adesc, bdesc, idesc, acc);
+                                }
+                            }
+                            acc = 1u;
+                            aoff += sgn;
+                            b_addr += b_step;
+                        }
+                        aoff += sgn * (p.EW - p.TW);
+                    }
+                    aoff += sgn * (p.EH - p.TH) * p.EW;
+                }
+                __syncwarp();
+                if (leader) tc_commit(empty0 + 8 * stage);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            if (leader) tc_commit(tfull0 + 8 * buf);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 5..8)
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;          // tile row -> (lh, lw)
+        const int lh = r >> 3, lw = r & 7;
+        int it = 0;
+        for (int wk = blockIdx.x; wk < p.nwork; wk += gridDim.x, it++) {
+            const int nb = wk % p.nblk;
+            int brick = wk / p.nblk;
+            const int bw = brick % p.bw_tiles; brick /= p.bw_tiles;
+            const int bh = brick % p.bh_tiles; brick /= p.bh_tiles;
+            const int bd = brick % p.bd_tiles;
+            const int n = brick / p.bd_tiles;
+            const int buf = it & 1;
+            mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
+            tc_fence_after();
+            const int gh = bh * MH + lh, gw = bw * MW + lw;
+            const int yh = gh * p.oso + p.ooh, yw = gw * p.oso + p.oow;
+            const bool row_ok = gh < p.GH && gw < p.GW && yh < p.YH && yw < p.YW;
+            for (int m = 0; m < BD; m++) {
+                const int gd = bd * BD + m;
+                const int yd = gd * p.oso + p.ood;
+                const bool ok = row_ok && gd < p.GD && yd < p.YD;
+                for (int n0 = 0; n0 < p.NCTA; n0 += 16) {
+                    uint32_t v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * BD + m) * p.NCTA + n0), v);
+                    const int col0 = nb * p.NCTA + n0;
+                    if (ok && col0 < p.Cy) {
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            f[j] = __uint_as_float(v[j]);
+                            if (p.bias) f[j] += p.bias[col0 + j];
+                            if (p.act == VG_ACT_TANH) f[j] = tanhf(f[j]);
+                        }
+                        bf16* o = (bf16*)p.y + ((((size_t)n * p.YD + yd) * p.YH + yh) * p.YW + yw) * p.Cy + col0;
+                        store8<bf16>(o, f);
+                        store8<bf16>(o + 8, f + 8);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * buf);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(p.tmem_cols));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+}  // namespace
+
+unsigned long long g_vg_tc_launches = 0;
+extern "C" unsigned long long vg_tc_launch_count(void) { return g_vg_tc_launches; }
+
+// N-block width used by the tensor-core path for a GEMM with `ncols` output columns and T taps (0 = not eligible)
+int vg_tc_ncta(int ncols, int T) {
+    if (ncols < 16 || ncols % 16) return 0;
+    const int cap = (72 * 1024) / (T * 32);   // weight stage = T*2*NCTA*16 bytes
+    int best = 0;
+    long best_pad = 0;
+    const int cands[4] = {64, 48, 32, 16};
+    for (int i = 0; i < 4; i++) {
+        int c = cands[i];
+        if (c > cap) continue;
+        long padded = (long)((ncols + c - 1) / c) * c;
+        if (!best || padded < best_pad) { best = c; best_pad = padded; }
+    }
+    return best;
+}
+
+size_t vg_tc_pack_elems(int ncols, int K_total, int T) {
+    int ncta = vg_tc_ncta(ncols, T);
+    if (!ncta || K_total % 16) return 0;
+    size_t nblk = (ncols + ncta - 1) / ncta;
+    return nblk * (size_t)(K_total / 16) * T * 2 * ncta * 8;
+}
+
+// Launch one gather convolution on the tcgen05 path.  Source tensor x: [Nb, XD, XH, XW, Cx] bf16.
+// Returns VG_ERR_UNSUPPORTED when the shape does not fit (caller falls back to the mma.sync path).
+int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf16* wpack, void* y, const float* bias, int YD, int YH,
+                 int YW, int Cy, int GD, int GH, int GW, int TD, int TH, int TW, int st, int oso, int ood, int ooh, int oow, int act,
+                 cudaStream_t stream) {
+    const int T = TD * TH * TW;
+    const int ncta = vg_tc_ncta(Cy, T);
+    if (!ncta || Cx % 16) return VG_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return VG_ERR_UNSUPPORTED;
+    static int loader = -1;   // 0 = gather (default), 1 = tma
+    if (loader < 0) {
+        const char* e = getenv("VG_TC_LOADER");
+        loader = (e && e[0] == 't') ? 1 : 0;
+    }
+    static int dbg = -1;
+    if (dbg < 0) {
+        const char* e = getenv("VG_TC_DEBUG");
+        dbg = e ? atoi(e) : 0;
+    }
+    TcParams p{};
+    p.use_tma = loader;
+    p.dbg = dbg;
+    p.x = x; p.XD = XD; p.XH = XH; p.XW = XW; p.Cx = Cx;
+    p.w = wpack; p.y = y; p.bias = bias;
+    p.Nb = Nb; p.nchunks = Cx / 16;
+    p.YD = YD; p.YH = YH; p.YW = YW; p.Cy = Cy;
+    p.GD = GD; p.GH = GH; p.GW = GW;
+    p.TD = TD; p.TH = TH; p.TW = TW; p.st = st;
+    p.oso = oso; p.ood = ood; p.ooh = ooh; p.oow = oow;
+    p.NCTA = ncta; p.nblk = (Cy + ncta - 1) / ncta;
+    p.act = act;
+    p.EH = MH + TH - 1; p.EW = MW + TW - 1;
+    p.wstage_bytes = (uint32_t)T * 2 * ncta * 16;
+    const size_t smem_cap = 220 * 1024;
+    int BD = 4;
+    while (BD > GD && BD > 1) BD >>= 1;
+    for (;; BD >>= 1) {
+        p.BD = BD;
+        p.ED = BD + TD - 1;
+        p.plane_box_bytes = (uint32_t)p.ED * p.EH * p.EW * 16;
+        p.plane_bytes = (p.plane_box_bytes + 127) & ~127u;
+        p.stage_bytes = 2 * p.plane_bytes + p.wstage_bytes;
+        p.stages = (int)((smem_cap - 256) / p.stage_bytes);
+        if (p.stages > 4) p.stages = 4;
+        if (p.stages >= 2 && 2 * BD * ncta <= 512) break;
+        if (BD == 1) return VG_ERR_UNSUPPORTED;
+    }
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * p.BD * ncta)) cols <<= 1;
+    p.tmem_cols = cols;
+    p.bd_tiles = (GD + p.BD - 1) / p.BD; p.bh_tiles = (GH + MH - 1) / MH; p.bw_tiles = (GW + MW - 1) / MW;
+    const long long nwork = (long long)p.bd_tiles * p.bh_tiles * p.bw_tiles * Nb * p.nblk;
+    if (nwork > 0x7fffffff) return VG_ERR_UNSUPPORTED;
+    p.nwork = (int)nwork;
+
+    CUtensorMap tmap;
+    cuuint64_t dims[5] = {(cuuint64_t)Cx, (cuuint64_t)XW, (cuuint64_t)XH, (cuuint64_t)XD, (cuuint64_t)Nb};
+    cuuint64_t strides[4] = {(cuuint64_t)Cx * 2, (cuuint64_t)XW * Cx * 2, (cuuint64_t)XH * XW * Cx * 2,
+                             (cuuint64_t)XD * XH * XW * Cx * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)p.EW, (cuuint32_t)p.EH, (cuuint32_t)p.ED, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return VG_ERR_UNSUPPORTED;
+
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 256;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(tc_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return VG_ERR_CUDA;
+        attr_done = true;
+    }
+    int grid = p.nwork < 148 ? p.nwork : 148;
+    if (p.BD == 4) tc_conv_kernel<4><<<grid, TC_THREADS, smem, stream>>>(tmap, p);
+    else if (p.BD == 2) tc_conv_kernel<2><<<grid, TC_THREADS, smem, stream>>>(tmap, p);
+    else tc_conv_kernel<1><<<grid, TC_THREADS, smem, stream>>>(tmap, p);
+    VG_LAUNCHED(1);
+    g_vg_tc_launches++;
+    return VG_OK;
+}
+
+// pack kernel for the tensor-core layout: out[nb][c][t][kh][n][j] = src(t, k = c*16+kh*8+j, col = nb*NCTA+n)
+// fwd:   src(t,k,col) = w[t][k][col]            (K = Cin, cols = Cout)
+// dgrad: src(t',k,col) = w[tap(t')][col][k]      (K = Cout, cols = Cin), taps restricted to one stride-parity class
+__global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int K, int stride, int Cin, int Cout, int dgrad,
+                               int ad, int ah, int aw, int td, int th, int tw, int ncta, int nblk) {
+    const int T = td * th * tw;
+    const int Kt = dgrad ? Cout : Cin, ncols = dgrad ? Cin : Cout;
+    const int nchunks = Kt / 16;
+    size_t total = (size_t)nblk * nchunks * T * 2 * ncta * 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        int j = (int)(r % 8); r /= 8;
+        int n = (int)(r % ncta); r /= ncta;
+        int kh = (int)(r % 2); r /= 2;
+        int t = (int)(r % T); r /= T;
+        int c = (int)(r % nchunks);
+        int nb = (int)(r / nchunks);
+        int k = c * 16 + kh * 8 + j, col = nb * ncta + n;
+        int w_ = t % tw, h_ = (t / tw) % th, d_ = t / (tw * th);
+        int kd = dgrad ? ad + stride * d_ : d_, kh2 = dgrad ? ah + stride * h_ : h_, kw = dgrad ? aw + stride * w_ : w_;
+        int tap = (kd * K + kh2) * K + kw;
+        float v = 0.f;
+        if (col < ncols) v = dgrad ? w[((size_t)tap * Cin + col) * Cout + k] : w[((size_t)tap * Cin + k) * Cout + col];
+        out[i] = __float2bfloat16(v);
+    }
+}
+
+int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, int dgrad, int ad, int ah, int aw, int td, int th,
+               int tw, cudaStream_t st) {
+    const int T = td * th * tw;
+    const int ncols = dgrad ? Cin : Cout;
+    const int ncta = vg_tc_ncta(ncols, T);
+    if (!ncta) return VG_ERR_UNSUPPORTED;
+    const int nblk = (ncols + ncta - 1) / ncta;
+    size_t total = vg_tc_pack_elems(ncols, dgrad ? Cout : Cin, T);
+    tc_pack_kernel<<<vg_grid_for((long long)total, 256, 4), 256, 0, st>>>(w, out, K, stride, Cin, Cout, dgrad, ad, ah, aw, td, th, tw, ncta,
+                                                                          nblk);
+    VG_LAUNCHED(1);
+    return VG_OK;
+}
