@@ -153,6 +153,8 @@ int vg_clip_adam_step(float* w, const float* g, float* m, float* v, const long l
  * Sliding-window stitching (custom_callback.py:123,165-166,177-183,192,202).
  * pred/cnt: [H,W,D] fp32 volumes; win: [B,kH,kW,kD] generator outputs; starts: [B][3] window origins.
  * ------------------------------------------------------------------------------------------- */
+/* win[B,kH,kW,kD] = windows of vol[H,W,D] at starts[B][3] */
+int vg_stitch_gather(const float* vol, int H, int W, int D, float* win, const int* starts, int B, int kH, int kW, int kD, void* stream);
 int vg_stitch_accumulate(float* pred, float* cnt, int H, int W, int D, const float* win, const int* starts, int B, int kH,
                          int kW, int kD, int pH, int pW, int pD, void* stream);
 /* out[oh,ow,od] = 255 * minmax_norm( (pred/cnt)[crop] ): two calls — divide+minmax, then scale */

@@ -31,41 +31,86 @@ __device__ __forceinline__ float act_grad(float z, int act, float slope) {
     return 1.f;
 }
 
+// Thread mapping shared by all four streaming kernels: a block has nthr = (256/cg)*cg threads
+// (cg = C/8 channel groups), thread = (voxel lane, channel group), so a thread's 8 channels -- and their
+// scale / shift / mean / rstd -- are fixed for its whole loop and live in registers.  Voxels are walked
+// flat (grid-stride over the sample), U at a time, so every thread keeps U independent 128-bit loads in
+// flight; (d,h,w) are carried incrementally (no divisions in the loop).  Raw 8-element packets are kept
+// packed until they are consumed to hold the register count down.
+constexpr int U = 4;
+
+template <typename T> struct Raw;
+template <> struct Raw<bf16> { bf16x8 v; };
+template <> struct Raw<float> { float4 a, b; };
+template <typename T> __device__ __forceinline__ void load_raw(const T* p, Raw<T>& r);
+template <> __device__ __forceinline__ void load_raw<bf16>(const bf16* p, Raw<bf16>& r) { r.v = *reinterpret_cast<const bf16x8*>(p); }
+template <> __device__ __forceinline__ void load_raw<float>(const float* p, Raw<float>& r) {
+    r.a = reinterpret_cast<const float4*>(p)[0];
+    r.b = reinterpret_cast<const float4*>(p)[1];
+}
+__device__ __forceinline__ void unpack_raw(const Raw<bf16>& r, float* f) { unpack8(r.v, f); }
+__device__ __forceinline__ void unpack_raw(const Raw<float>& r, float* f) {
+    f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+
+// walks voxels v = v0, v0+S, v0+2S, ... of a [PD][PH][PW] volume keeping (pd,ph,pw) without divisions
+struct VoxIter {
+    int pd, ph, pw, sd, sh, sw, PH, PW;
+    __device__ __forceinline__ void init(int v, int S, int PH_, int PW_) {
+        PH = PH_; PW = PW_;
+        pw = v % PW; int r = v / PW; ph = r % PH; pd = r / PH;
+        sw = S % PW; r = S / PW; sh = r % PH; sd = r / PH;
+    }
+    __device__ __forceinline__ void next() {
+        pw += sw;
+        int c = pw >= PW;
+        pw -= c ? PW : 0;
+        ph += sh + c;
+        c = ph >= PH;
+        ph -= c ? PH : 0;
+        pd += sd + c;
+    }
+};
+
 // ------------------------------------------------------------------ statistics
 // partial[(n*nblk + blk)*C*2 + c*2 + {0,1}] = sum / sumsq of (x - shift_c) over the block's voxels,
 // shift_c = x[n,0,c] (keeps E[x^2]-E[x]^2 well conditioned)
 template <typename T>
-__global__ void __launch_bounds__(NT) in_stats_partial_kernel(const T* __restrict__ x, size_t V, int C, int nblk,
+__global__ void __launch_bounds__(NT) in_stats_partial_kernel(const T* __restrict__ x, int V, int C,
                                                               float* __restrict__ partial) {
-    extern __shared__ float sm[];  // [nvl][C][2]
-    int n = blockIdx.y, blk = blockIdx.x;
-    int cg = C / 8, nvl = NT / cg;
-    int g = threadIdx.x % cg, vl = threadIdx.x / cg;
-    const T* xn = x + (size_t)n * V * C;
+    extern __shared__ float sm[];  // [vlanes][C][2]
+    const int n = blockIdx.y, cg = C / 8;
+    const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
+    const T* xn = x + (size_t)n * V * C + c8 * 8;
     float shift[8], s1[8], s2[8];
-    load8<T>(xn + g * 8, shift);
+    load8<T>(xn, shift);
 #pragma unroll
     for (int k = 0; k < 8; k++) s1[k] = s2[k] = 0.f;
-    size_t per = (V + nblk - 1) / nblk;
-    size_t v0 = (size_t)blk * per, v1 = v0 + per < V ? v0 + per : V;
-    if (vl < nvl) {
-        for (size_t v = v0 + vl; v < v1; v += nvl) {
-            float f[8];
-            load8<T>(xn + v * C + g * 8, f);
+    const int S = gridDim.x * nvl;
+    for (int v = blockIdx.x * nvl + vl; v < V; v += U * S) {
+        Raw<T> raw[U];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                float d = f[k] - shift[k];
-                s1[k] += d;
-                s2[k] += d * d;
+        for (int u = 0; u < U; u++)
+            if (v + u * S < V) load_raw<T>(xn + (size_t)(v + u * S) * C, raw[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (v + u * S < V) {
+                float f[8];
+                unpack_raw(raw[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    float d = f[k] - shift[k];
+                    s1[k] += d;
+                    s2[k] += d * d;
+                }
             }
-        }
-        float* row = sm + ((size_t)vl * C + g * 8) * 2;
-#pragma unroll
-        for (int k = 0; k < 8; k++) { row[2 * k] = s1[k]; row[2 * k + 1] = s2[k]; }
     }
+    float* row = sm + ((size_t)vl * C + c8 * 8) * 2;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { row[2 * k] = s1[k]; row[2 * k + 1] = s2[k]; }
     __syncthreads();
-    float* out = partial + ((size_t)n * nblk + blk) * C * 2;
-    for (int i = threadIdx.x; i < C * 2; i += NT) {
+    float* out = partial + ((size_t)n * gridDim.x + blockIdx.x) * C * 2;
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
         float a = 0.f;
         for (int l = 0; l < nvl; l++) a += sm[(size_t)l * C * 2 + i];
         out[i] = a;
@@ -107,145 +152,156 @@ struct ApplyArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(NT) in_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+__global__ void __launch_bounds__(NT, 2) in_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
                                                       Geo g, ApplyArgs a) {
-    int cg = g.C / 8;
-    int PD = g.D + g.pad_lo + g.pad_hi, PH = g.H + g.pad_lo + g.pad_hi, PW = g.W + g.pad_lo + g.pad_hi;
-    size_t total = (size_t)g.N * PD * PH * PW * cg;
-    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
-        int c8 = (int)(i % cg);
-        size_t pv = i / cg;
-        int pw = (int)(pv % PW), ph = (int)((pv / PW) % PH), pd = (int)((pv / ((size_t)PW * PH)) % PD);
-        int n = (int)(pv / ((size_t)PW * PH * PD));
-        int d = pd - g.pad_lo, h = ph - g.pad_lo, w = pw - g.pad_lo;
-        bool oob = (unsigned)d >= (unsigned)g.D || (unsigned)h >= (unsigned)g.H || (unsigned)w >= (unsigned)g.W;
-        float o[8];
-        if (oob && g.pad_mode == VG_PAD_ZERO) {
+    const int n = blockIdx.y, cg = g.C / 8;
+    const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
+    const int PD = g.D + g.pad_lo + g.pad_hi, PH = g.H + g.pad_lo + g.pad_hi, PW = g.W + g.pad_lo + g.pad_hi;
+    const int M = PD * PH * PW;
+    float scale[8], shift[8], drop[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) o[k] = 0.f;
-            store8<T>(y + i * 8, o);
-            continue;
-        }
-        if (oob) { d = reflect1(d, g.D); h = reflect1(h, g.H); w = reflect1(w, g.W); }
-        size_t src = ((((size_t)n * g.D + d) * g.H + h) * g.W + w) * g.C + c8 * 8;
-        float f[8];
-        load8<T>(x + src, f);
-        int sc = n * g.C + c8 * 8;
-        float r[8];
-        if (res) load8<T>(res + src, r);
+    for (int k = 0; k < 8; k++) {
+        const int c = c8 * 8 + k, sc = n * g.C + c;
+        scale[k] = a.gamma[c] * a.rstd[sc];
+        shift[k] = a.beta[c] - a.mean[sc] * scale[k];
+        drop[k] = a.drop ? a.drop[sc] : 1.f;
+    }
+    const size_t in_sample = (size_t)g.D * g.H * g.W * g.C;
+    const T* xn = x + (size_t)n * in_sample + c8 * 8;
+    const T* rn = res ? res + (size_t)n * in_sample + c8 * 8 : nullptr;
+    T* yn = y + (size_t)n * M * g.C + c8 * 8;
+    const int S = gridDim.x * nvl;
+    VoxIter it;
+    it.init(blockIdx.x * nvl + vl, S, PH, PW);
+    for (int v = blockIdx.x * nvl + vl; v < M; v += U * S) {
+        Raw<T> rx[U], rr[U];
+        int src[U];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            float scale = a.gamma[c8 * 8 + k] * a.rstd[sc + k];
-            float z = (f[k] - a.mean[sc + k]) * scale + a.beta[c8 * 8 + k];
-            float v = act_fwd(z, a.act, a.slope);
-            if (a.drop) v *= a.drop[sc + k];
-            if (res) v += r[k];
-            o[k] = v;
+        for (int u = 0; u < U; u++) {
+            src[u] = -1;
+            if (v + u * S < M) {
+                int d = it.pd - g.pad_lo, h = it.ph - g.pad_lo, w = it.pw - g.pad_lo;
+                const bool oob = (unsigned)d >= (unsigned)g.D || (unsigned)h >= (unsigned)g.H || (unsigned)w >= (unsigned)g.W;
+                if (!(oob && g.pad_mode == VG_PAD_ZERO)) {
+                    if (oob) { d = reflect1(d, g.D); h = reflect1(h, g.H); w = reflect1(w, g.W); }
+                    src[u] = (d * g.H + h) * g.W + w;
+                    load_raw<T>(xn + (size_t)src[u] * g.C, rx[u]);
+                    if (rn) load_raw<T>(rn + (size_t)src[u] * g.C, rr[u]);
+                }
+            }
+            it.next();
         }
-        if (a.noise) {
-            // explicit noise tensor: padded layout for REFLECT (noise is added after the pad layer),
-            // unpadded layout for ZERO ('same' convs pad after the noise layer)
-            size_t ni = g.pad_mode == VG_PAD_REFLECT ? i * 8 : src;
 #pragma unroll
-            for (int k = 0; k < 8; k++) o[k] += a.noise[ni + k];
-        } else if (a.noise_std > 0.f) {
-            uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-            uint4 r0 = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0u, 0x56414e47u), key);
-            uint4 r1 = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 1u, 0x56414e47u), key);
-            float2 n0 = box_muller(r0.x, r0.y), n1 = box_muller(r0.z, r0.w), n2 = box_muller(r1.x, r1.y),
-                   n3 = box_muller(r1.z, r1.w);
-            o[0] += a.noise_std * n0.x; o[1] += a.noise_std * n0.y; o[2] += a.noise_std * n1.x; o[3] += a.noise_std * n1.y;
-            o[4] += a.noise_std * n2.x; o[5] += a.noise_std * n2.y; o[6] += a.noise_std * n3.x; o[7] += a.noise_std * n3.y;
+        for (int u = 0; u < U; u++) {
+            const int vv = v + u * S;
+            if (vv >= M) continue;
+            float o[8];
+            if (src[u] < 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) o[k] = 0.f;
+            } else {
+                float f[8];
+                unpack_raw(rx[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; k++) o[k] = act_fwd(fmaf(f[k], scale[k], shift[k]), a.act, a.slope) * drop[k];
+                if (rn) {
+                    unpack_raw(rr[u], f);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) o[k] += f[k];
+                }
+                if (a.noise) {
+                    // explicit noise tensor: padded layout for REFLECT (noise is added after the pad layer),
+                    // unpadded layout for ZERO ('same' convs pad after the noise layer)
+                    const float* np = g.pad_mode == VG_PAD_REFLECT ? a.noise + ((size_t)n * M + vv) * g.C + c8 * 8
+                                                                   : a.noise + (size_t)n * in_sample + (size_t)src[u] * g.C + c8 * 8;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) o[k] += np[k];
+                } else if (a.noise_std > 0.f) {
+                    const unsigned long long i = ((unsigned long long)n * M + vv) * cg + c8;
+                    uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                    uint4 r0 = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0u, 0x56414e47u), key);
+                    uint4 r1 = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 1u, 0x56414e47u), key);
+                    float2 n0 = box_muller(r0.x, r0.y), n1 = box_muller(r0.z, r0.w), n2 = box_muller(r1.x, r1.y),
+                           n3 = box_muller(r1.z, r1.w);
+                    o[0] += a.noise_std * n0.x; o[1] += a.noise_std * n0.y; o[2] += a.noise_std * n1.x; o[3] += a.noise_std * n1.y;
+                    o[4] += a.noise_std * n2.x; o[5] += a.noise_std * n2.y; o[6] += a.noise_std * n3.x; o[7] += a.noise_std * n3.y;
+                }
+            }
+            store8<T>(yn + (size_t)vv * g.C, o);
         }
-        store8<T>(y + i * 8, o);
     }
 }
 
 // ------------------------------------------------------------------ backward
-// gradient w.r.t. the (unpadded) apply output = incoming gradient in padded layout folded back:
-// REFLECT: every padded position whose mirror is this voxel; ZERO: the interior only.
-template <typename T>
-__device__ __forceinline__ void load_folded(const T* __restrict__ dy, const Geo& g, int n, int d, int h, int w, int c8,
-                                            float* out) {
-    int PH = g.H + g.pad_lo + g.pad_hi, PW = g.W + g.pad_lo + g.pad_hi, PD = g.D + g.pad_lo + g.pad_hi;
-    if (g.pad_lo == 0 && g.pad_hi == 0) {
-        load8<T>(dy + ((((size_t)n * g.D + d) * g.H + h) * g.W + w) * g.C + c8 * 8, out);
-        return;
-    }
-    if (g.pad_mode == VG_PAD_ZERO) {
-        load8<T>(dy + ((((size_t)n * PD + d + g.pad_lo) * PH + h + g.pad_lo) * PW + w + g.pad_lo) * g.C + c8 * 8, out);
-        return;
-    }
-    // REFLECT, pad 1 each side
-    int dd[2], hh[2], ww[2], nd = 1, nh = 1, nw = 1;
-    dd[0] = d + 1; hh[0] = h + 1; ww[0] = w + 1;
-    // (for S==3 a voxel can be the mirror of both borders; handled by the two independent tests)
-    int dd2[3], hh2[3], ww2[3];
-    dd2[0] = d + 1; nd = 1; if (d == 1) dd2[nd++] = 0; if (d == g.D - 2) dd2[nd++] = g.D + 1;
-    hh2[0] = h + 1; nh = 1; if (h == 1) hh2[nh++] = 0; if (h == g.H - 2) hh2[nh++] = g.H + 1;
-    ww2[0] = w + 1; nw = 1; if (w == 1) ww2[nw++] = 0; if (w == g.W - 2) ww2[nw++] = g.W + 1;
-    (void)dd; (void)hh; (void)ww;
-#pragma unroll
-    for (int k = 0; k < 8; k++) out[k] = 0.f;
-    for (int a = 0; a < nd; a++)
-        for (int b = 0; b < nh; b++)
-            for (int c = 0; c < nw; c++) {
-                float f[8];
-                load8<T>(dy + ((((size_t)n * PD + dd2[a]) * PH + hh2[b]) * PW + ww2[c]) * g.C + c8 * 8, f);
-#pragma unroll
-                for (int k = 0; k < 8; k++) out[k] += f[k];
-            }
-}
-
 struct BwdArgs {
     const float *mean, *rstd, *gamma, *beta, *drop;
     float slope;
     int act;
 };
 
-// partial[(n*nblk+blk)*C*2 + c*2 + {0,1}] = sum g, sum g*xhat  with g = fold(dy)*drop*act'(z)
+// partial[(n*nblk+blk)*C*2 + c*2 + {0,1}] = sum g, sum g*xhat  with g = dy*drop*act'(z).  The sums are linear in
+// dy, so the pass walks the PADDED gradient tensor and reads x at the mirrored voxel: no folding needed here.
 template <typename T>
-__global__ void __launch_bounds__(NT) in_bwd_partial_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g,
-                                                            BwdArgs a, int nblk, float* __restrict__ partial) {
+__global__ void __launch_bounds__(NT, 2) in_bwd_partial_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g,
+                                                            BwdArgs a, float* __restrict__ partial) {
     extern __shared__ float sm[];
-    int n = blockIdx.y, blk = blockIdx.x;
-    int C = g.C, cg = C / 8, nvl = NT / cg;
-    int c8 = threadIdx.x % cg, vl = threadIdx.x / cg;
-    size_t V = (size_t)g.D * g.H * g.W;
-    float s1[8], s2[8];
+    const int n = blockIdx.y, C = g.C, cg = C / 8;
+    const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
+    const int PD = g.D + g.pad_lo + g.pad_hi, PH = g.H + g.pad_lo + g.pad_hi, PW = g.W + g.pad_lo + g.pad_hi;
+    const int M = PD * PH * PW;
+    float mu[8], rs[8], ga[8], be[8], dr[8], s1[8], s2[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) s1[k] = s2[k] = 0.f;
-    size_t per = (V + nblk - 1) / nblk;
-    size_t v0 = (size_t)blk * per, v1 = v0 + per < V ? v0 + per : V;
-    if (vl < nvl) {
-        float mu[8], rs[8], ga[8], be[8], dr[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            mu[k] = a.mean[n * C + c8 * 8 + k]; rs[k] = a.rstd[n * C + c8 * 8 + k];
-            ga[k] = a.gamma[c8 * 8 + k]; be[k] = a.beta[c8 * 8 + k];
-            dr[k] = a.drop ? a.drop[n * C + c8 * 8 + k] : 1.f;
-        }
-        for (size_t v = v0 + vl; v < v1; v += nvl) {
-            int w = (int)(v % g.W), h = (int)((v / g.W) % g.H), d = (int)(v / ((size_t)g.W * g.H));
-            float f[8], gy[8];
-            load8<T>(x + ((size_t)n * V + v) * C + c8 * 8, f);
-            load_folded<T>(dy, g, n, d, h, w, c8, gy);
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                float xh = (f[k] - mu[k]) * rs[k];
-                float z = xh * ga[k] + be[k];
-                float gg = gy[k] * dr[k] * act_grad(z, a.act, a.slope);
-                s1[k] += gg;
-                s2[k] += gg * xh;
-            }
-        }
-        float* row = sm + ((size_t)vl * C + c8 * 8) * 2;
-#pragma unroll
-        for (int k = 0; k < 8; k++) { row[2 * k] = s1[k]; row[2 * k + 1] = s2[k]; }
+    for (int k = 0; k < 8; k++) {
+        const int c = c8 * 8 + k;
+        mu[k] = a.mean[n * C + c]; rs[k] = a.rstd[n * C + c];
+        ga[k] = a.gamma[c]; be[k] = a.beta[c];
+        dr[k] = a.drop ? a.drop[n * C + c] : 1.f;
+        s1[k] = s2[k] = 0.f;
     }
+    const T* xn = x + (size_t)n * g.D * g.H * g.W * C + c8 * 8;
+    const T* dyn = dy + (size_t)n * M * C + c8 * 8;
+    const int S = gridDim.x * nvl;
+    VoxIter it;
+    it.init(blockIdx.x * nvl + vl, S, PH, PW);
+    for (int v = blockIdx.x * nvl + vl; v < M; v += U * S) {
+        Raw<T> rx[U], rg[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            ok[u] = false;
+            if (v + u * S < M) {
+                int d = it.pd - g.pad_lo, h = it.ph - g.pad_lo, w = it.pw - g.pad_lo;
+                const bool oob = (unsigned)d >= (unsigned)g.D || (unsigned)h >= (unsigned)g.H || (unsigned)w >= (unsigned)g.W;
+                if (!(oob && g.pad_mode == VG_PAD_ZERO)) {
+                    if (oob) { d = reflect1(d, g.D); h = reflect1(h, g.H); w = reflect1(w, g.W); }
+                    ok[u] = true;
+                    load_raw<T>(xn + (size_t)((d * g.H + h) * g.W + w) * C, rx[u]);
+                    load_raw<T>(dyn + (size_t)(v + u * S) * C, rg[u]);
+                }
+            }
+            it.next();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (ok[u]) {
+                float f[8], gy[8];
+                unpack_raw(rx[u], f);
+                unpack_raw(rg[u], gy);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    float xh = (f[k] - mu[k]) * rs[k];
+                    float gg = gy[k] * dr[k] * act_grad(fmaf(xh, ga[k], be[k]), a.act, a.slope);
+                    s1[k] += gg;
+                    s2[k] += gg * xh;
+                }
+            }
+    }
+    float* row = sm + ((size_t)vl * C + c8 * 8) * 2;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { row[2 * k] = s1[k]; row[2 * k + 1] = s2[k]; }
     __syncthreads();
-    float* out = partial + ((size_t)n * nblk + blk) * C * 2;
-    for (int i = threadIdx.x; i < C * 2; i += NT) {
+    float* out = partial + ((size_t)n * gridDim.x + blockIdx.x) * C * 2;
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
         float acc = 0.f;
         for (int l = 0; l < nvl; l++) acc += sm[(size_t)l * C * 2 + i];
         out[i] = acc;
@@ -258,7 +314,8 @@ __global__ void __launch_bounds__(256) in_bwd_final_kernel(const float* __restri
                                                            float* __restrict__ dbeta) {
     int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= N * C) return;
-    int n = i / C, c = i % C;
+    int c = i % C;
+    int n = i / C;
     double s1 = 0, s2 = 0;
     for (int b = lane; b < nblk; b += 32) {
         const float* p = partial + (((size_t)n * nblk + b) * C + c) * 2;
@@ -275,57 +332,111 @@ __global__ void __launch_bounds__(256) in_bwd_final_kernel(const float* __restri
     }
 }
 
-// dx = gamma*rstd*(g - S1/V - xhat*S2/V); dres = fold(dy) (optional)
+// dx = gamma*rstd*(g - S1/V - xhat*S2/V) with g = fold(dy)*drop*act'(z); dres = fold(dy) (optional).
+// fold: REFLECT -> every padded position whose mirror is this voxel (1 for interior voxels, up to 8 on the
+// shell); ZERO -> the interior only.
 template <typename T>
-__global__ void __launch_bounds__(NT) in_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g, BwdArgs a,
+__global__ void __launch_bounds__(NT, 2) in_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g, BwdArgs a,
                                                           const float* __restrict__ sums, T* __restrict__ dx,
                                                           T* __restrict__ dres, int accumulate_dx) {
-    int C = g.C, cg = C / 8;
-    size_t V = (size_t)g.D * g.H * g.W;
-    size_t total = (size_t)g.N * V * cg;
-    float invV = 1.f / (float)V;
-    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
-        int c8 = (int)(i % cg);
-        size_t nv = i / cg;
-        size_t v = nv % V;
-        int n = (int)(nv / V);
-        int w = (int)(v % g.W), h = (int)((v / g.W) % g.H), d = (int)(v / ((size_t)g.W * g.H));
-        float f[8], gy[8], o[8];
-        load8<T>(x + i * 8, f);
-        load_folded<T>(dy, g, n, d, h, w, c8, gy);
-        if (dres) store8<T>(dres + i * 8, gy);
-        if (accumulate_dx) load8<T>(dx + i * 8, o);
+    const int n = blockIdx.y, C = g.C, cg = C / 8;
+    const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
+    const int PH = g.H + g.pad_lo + g.pad_hi, PW = g.W + g.pad_lo + g.pad_hi, PD = g.D + g.pad_lo + g.pad_hi;
+    const int V = g.D * g.H * g.W;
+    const float invV = 1.f / (float)V;
+    const bool refl = g.pad_mode == VG_PAD_REFLECT && (g.pad_lo | g.pad_hi);
+    float mu[8], rs[8], ga[8], be[8], dr[8], c1[8], c2[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            int sc = n * C + c8 * 8 + k;
-            float rs = a.rstd[sc], ga = a.gamma[c8 * 8 + k];
-            float xh = (f[k] - a.mean[sc]) * rs;
-            float z = xh * ga + a.beta[c8 * 8 + k];
-            float gg = gy[k] * (a.drop ? a.drop[sc] : 1.f) * act_grad(z, a.act, a.slope);
-            float val = ga * rs * (gg - sums[2 * sc] * invV - xh * sums[2 * sc + 1] * invV);
-            o[k] = accumulate_dx ? o[k] + val : val;
+    for (int k = 0; k < 8; k++) {
+        const int c = c8 * 8 + k, sc = n * C + c;
+        mu[k] = a.mean[sc]; rs[k] = a.rstd[sc];
+        ga[k] = a.gamma[c]; be[k] = a.beta[c];
+        dr[k] = a.drop ? a.drop[sc] : 1.f;
+        c1[k] = sums[2 * sc] * invV;
+        c2[k] = sums[2 * sc + 1] * invV;
+    }
+    const T* xn = x + (size_t)n * V * C + c8 * 8;
+    const T* dyn = dy + (size_t)n * PD * PH * PW * C + c8 * 8;
+    T* dxn = dx + (size_t)n * V * C + c8 * 8;
+    T* drn = dres ? dres + (size_t)n * V * C + c8 * 8 : nullptr;
+    const int S = gridDim.x * nvl;
+    VoxIter it;
+    it.init(blockIdx.x * nvl + vl, S, g.H, g.W);
+    for (int v = blockIdx.x * nvl + vl; v < V; v += U * S) {
+        Raw<T> rx[U], rg[U];
+        int cd[U], ch[U], cw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            cd[u] = it.pd; ch[u] = it.ph; cw[u] = it.pw;
+            if (v + u * S < V) {
+                load_raw<T>(xn + (size_t)(v + u * S) * C, rx[u]);
+                load_raw<T>(dyn + (size_t)(((cd[u] + g.pad_lo) * PH + ch[u] + g.pad_lo) * PW + cw[u] + g.pad_lo) * C, rg[u]);
+            }
+            it.next();
         }
-        store8<T>(dx + i * 8, o);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int vv = v + u * S;
+            if (vv >= V) continue;
+            float f[8], gy[8];
+            unpack_raw(rx[u], f);
+            unpack_raw(rg[u], gy);
+            const int d = cd[u], h = ch[u], w = cw[u];
+            if (refl && (d == 1 || d == g.D - 2 || h == 1 || h == g.H - 2 || w == 1 || w == g.W - 2)) {
+                // shell voxel: add the mirrored halo positions (rare)
+                int dd[3], hh[3], ww[3], nd = 1, nh = 1, nw = 1;
+                dd[0] = d + 1; hh[0] = h + 1; ww[0] = w + 1;
+                if (d == 1) dd[nd++] = 0;
+                if (d == g.D - 2) dd[nd++] = g.D + 1;
+                if (h == 1) hh[nh++] = 0;
+                if (h == g.H - 2) hh[nh++] = g.H + 1;
+                if (w == 1) ww[nw++] = 0;
+                if (w == g.W - 2) ww[nw++] = g.W + 1;
+                for (int i0 = 0; i0 < nd; i0++)
+                    for (int i1 = 0; i1 < nh; i1++)
+                        for (int i2 = 0; i2 < nw; i2++) {
+                            if (i0 + i1 + i2 == 0) continue;
+                            float t[8];
+                            load8<T>(dyn + (size_t)((dd[i0] * PH + hh[i1]) * PW + ww[i2]) * C, t);
+#pragma unroll
+                            for (int k = 0; k < 8; k++) gy[k] += t[k];
+                        }
+            }
+            if (drn) store8<T>(drn + (size_t)vv * C, gy);
+            float o[8];
+            if (accumulate_dx) load8<T>(dxn + (size_t)vv * C, o);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                float xh = (f[k] - mu[k]) * rs[k];
+                float gg = gy[k] * dr[k] * act_grad(fmaf(xh, ga[k], be[k]), a.act, a.slope);
+                float val = ga[k] * rs[k] * (gg - c1[k] - xh * c2[k]);
+                o[k] = accumulate_dx ? o[k] + val : val;
+            }
+            store8<T>(dxn + (size_t)vv * C, o);
+        }
     }
 }
 
-inline int pick_nblk(size_t V, int N) {
-    long long want = (148LL * 6 + N - 1) / N;
-    long long maxb = (long long)((V + 255) / 256);
+inline int block_threads(int C) { int cg = C / 8; return (NT / cg) * cg; }
+// blocks per sample for a pass over `vox` voxels: ~8 waves of 148 SMs over the whole batch, at least U voxels per lane
+inline int pick_grid(long long vox, int N, int C) {
+    long long nvl = block_threads(C) / (C / 8);
+    long long want = (148 * 8 + N - 1) / N;
+    long long maxb = (vox + nvl * U - 1) / (nvl * U);
     if (want > maxb) want = maxb;
-    if (want < 1) want = 1;
-    return (int)want;
+    return want < 1 ? 1 : (int)want;
 }
 
 template <typename T>
-int stats_impl(const T* x, int N, size_t V, int C, float* mean, float* rstd, void* ws, size_t ws_bytes, cudaStream_t st) {
-    int nblk = pick_nblk(V, N);
+int stats_impl(const T* x, int N, int D, int H, int W, int C, float* mean, float* rstd, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const long long V = (long long)D * H * W;
+    if (V * C >= (1LL << 31)) return VG_ERR_UNSUPPORTED;
+    const int nblk = pick_grid(V, N, C), nthr = block_threads(C);
     size_t need = (size_t)N * nblk * C * 2 * sizeof(float);
     if (ws_bytes < need) return VG_ERR_WORKSPACE;
-    int cg = C / 8, nvl = NT / cg;
-    size_t smem = (size_t)nvl * C * 2 * sizeof(float);
-    in_stats_partial_kernel<T><<<dim3(nblk, N), NT, smem, st>>>(x, V, C, nblk, (float*)ws); VG_LAUNCHED(1);
-    in_stats_final_kernel<T><<<vg_cdiv(N * C, 8), 256, 0, st>>>(x, (const float*)ws, V, C, nblk, N, mean, rstd); VG_LAUNCHED(1);
+    size_t smem = (size_t)(nthr / (C / 8)) * C * 2 * sizeof(float);
+    in_stats_partial_kernel<T><<<dim3(nblk, N), nthr, smem, st>>>(x, (int)V, C, (float*)ws); VG_LAUNCHED(1);
+    in_stats_final_kernel<T><<<vg_cdiv(N * C, 8), 256, 0, st>>>(x, (const float*)ws, (size_t)V, C, nblk, N, mean, rstd); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -335,17 +446,17 @@ int stats_impl(const T* x, int N, size_t V, int C, float* mean, float* rstd, voi
 extern "C" {
 
 size_t vg_instnorm_workspace_bytes(int N, int D, int H, int W, int C) {
-    size_t V = (size_t)D * H * W;
-    return (size_t)N * pick_nblk(V, N) * C * 2 * sizeof(float) + (size_t)N * C * 2 * sizeof(float);
+    // partials of the widest pass (the backward reduction walks the padded volume: up to (D+3)(H+3)(W+3)) + per-(n,c) sums
+    size_t nblk = (size_t)pick_grid((long long)(D + 3) * (H + 3) * (W + 3), N, C);
+    return (size_t)N * nblk * C * 2 * sizeof(float) + (size_t)N * C * 2 * sizeof(float);
 }
 
 int vg_instnorm_stats(const void* x, int dtype, int N, int D, int H, int W, int C, float* mean, float* rstd, void* ws,
                       size_t ws_bytes, void* stream) {
     VG_REQUIRE(x && mean && rstd && ws && N > 0 && C % 8 == 0 && C >= 8 && C <= 8 * NT);
-    size_t V = (size_t)D * H * W;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == VG_BF16) return stats_impl<bf16>((const bf16*)x, N, V, C, mean, rstd, ws, ws_bytes, st);
-    if (dtype == VG_F32) return stats_impl<float>((const float*)x, N, V, C, mean, rstd, ws, ws_bytes, st);
+    if (dtype == VG_BF16) return stats_impl<bf16>((const bf16*)x, N, D, H, W, C, mean, rstd, ws, ws_bytes, st);
+    if (dtype == VG_F32) return stats_impl<float>((const float*)x, N, D, H, W, C, mean, rstd, ws, ws_bytes, st);
     return VG_ERR_INVALID;
 }
 
@@ -353,23 +464,24 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
                       const float* rstd, const float* gamma, const float* beta, const float* drop, const float* noise,
                       void* stream) {
     VG_REQUIRE(d && x && y && mean && rstd && gamma && beta);
-    VG_REQUIRE(d->C % 8 == 0 && d->pad_lo >= 0 && d->pad_hi >= 0);
+    VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT && d->pad_lo >= 0 && d->pad_hi >= 0);
     if (d->pad_mode == VG_PAD_REFLECT && (d->pad_lo || d->pad_hi))
         VG_REQUIRE(d->pad_lo == 1 && d->pad_hi == 1 && d->D >= 2 && d->H >= 2 && d->W >= 2);
     Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode};
     ApplyArgs a{mean, rstd, gamma, beta, drop, noise, d->slope, d->noise_std, d->act, d->seed};
-    size_t P = (size_t)(d->D + d->pad_lo + d->pad_hi) * (d->H + d->pad_lo + d->pad_hi) * (d->W + d->pad_lo + d->pad_hi);
-    size_t total = (size_t)d->N * P * (d->C / 8);
-    int grid = vg_grid_for(total, NT, 16);
+    const int pp = d->pad_lo + d->pad_hi;
+    const long long M = (long long)(d->D + pp) * (d->H + pp) * (d->W + pp);
+    VG_REQUIRE(M * d->C < (1LL << 31));
+    dim3 grid(pick_grid(M, d->N, d->C), d->N);
+    const int nthr = block_threads(d->C);
     cudaStream_t st = (cudaStream_t)stream;
     if (d->dtype == VG_BF16) {
-        in_apply_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, g, a); VG_LAUNCHED(1);
-    }
-    else if (d->dtype == VG_F32) {
-        in_apply_kernel<float><<<grid, NT, 0, st>>>((const float*)x, (const float*)residual, (float*)y, g, a); VG_LAUNCHED(1);
-    }
-    else
+        in_apply_kernel<bf16><<<grid, nthr, 0, st>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, g, a); VG_LAUNCHED(1);
+    } else if (d->dtype == VG_F32) {
+        in_apply_kernel<float><<<grid, nthr, 0, st>>>((const float*)x, (const float*)residual, (float*)y, g, a); VG_LAUNCHED(1);
+    } else {
         return VG_ERR_INVALID;
+    }
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -383,27 +495,28 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
     VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT);
     Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode};
     BwdArgs a{mean, rstd, gamma, beta, drop, d->slope, d->act};
-    size_t V = (size_t)d->D * d->H * d->W;
-    int nblk = pick_nblk(V, d->N);
+    const int pp = d->pad_lo + d->pad_hi;
+    const long long M = (long long)(d->D + pp) * (d->H + pp) * (d->W + pp);
+    VG_REQUIRE(M * d->C < (1LL << 31));
+    const int nblk = pick_grid(M, d->N, d->C);
     size_t need_p = (size_t)d->N * nblk * d->C * 2 * sizeof(float), need_s = (size_t)d->N * d->C * 2 * sizeof(float);
     if (ws_bytes < need_p + need_s) return VG_ERR_WORKSPACE;
     float* partial = (float*)ws;
     float* sums = (float*)((char*)ws + need_p);
-    int cg = d->C / 8, nvl = NT / cg;
-    size_t smem = (size_t)nvl * d->C * 2 * sizeof(float);
-    size_t total = (size_t)d->N * V * cg;
-    int grid = vg_grid_for(total, NT, 16);
+    const int nthr = block_threads(d->C);
+    size_t smem = (size_t)(nthr / (d->C / 8)) * d->C * 2 * sizeof(float);
+    dim3 grid2(pick_grid((long long)d->D * d->H * d->W, d->N, d->C), d->N);
     cudaStream_t st = (cudaStream_t)stream;
     if (d->dtype == VG_BF16) {
-        in_bwd_partial_kernel<bf16><<<dim3(nblk, d->N), NT, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, nblk, partial); VG_LAUNCHED(1);
+        in_bwd_partial_kernel<bf16><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial); VG_LAUNCHED(1);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta); VG_LAUNCHED(1);
-        in_bwd_apply_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres,
-                                                      accumulate_dx); VG_LAUNCHED(1);
+        in_bwd_apply_kernel<bf16><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres,
+                                                         accumulate_dx); VG_LAUNCHED(1);
     } else if (d->dtype == VG_F32) {
-        in_bwd_partial_kernel<float><<<dim3(nblk, d->N), NT, smem, st>>>((const float*)dy, (const float*)x, g, a, nblk, partial); VG_LAUNCHED(1);
+        in_bwd_partial_kernel<float><<<dim3(nblk, d->N), nthr, smem, st>>>((const float*)dy, (const float*)x, g, a, partial); VG_LAUNCHED(1);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta); VG_LAUNCHED(1);
-        in_bwd_apply_kernel<float><<<grid, NT, 0, st>>>((const float*)dy, (const float*)x, g, a, sums, (float*)dx, (float*)dres,
-                                                       accumulate_dx); VG_LAUNCHED(1);
+        in_bwd_apply_kernel<float><<<grid2, nthr, 0, st>>>((const float*)dy, (const float*)x, g, a, sums, (float*)dx, (float*)dres,
+                                                          accumulate_dx); VG_LAUNCHED(1);
     } else {
         return VG_ERR_INVALID;
     }

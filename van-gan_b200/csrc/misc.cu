@@ -210,6 +210,18 @@ __global__ void __launch_bounds__(NT) stitch_accumulate_kernel(float* __restrict
     }
 }
 
+// win[b][x][y][z] = vol[starts[b] + (x,y,z)]   (window extraction, custom_callback.py:167-169)
+__global__ void __launch_bounds__(NT) stitch_gather_kernel(const float* __restrict__ vol, int H, int W, int D, float* __restrict__ win,
+                                                           const int* __restrict__ starts, int B, int kH, int kW, int kD) {
+    size_t per = (size_t)kH * kW * kD, total = per * B;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        int b = (int)(i / per);
+        size_t r = i % per;
+        int z = (int)(r % kD), y = (int)((r / kD) % kW), x = (int)(r / ((size_t)kD * kW));
+        win[i] = vol[(((size_t)(starts[3 * b] + x)) * W + starts[3 * b + 1] + y) * D + starts[3 * b + 2] + z];
+    }
+}
+
 __device__ __forceinline__ uint32_t enc_f(float f) {
     uint32_t b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -327,6 +339,14 @@ int vg_clip_adam_step(float* w, const float* g, float* m, float* v, const long l
     seg_sqnorm_kernel<<<vg_grid_for(total / 4 + 1, NT, 8), NT, 0, st>>>(g, seg_offsets, nseg, norm_ws, total); VG_LAUNCHED(1);
     clip_adam_kernel<<<vg_grid_for(total, NT, 16), NT, 0, st>>>(w, g, m, v, seg_offsets, nseg, norm_ws, lr_t, beta1, beta2, eps,
                                                                clipnorm, total); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_stitch_gather(const float* vol, int H, int W, int D, float* win, const int* starts, int B, int kH, int kW, int kD, void* stream) {
+    VG_REQUIRE(vol && win && starts && B > 0);
+    stitch_gather_kernel<<<vg_grid_for((size_t)B * kH * kW * kD, NT, 16), NT, 0, (cudaStream_t)stream>>>(vol, H, W, D, win, starts, B, kH,
+                                                                                                   kW, kD); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
