@@ -148,3 +148,6 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
                  cudaStream_t stream);
 int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, int dgrad, int ad, int ah, int aw, int td, int th,
                int tw, cudaStream_t st);
+// tensor-core (tcgen05) weight-gradient path, wgrad_tc.cu
+int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, int XH, int XW, int Cx, int OD, int OH, int OW, int Cy,
+                    int K, cudaStream_t stream);

@@ -685,6 +685,15 @@ inline bool tc_enabled() {
     }
     return v == 1;
 }
+// VG_WGRAD_PATH=mma forces the mma.sync weight-gradient kernel (A/B testing and cross-checks)
+inline bool tc_wgrad_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VG_WGRAD_PATH");
+        v = (e && e[0] == 'm') ? 0 : 1;
+    }
+    return v == 1 && tc_enabled();
+}
 inline size_t mma_fwd_elems(const vg_conv3d_desc* d) {
     return d->Cin == 1 ? 0 : (size_t)d->K * d->K * d->K * rup(d->Cout, NPAD) * d->Cin;
 }
@@ -887,6 +896,11 @@ int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, floa
                                                                                 d->IH, d->IW, OD, OH, OW, d->Cin, d->K, per_block); VG_LAUNCHED(1);
         VG_CHECK_LAUNCH();
         return VG_OK;
+    }
+    if (tc_wgrad_enabled() && d->stride == 1) {
+        int rc = vg_wg_tc_launch((const bf16*)x, (const bf16*)dy, dw, d->N, d->ID, d->IH, d->IW, d->Cin, OD, OH, OW, d->Cout, d->K, st);
+        if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
+        if (rc != VG_ERR_UNSUPPORTED) return rc;
     }
     WGrad p{};
     p.x = (const bf16*)x; p.dy = (const bf16*)dy; p.dw = dw;

@@ -1,0 +1,432 @@
+// Conv3D weight gradient (stride 1) on the 5th-generation tensor cores.
+//
+// Replaces cuDNN Conv3DBackpropFilterV2 behind every stride-1 Keras Conv3D on the hot path
+// (resunet_model.py:64-65,89-90,96,133-134; discriminator.py:91-103), i.e. the `minimize` calls at
+// vangan.py:426-438.
+//
+//     dW[td,th,tw][ci][co] = sum over output voxels v of  X[v + t][ci] * dY[v][co]
+//
+// GEMM view: the reduction (K) dimension is the voxel index, which in NDHWC storage is the SLOW index
+// of both operands -> both operands are "MN-major" for tcgen05.mma.  One MMA consumes 16 consecutive
+// w-voxels (K = 16).  The two operands are staged in shared memory as planes of 16-byte cells (8 channels
+// of one voxel), w-contiguous, so 8 consecutive voxels x 8 channels form one canonical 128-byte
+// no-swizzle core matrix, and a filter tap is nothing but a different descriptor start address.
+//
+// Channel counts on this path are small (16..64 at the expensive resolutions), far below the MMA's
+// M = 64/128 and a poor match for N, so two folds turn unused MMA area into useful taps:
+//   * th-fold (M side): the X planes are laid out [d][chunk][h][plane][w]; M-groups then run over
+//     (row offset j, plane) at one constant stride, so an M = 128 (or 64) operand holds R = M/CC
+//     consecutive h-rows of a CC-channel chunk: D rows (j, ci) accumulate the taps th = th_base + j.
+//   * td-fold (N side): the dY planes are laid out [h][d][plane][w] with K-1 zero slices on either side,
+//     so an N = K*CO operand holds K consecutive d-slices: D columns (r, co) accumulate td = K-1-r.
+// The remaining tap index (tw, and th_base / td when not folded) selects the TMEM accumulator.
+// A CTA owns a set of accumulators (<= 512 TMEM columns) for one (ci-block, co-block, tap-set) tile and a
+// split-K share of the voxel bricks; it finishes with fp32 red.global.add into dW (Keras layout).
+//
+// Roles (416 threads): warps 0-7 gather the X halo brick and the dY brick (16-byte cp.async, zero fill
+// outside the tensors), warp 8 issues tcgen05.mma (one elected lane) and owns TMEM, warps 9-12 drain the
+// accumulators at the end.  Stages form a full/empty mbarrier ring released by tcgen05.commit.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "tc_ptx.cuh"
+
+namespace {
+
+using namespace tcp;
+
+constexpr int WG_NPROD = 256;                 // producer threads: warps 0..7
+constexpr int WG_MMA_WARP = WG_NPROD / 32;    // warp 8 issues the MMAs, warps 9..12 drain TMEM
+constexpr int WG_THREADS = WG_NPROD + 32 + 128;
+constexpr int WG_MAXACC = 16;
+constexpr int WG_KW = 16;   // voxels along w per MMA (K of the bf16 MMA)
+// Plane pitches (in 16-byte cells) are ODD: for a fixed k the MMA reads one 16-byte row from every M/N-group, i.e. addresses
+// at a stride of one plane pitch; an odd pitch spreads 8 consecutive groups over all 8 bank groups (no conflicts), whereas a
+// pitch that is a multiple of 8 cells serialises them (measured: 16-29 B/cycle of operand fetch).
+constexpr int WG_XW = 19;   // X plane pitch: >= 16 + K - 1 for K <= 4
+constexpr int WG_YP = 17;   // dY plane pitch
+
+struct WgParams {
+    const bf16* x;
+    const bf16* dy;
+    float* dw;
+    int Nb, XD, XH, XW, Cx, OD, OH, OW, Cy, K;
+    int M, CC, R, PLC, NCH, CB;     // MMA M; channels per chunk; rows folded; planes per chunk; chunks per CTA; CB = NCH*CC
+    int CO, NF, Nmma, NPLy;         // co block; slices folded (1 or K); MMA N = NF*CO; dY planes = CO/8
+    int nth, NTA, TPC, nsets;       // th bases; tap-accumulators in total / per CTA; tap sets
+    int n_co_blocks, tiles, ksplit;
+    int BDo, BHo, bd_tiles, bh_tiles, bw_tiles, nbricks;
+    int XDb, XHb, XHu, XWb, YDb, nB, ypad;   // XHu: rows that carry useful taps (<= XHb)
+    uint32_t x_bytes, stage_bytes, tmem_cols;
+    int stages;
+};
+
+// One gathered region: cells of 16 bytes (8 channels of one voxel).
+struct Region {
+    const bf16* g;        // sample base + channel offset
+    int gd0, gh0, gw0;    // global origin of the region
+    int GD, GH, GW, C;    // tensor bounds and channels per voxel
+    int nd, nh, nw, np;   // extents: slices, rows, voxels per row, planes (8-channel groups)
+    int sd, sh, sc, sp;   // shared-memory strides in cells: slice, row, chunk, plane (voxel stride = 1)
+    FastDiv by_segs, by_np, by_plc, by_nh;
+    int plc;
+};
+
+// 16-byte cp.async per cell (zero fill outside the tensor): no register staging, so a whole stage is in flight per SM.
+// Work unit = 32 consecutive cells of one (slice, row): the row decode is warp-uniform, lanes only split (voxel, plane).
+__device__ __forceinline__ void gather_region(const Region& r, uint32_t dst_base, int warp, int lane) {
+    const int cells = r.nw * r.np;
+    const int segs = (cells + 31) >> 5;
+    const int units = r.nd * r.nh * segs;
+#pragma unroll 2
+    for (int u = warp; u < units; u += WG_NPROD / 32) {
+        const uint32_t row = r.by_segs.div(u), seg = u - row * segs;
+        const uint32_t d = r.by_nh.div(row), h = row - d * r.nh;
+        const int gd = r.gd0 + (int)d, gh = r.gh0 + (int)h;
+        const bool rowok = (unsigned)gd < (unsigned)r.GD && (unsigned)gh < (unsigned)r.GH;
+        const bf16* srow = r.g + (((size_t)(rowok ? gd : 0) * r.GH + (rowok ? gh : 0)) * r.GW) * r.C;
+        const uint32_t drow = dst_base + (uint32_t)(d * r.sd + h * r.sh) * 16u;
+        const uint32_t e = seg * 32 + lane;
+        if (e < (uint32_t)cells) {
+            const uint32_t w = r.by_np.div(e), pp = e - w * r.np;
+            const uint32_t c = r.by_plc.div(pp), pl = pp - c * r.plc;
+            const int gw = r.gw0 + (int)w;
+            const bool ok = rowok && (unsigned)gw < (unsigned)r.GW;
+            const bf16* src = ok ? srow + (size_t)gw * r.C + pp * 8 : r.g;
+            const uint32_t dst = drow + (uint32_t)(c * r.sc + pl * r.sp + w) * 16u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+    }
+}
+
+struct IssueCtx {
+    uint64_t a_desc0, b_desc0;
+    uint32_t idesc, leader, tmem_base, sbase16, stage16, x16, full0, empty0, done_bar;
+    int a_sd, a_sh, b_sd, b_sh, nB, BHo, Nmma, stages, first, nbricks, step;
+};
+
+// The MMA warp's whole life: for every brick of this CTA wait for the stage, issue nB x BHo x NACC MMAs, release the stage.
+// Descriptors advance by plain 64-bit adds on the 14-bit start-address field (shared memory is < 256 KB, so no carry).
+template <int NACC>
+__device__ __forceinline__ void issue_bricks(const IssueCtx& c, const int* s_aoff) {
+    uint64_t adesc[NACC];
+    uint32_t tm[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; a++) {
+        adesc[a] = c.a_desc0 + (uint32_t)s_aoff[a];
+        tm[a] = c.tmem_base + (uint32_t)(a * c.Nmma);
+    }
+    int stage = 0;
+    uint32_t phase = 0, accflag = 0;
+    for (int brick = c.first; brick < c.nbricks; brick += c.step) {
+        mbar_wait(c.full0 + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t xs16 = c.sbase16 + stage * c.stage16;
+        uint32_t a_row = xs16, b_row = xs16 + c.x16;
+        for (int bs = 0; bs < c.nB; bs++) {
+            uint32_t a_pos = a_row, b_pos = b_row;
+            for (int h = 0; h < c.BHo; h++) {
+                if (c.leader) {
+                    const uint64_t bdesc = c.b_desc0 + b_pos;
+#pragma unroll
+                    for (int a = 0; a < NACC; a++) tc_mma(tm[a], adesc[a] + a_pos, bdesc, c.idesc, accflag);
+                }
+                accflag = 1u;
+                a_pos += c.a_sh; b_pos += c.b_sh;
+            }
+            a_row += c.a_sd; b_row += c.b_sd;
+        }
+        __syncwarp();
+        if (c.leader) tc_commit(c.empty0 + 8 * stage);
+        if (++stage == c.stages) { stage = 0; phase ^= 1; }
+    }
+    if (c.leader) tc_commit(c.done_bar);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* bar_base = smem + (size_t)p.stages * p.stage_bytes;
+    const uint32_t full0 = s_addr(bar_base), empty0 = full0 + 8 * p.stages, done_bar = empty0 + 8 * p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_base + 16 * p.stages + 16);
+    int* s_aoff = reinterpret_cast<int*>(bar_base + 16 * p.stages + 32);   // WG_MAXACC ints
+    const uint32_t sbase = s_addr(smem);
+
+    // ---- which tile / split is this CTA
+    const int tile = blockIdx.x % p.tiles, split = blockIdx.x / p.tiles;
+    const int set = tile % p.nsets;
+    const int cob = (tile / p.nsets) % p.n_co_blocks;
+    const int cib = tile / (p.nsets * p.n_co_blocks);
+    const int q0 = set * p.TPC;
+    const int nq = min(p.TPC, p.NTA - q0);
+    const int nacc = nq * p.NCH;
+    const bool fold = p.NF > 1;
+    // tap-accumulator q -> (tw fastest, then th base, then td)
+    int td_min = 1 << 30, thb_min = 1 << 30, tw_min = 1 << 30;
+    for (int i = 0; i < nq; i++) {
+        const int q = q0 + i;
+        const int tw = q % p.K, thb = (q / p.K) % p.nth, td = q / (p.K * p.nth);
+        td_min = min(td_min, td); thb_min = min(thb_min, thb); tw_min = min(tw_min, tw);
+    }
+    if (fold) td_min = 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(full0 + 8 * s, WG_NPROD);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(done_bar, 1);
+        mbar_init_fence();
+        for (int i = 0; i < nq; i++) {
+            const int q = q0 + i;
+            const int tw = q % p.K, thb = (q / p.K) % p.nth, td = fold ? 0 : q / (p.K * p.nth);
+            for (int c = 0; c < p.NCH; c++)
+                s_aoff[i * p.NCH + c] = ((((td - td_min) * p.NCH + c) * p.XHb + (thb - thb_min) * p.R) * p.PLC) * p.XWb + (tw - tw_min);
+        }
+    }
+    // zero the stages once: the dY pad slices (td-fold) are never written again
+    for (uint32_t o = threadIdx.x * 16u; o < (uint32_t)p.stages * p.stage_bytes; o += WG_THREADS * 16u)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(sbase + o), "r"(0) : "memory");
+    fence_async_smem();
+    if (warp == WG_MMA_WARP) tmem_alloc(s_addr(tmem_slot), p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < WG_MMA_WARP) {
+        // ------------------------------------------------------------------ gather producers
+        Region rx, ry;
+        rx.GD = p.XD; rx.GH = p.XH; rx.GW = p.XW; rx.C = p.Cx;
+        rx.nd = p.XDb; rx.nh = p.XHu; rx.nw = p.XWb; rx.np = p.NCH * p.PLC;
+        rx.sd = p.NCH * p.XHb * p.PLC * p.XWb; rx.sh = p.PLC * p.XWb; rx.sc = p.XHb * p.PLC * p.XWb; rx.sp = p.XWb; rx.plc = p.PLC;
+        rx.by_segs = FastDiv((rx.nw * rx.np + 31) >> 5); rx.by_np = FastDiv(rx.np); rx.by_plc = FastDiv(rx.plc); rx.by_nh = FastDiv(rx.nh);
+        ry.GD = p.OD; ry.GH = p.OH; ry.GW = p.OW; ry.C = p.Cy;
+        ry.nd = p.BDo; ry.nh = p.BHo; ry.nw = WG_KW; ry.np = p.NPLy;
+        ry.sd = p.NPLy * WG_YP; ry.sh = p.YDb * p.NPLy * WG_YP; ry.sc = 0; ry.sp = WG_YP; ry.plc = p.NPLy;
+        ry.by_segs = FastDiv((ry.nw * ry.np + 31) >> 5); ry.by_np = FastDiv(ry.np); ry.by_plc = FastDiv(ry.plc); ry.by_nh = FastDiv(ry.nh);
+        int stage = 0, prev_stage = -1;
+        uint32_t phase = 0;
+        for (int brick = split; brick < p.nbricks; brick += p.ksplit) {
+            int b = brick;
+            const int bw = b % p.bw_tiles; b /= p.bw_tiles;
+            const int bh = b % p.bh_tiles; b /= p.bh_tiles;
+            const int bd = b % p.bd_tiles;
+            const int n = b / p.bd_tiles;
+            rx.g = p.x + (size_t)n * p.XD * p.XH * p.XW * p.Cx + (size_t)cib * p.CB;
+            rx.gd0 = bd * p.BDo + td_min; rx.gh0 = bh * p.BHo + thb_min * p.R; rx.gw0 = bw * WG_KW + tw_min;
+            ry.g = p.dy + (size_t)n * p.OD * p.OH * p.OW * p.Cy + (size_t)cob * p.CO;
+            ry.gd0 = bd * p.BDo; ry.gh0 = bh * p.BHo; ry.gw0 = bw * WG_KW;
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t xs = sbase + stage * p.stage_bytes;
+            gather_region(rx, xs, warp, lane);
+            gather_region(ry, xs + p.x_bytes + (uint32_t)p.ypad * p.NPLy * WG_YP * 16u, warp, lane);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            if (prev_stage >= 0) {
+                // the previous brick's copies have landed: publish them to the async proxy and hand the stage to the MMA warp
+                asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+                fence_async_smem();
+                mbar_arrive(full0 + 8 * prev_stage);
+            }
+            prev_stage = stage;
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (prev_stage >= 0) {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            fence_async_smem();
+            mbar_arrive(full0 + 8 * prev_stage);
+        }
+    } else if (warp == WG_MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issuer
+        // One elected lane issues; the loops are warp-uniform so descriptors stay in uniform registers.  The issue loop is
+        // the critical resource of this kernel (one MMA is only 24-128 tensor-pipe cycles), hence the compile-time NACC.
+        IssueCtx c;
+        c.idesc = make_idesc_bf16(p.M, p.Nmma, 1, 1);
+        c.leader = elect_one();
+        c.a_desc0 = ((uint64_t)((uint32_t)p.XWb | (1u << 14)) << 32) | (8u << 16);   // SBO = X plane pitch | version ; LBO = 128 B
+        c.b_desc0 = ((uint64_t)((uint32_t)WG_YP | (1u << 14)) << 32) | (8u << 16);   // SBO = dY plane pitch
+        c.a_sd = p.NCH * p.XHb * p.PLC * p.XWb; c.a_sh = p.PLC * p.XWb;
+        c.b_sd = p.NPLy * WG_YP; c.b_sh = p.YDb * p.NPLy * WG_YP;
+        c.nB = p.nB; c.BHo = p.BHo; c.Nmma = p.Nmma; c.tmem_base = tmem_base;
+        c.sbase16 = sbase >> 4; c.stage16 = p.stage_bytes >> 4; c.x16 = p.x_bytes >> 4; c.stages = p.stages;
+        c.full0 = full0; c.empty0 = empty0; c.done_bar = done_bar;
+        c.first = split; c.nbricks = p.nbricks; c.step = p.ksplit;
+        switch (nacc) {
+            case 1: issue_bricks<1>(c, s_aoff); break;
+            case 2: issue_bricks<2>(c, s_aoff); break;
+            case 3: issue_bricks<3>(c, s_aoff); break;
+            case 4: issue_bricks<4>(c, s_aoff); break;
+            case 5: issue_bricks<5>(c, s_aoff); break;
+            case 6: issue_bricks<6>(c, s_aoff); break;
+            case 7: issue_bricks<7>(c, s_aoff); break;
+            case 8: issue_bricks<8>(c, s_aoff); break;
+            case 9: issue_bricks<9>(c, s_aoff); break;
+            case 10: issue_bricks<10>(c, s_aoff); break;
+            case 11: issue_bricks<11>(c, s_aoff); break;
+            case 12: issue_bricks<12>(c, s_aoff); break;
+            case 13: issue_bricks<13>(c, s_aoff); break;
+            case 14: issue_bricks<14>(c, s_aoff); break;
+            case 15: issue_bricks<15>(c, s_aoff); break;
+            default: issue_bricks<16>(c, s_aoff); break;
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: TMEM -> red.global.add
+        const int qd = warp & 3;                      // TMEM lane quarter this warp may access
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        // lane -> MMA row m.  M = 128: m = 32*qd + lane.  M = 64: rows live in lanes 0-15 of each quarter, m = 16*qd + lane.
+        const int m = p.M == 128 ? qd * 32 + lane : qd * 16 + lane;
+        const bool lane_ok = p.M == 128 || lane < 16;
+        const int j = m / p.CC, cil = m - j * p.CC;
+        for (int a = 0; a < nacc; a++) {
+            const int i = a / p.NCH, c = a - i * p.NCH;
+            const int q = q0 + i;
+            const int tw = q % p.K, thb = (q / p.K) % p.nth, tdq = q / (p.K * p.nth);
+            const int th = thb * p.R + j;
+            const bool row_ok = lane_ok && th < p.K;
+            const int ci = cib * p.CB + c * p.CC + cil;
+            for (int n0 = 0; n0 < p.Nmma; n0 += 16) {
+                uint32_t v[16];
+                tc_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * p.Nmma + n0), v);
+                if (row_ok) {
+                    const int r = n0 / p.CO, col = n0 - r * p.CO;
+                    const int td = fold ? p.K - 1 - r : tdq;
+                    float* o = p.dw + ((size_t)((td * p.K + th) * p.K + tw) * p.Cx + ci) * p.Cy + cob * p.CO + col;
+#pragma unroll
+                    for (int e = 0; e < 16; e++) atomicAdd(o + e, __uint_as_float(v[e]));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WG_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+inline int largest_div(int v, const int* cands, int n) {
+    for (int i = 0; i < n; i++)
+        if (v % cands[i] == 0) return cands[i];
+    return 0;
+}
+
+}  // namespace
+
+unsigned long long g_vg_wg_tc_launches = 0;
+
+// dw[K,K,K,Cx,Cy] += X^T * dY on tcgen05 (stride 1).  Returns VG_ERR_UNSUPPORTED when the shape does not fit.
+int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, int XH, int XW, int Cx, int OD, int OH, int OW, int Cy,
+                    int K, cudaStream_t stream) {
+    if (Cx % 16 || Cy % 16 || K < 1 || K > 4) return VG_ERR_UNSUPPORTED;
+    WgParams p{};
+    p.x = x; p.dy = dy; p.dw = dw;
+    p.Nb = Nb; p.XD = XD; p.XH = XH; p.XW = XW; p.Cx = Cx; p.OD = OD; p.OH = OH; p.OW = OW; p.Cy = Cy; p.K = K;
+    const int ccs[4] = {128, 64, 32, 16};
+    p.CC = largest_div(Cx, ccs, 4);
+    p.M = p.CC == 16 ? 64 : 128;
+    p.R = p.M / p.CC;
+    p.PLC = p.CC / 8;
+    const int cos[5] = {256, 128, 64, 32, 16};
+    p.CO = largest_div(Cy, cos, 5);
+    p.NPLy = p.CO / 8;
+    p.NF = (K > 1 && K * p.CO <= 256) ? K : 1;
+    p.Nmma = p.NF * p.CO;
+    if (p.M == 128 && p.Nmma % 16) return VG_ERR_UNSUPPORTED;
+    p.nth = (K + p.R - 1) / p.R;
+    p.NTA = (p.NF > 1 ? 1 : K) * p.nth * K;
+    int maxacc = 512 / p.Nmma;
+    if (maxacc > WG_MAXACC) maxacc = WG_MAXACC;
+    const int nch_tot = Cx / p.CC;
+    const size_t smem_cap = 220 * 1024;
+    const int cand[7][2] = {{8, 8}, {8, 4}, {4, 4}, {4, 2}, {2, 2}, {2, 1}, {1, 1}};
+    bool found = false;
+    for (int attempt = 0; attempt < 2 && !found; attempt++) {
+        // attempt 0: all channel chunks of X in one CTA (dY staged once); attempt 1: one chunk per CTA
+        if (attempt == 0) {
+            if (p.NTA * nch_tot > maxacc) continue;
+            p.NCH = nch_tot; p.TPC = p.NTA;
+        } else {
+            p.NCH = 1; p.TPC = p.NTA < maxacc ? p.NTA : maxacc;
+        }
+        p.CB = p.NCH * p.CC;
+        p.nsets = (p.NTA + p.TPC - 1) / p.TPC;
+        p.n_co_blocks = Cy / p.CO;
+        p.tiles = (Cx / p.CB) * p.n_co_blocks * p.nsets;
+        // spans of the tap sets
+        int tdspan = 0, thspan = 0;
+        for (int s = 0; s < p.nsets; s++) {
+            int tdl = 1 << 30, tdh = -1, thl = 1 << 30, thh = -1;
+            for (int q = s * p.TPC; q < p.NTA && q < (s + 1) * p.TPC; q++) {
+                int thb = (q / K) % p.nth, td = q / (K * p.nth);
+                tdl = td < tdl ? td : tdl; tdh = td > tdh ? td : tdh;
+                thl = thb < thl ? thb : thl; thh = thb > thh ? thb : thh;
+            }
+            if (tdh - tdl > tdspan) tdspan = tdh - tdl;
+            if (thh - thl > thspan) thspan = thh - thl;
+        }
+        p.XWb = WG_XW;
+        const int want = 148 / p.tiles > 0 ? 148 / p.tiles : 1;
+        int best = -1;
+        for (int ci = 0; ci < 7; ci++) {
+            const int bdo = cand[ci][0], bho = cand[ci][1];
+            if (bdo > 1 && bdo >= 2 * OD) continue;
+            if (bho > 1 && bho >= 2 * OH) continue;
+            const int xdb = p.NF > 1 ? bdo + K - 1 : bdo + tdspan;
+            const int xhb = bho + thspan * p.R + p.R - 1;
+            const int ydb = p.NF > 1 ? bdo + 2 * (K - 1) : bdo;
+            const size_t xb = (size_t)xdb * p.NCH * xhb * p.PLC * p.XWb * 16;
+            const size_t yb = (size_t)bho * ydb * p.NPLy * WG_YP * 16;
+            if (2 * (xb + yb) + 256 > smem_cap) continue;
+            const long long nbr = (long long)Nb * ((OD + bdo - 1) / bdo) * ((OH + bho - 1) / bho) * ((OW + WG_KW - 1) / WG_KW);
+            best = ci;
+            if (nbr >= 2LL * want) break;   // enough bricks to feed every split; else keep shrinking
+        }
+        if (best < 0) continue;
+        p.BDo = cand[best][0]; p.BHo = cand[best][1];
+        p.XDb = p.NF > 1 ? p.BDo + K - 1 : p.BDo + tdspan;
+        p.XHb = p.BHo + thspan * p.R + p.R - 1;
+        p.XHu = p.BHo + thspan * p.R + (p.R < K ? p.R : K) - 1;
+        p.YDb = p.NF > 1 ? p.BDo + 2 * (K - 1) : p.BDo;
+        p.ypad = p.NF > 1 ? K - 1 : 0;
+        p.nB = p.NF > 1 ? p.BDo + K - 1 : p.BDo;
+        p.x_bytes = (uint32_t)((size_t)p.XDb * p.NCH * p.XHb * p.PLC * p.XWb * 16);
+        const uint32_t yb = (uint32_t)((size_t)p.BHo * p.YDb * p.NPLy * WG_YP * 16);
+        p.stage_bytes = (p.x_bytes + yb + 127) & ~127u;
+        p.stages = (int)((smem_cap - 256) / p.stage_bytes);
+        if (p.stages > 4) p.stages = 4;
+        if (p.stages < 2) continue;
+        found = true;
+    }
+    if (!found) return VG_ERR_UNSUPPORTED;
+    p.bd_tiles = (OD + p.BDo - 1) / p.BDo; p.bh_tiles = (OH + p.BHo - 1) / p.BHo; p.bw_tiles = (OW + WG_KW - 1) / WG_KW;
+    const long long nbricks = (long long)Nb * p.bd_tiles * p.bh_tiles * p.bw_tiles;
+    if (nbricks > 0x3fffffff) return VG_ERR_UNSUPPORTED;
+    p.nbricks = (int)nbricks;
+    p.ksplit = 148 / p.tiles;
+    if (p.ksplit < 1) p.ksplit = 1;
+    if (p.ksplit > p.nbricks) p.ksplit = p.nbricks;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(p.TPC * p.NCH * p.Nmma)) cols <<= 1;
+    if (cols > 512) return VG_ERR_UNSUPPORTED;
+    p.tmem_cols = cols;
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return VG_ERR_CUDA;
+        attr_done = true;
+    }
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 256;
+    wgrad_tc_kernel<<<p.tiles * p.ksplit, WG_THREADS, smem, stream>>>(p);
+    if (getenv("VG_DEBUG")) {
+        cudaError_t e = cudaPeekAtLastError();
+        fprintf(stderr, "[wgrad_tc] Cx=%d Cy=%d K=%d M=%d CC=%d NCH=%d CO=%d NF=%d N=%d TPC=%d nsets=%d tiles=%d ksplit=%d brick=%dx%d stages=%d stage=%uB tmem=%u : %s\n",
+                Cx, Cy, K, p.M, p.CC, p.NCH, p.CO, p.NF, p.Nmma, p.TPC, p.nsets, p.tiles, p.ksplit, p.BDo, p.BHo, p.stages, p.stage_bytes,
+                p.tmem_cols, cudaGetErrorString(e));
+    }
+    VG_LAUNCHED(1);
+    g_vg_wg_tc_launches++;
+    return VG_OK;
+}
