@@ -61,40 +61,41 @@ struct WgParams {
     int stages;
 };
 
-// One gathered region: cells of 16 bytes (8 channels of one voxel).
+// One gathered region: cells of 16 bytes (8 channels of one voxel).  A region row is (slice d, channel chunk c, row h);
+// inside a row the cells are (voxel w, plane pl) with P = 2^lgp planes per chunk.
 struct Region {
-    const bf16* g;        // sample base + channel offset
+    const bf16* g;        // sample base + channel offset of the CTA's channel block
     int gd0, gh0, gw0;    // global origin of the region
     int GD, GH, GW, C;    // tensor bounds and channels per voxel
-    int nd, nh, nw, np;   // extents: slices, rows, voxels per row, planes (8-channel groups)
-    int sd, sh, sc, sp;   // shared-memory strides in cells: slice, row, chunk, plane (voxel stride = 1)
-    FastDiv by_segs, by_np, by_plc, by_nh;
-    int plc;
+    int nd, nc, nh, nw;   // extents: slices, chunks, rows, voxels per row
+    int lgp;              // log2(planes per chunk)
+    int sd, sc, sh, sp;   // shared-memory strides in cells: slice, chunk, row, plane (voxel stride = 1)
+    FastDiv by_cnh, by_nh;
 };
 
 // 16-byte cp.async per cell (zero fill outside the tensor): no register staging, so a whole stage is in flight per SM.
-// Work unit = 32 consecutive cells of one (slice, row): the row decode is warp-uniform, lanes only split (voxel, plane).
+// A warp owns whole region rows: the row decode is warp-uniform and every lane keeps a fixed (plane, voxel phase), so the
+// per-cell work is two adds, a bounds test and the copy.
 __device__ __forceinline__ void gather_region(const Region& r, uint32_t dst_base, int warp, int lane) {
-    const int cells = r.nw * r.np;
-    const int segs = (cells + 31) >> 5;
-    const int units = r.nd * r.nh * segs;
-#pragma unroll 2
-    for (int u = warp; u < units; u += WG_NPROD / 32) {
-        const uint32_t row = r.by_segs.div(u), seg = u - row * segs;
-        const uint32_t d = r.by_nh.div(row), h = row - d * r.nh;
+    const int P = 1 << r.lgp;
+    const int pl = lane & (P - 1), wl = lane >> r.lgp, wps = 32 >> r.lgp;
+    const int rows = r.nd * r.nc * r.nh;
+    const uint32_t lane_dst = (uint32_t)(pl * r.sp + wl) * 16u;
+    const int lane_src = wl * r.C + pl * 8;
+    for (int row = warp; row < rows; row += WG_NPROD / 32) {
+        const uint32_t d = r.by_cnh.div(row), rem = row - d * (r.nc * r.nh);
+        const uint32_t c = r.by_nh.div(rem), h = rem - c * r.nh;
         const int gd = r.gd0 + (int)d, gh = r.gh0 + (int)h;
         const bool rowok = (unsigned)gd < (unsigned)r.GD && (unsigned)gh < (unsigned)r.GH;
-        const bf16* srow = r.g + (((size_t)(rowok ? gd : 0) * r.GH + (rowok ? gh : 0)) * r.GW) * r.C;
-        const uint32_t drow = dst_base + (uint32_t)(d * r.sd + h * r.sh) * 16u;
-        const uint32_t e = seg * 32 + lane;
-        if (e < (uint32_t)cells) {
-            const uint32_t w = r.by_np.div(e), pp = e - w * r.np;
-            const uint32_t c = r.by_plc.div(pp), pl = pp - c * r.plc;
-            const int gw = r.gw0 + (int)w;
-            const bool ok = rowok && (unsigned)gw < (unsigned)r.GW;
-            const bf16* src = ok ? srow + (size_t)gw * r.C + pp * 8 : r.g;
-            const uint32_t dst = drow + (uint32_t)(c * r.sc + pl * r.sp + w) * 16u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        const bf16* src = r.g + (((size_t)(rowok ? gd : 0) * r.GH + (rowok ? gh : 0)) * r.GW + r.gw0) * r.C + (c << (r.lgp + 3)) + lane_src;
+        uint32_t dst = dst_base + (uint32_t)(d * r.sd + c * r.sc + h * r.sh) * 16u + lane_dst;
+        const int wstep_src = wps * r.C;
+#pragma unroll 4
+        for (int w = wl; w < r.nw; w += wps) {
+            const bool ok = rowok && (unsigned)(r.gw0 + w) < (unsigned)r.GW;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(ok ? src : r.g), "r"(ok ? 16 : 0) : "memory");
+            src += wstep_src;
+            dst += (uint32_t)wps * 16u;
         }
     }
 }
@@ -197,14 +198,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
     if (warp < WG_MMA_WARP) {
         // ------------------------------------------------------------------ gather producers
         Region rx, ry;
+        int lgx = 0, lgy = 0;
+        while ((1 << lgx) < p.PLC) lgx++;
+        while ((1 << lgy) < p.NPLy) lgy++;
         rx.GD = p.XD; rx.GH = p.XH; rx.GW = p.XW; rx.C = p.Cx;
-        rx.nd = p.XDb; rx.nh = p.XHu; rx.nw = p.XWb; rx.np = p.NCH * p.PLC;
-        rx.sd = p.NCH * p.XHb * p.PLC * p.XWb; rx.sh = p.PLC * p.XWb; rx.sc = p.XHb * p.PLC * p.XWb; rx.sp = p.XWb; rx.plc = p.PLC;
-        rx.by_segs = FastDiv((rx.nw * rx.np + 31) >> 5); rx.by_np = FastDiv(rx.np); rx.by_plc = FastDiv(rx.plc); rx.by_nh = FastDiv(rx.nh);
+        rx.nd = p.XDb; rx.nc = p.NCH; rx.nh = p.XHu; rx.nw = p.XWb; rx.lgp = lgx;
+        rx.sd = p.NCH * p.XHb * p.PLC * p.XWb; rx.sc = p.XHb * p.PLC * p.XWb; rx.sh = p.PLC * p.XWb; rx.sp = p.XWb;
+        rx.by_cnh = FastDiv(rx.nc * rx.nh); rx.by_nh = FastDiv(rx.nh);
         ry.GD = p.OD; ry.GH = p.OH; ry.GW = p.OW; ry.C = p.Cy;
-        ry.nd = p.BDo; ry.nh = p.BHo; ry.nw = WG_KW; ry.np = p.NPLy;
-        ry.sd = p.NPLy * WG_YP; ry.sh = p.YDb * p.NPLy * WG_YP; ry.sc = 0; ry.sp = WG_YP; ry.plc = p.NPLy;
-        ry.by_segs = FastDiv((ry.nw * ry.np + 31) >> 5); ry.by_np = FastDiv(ry.np); ry.by_plc = FastDiv(ry.plc); ry.by_nh = FastDiv(ry.nh);
+        ry.nd = p.BDo; ry.nc = 1; ry.nh = p.BHo; ry.nw = WG_KW; ry.lgp = lgy;
+        ry.sd = p.NPLy * WG_YP; ry.sc = 0; ry.sh = p.YDb * p.NPLy * WG_YP; ry.sp = WG_YP;
+        ry.by_cnh = FastDiv(ry.nh); ry.by_nh = FastDiv(ry.nh);
         int stage = 0, prev_stage = -1;
         uint32_t phase = 0;
         for (int brick = split; brick < p.nbricks; brick += p.ksplit) {
@@ -222,13 +226,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
             gather_region(rx, xs, warp, lane);
             gather_region(ry, xs + p.x_bytes + (uint32_t)p.ypad * p.NPLy * WG_YP * 16u, warp, lane);
             asm volatile("cp.async.commit_group;\n" ::: "memory");
-            if (prev_stage >= 0) {
-                // the previous brick's copies have landed: publish them to the async proxy and hand the stage to the MMA warp
-                asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+            if (p.stages >= 3) {
+                // lagged publish: hand over the previous brick while this one is in flight
+                if (prev_stage >= 0) {
+                    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+                    fence_async_smem();   // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+                    mbar_arrive(full0 + 8 * prev_stage);
+                }
+                prev_stage = stage;
+            } else {
+                // two stages: a lagged publish would wait for the MMA warp to drain the other stage first -> publish at once
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
                 fence_async_smem();
-                mbar_arrive(full0 + 8 * prev_stage);
+                mbar_arrive(full0 + 8 * stage);
             }
-            prev_stage = stage;
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         if (prev_stage >= 0) {
