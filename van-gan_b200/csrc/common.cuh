@@ -150,4 +150,4 @@ int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, 
                int tw, cudaStream_t st);
 // tensor-core (tcgen05) weight-gradient path, wgrad_tc.cu
 int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, int XH, int XW, int Cx, int OD, int OH, int OW, int Cy,
-                    int K, cudaStream_t stream);
+                    int K, int stride, cudaStream_t stream);

@@ -897,8 +897,8 @@ int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, floa
         VG_CHECK_LAUNCH();
         return VG_OK;
     }
-    if (tc_wgrad_enabled() && d->stride == 1) {
-        int rc = vg_wg_tc_launch((const bf16*)x, (const bf16*)dy, dw, d->N, d->ID, d->IH, d->IW, d->Cin, OD, OH, OW, d->Cout, d->K, st);
+    if (tc_wgrad_enabled()) {
+        int rc = vg_wg_tc_launch((const bf16*)x, (const bf16*)dy, dw, d->N, d->ID, d->IH, d->IW, d->Cin, OD, OH, OW, d->Cout, d->K, d->stride, st);
         if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
         if (rc != VG_ERR_UNSUPPORTED) return rc;
     }

@@ -50,13 +50,14 @@ struct WgParams {
     const bf16* x;
     const bf16* dy;
     float* dw;
-    int Nb, XD, XH, XW, Cx, OD, OH, OW, Cy, K;
+    int Nb, XD, XH, XW, Cx, OD, OH, OW, Cy, K, st;   // st: convolution stride (1 or 2)
     int M, CC, R, PLC, NCH, CB;     // MMA M; channels per chunk; rows folded; planes per chunk; chunks per CTA; CB = NCH*CC
     int CO, NF, Nmma, NPLy;         // co block; slices folded (1 or K); MMA N = NF*CO; dY planes = CO/8
     int nth, NTA, TPC, nsets;       // th bases; tap-accumulators in total / per CTA; tap sets
     int n_co_blocks, tiles, ksplit;
     int BDo, BHo, bd_tiles, bh_tiles, bw_tiles, nbricks;
     int XDb, XHb, XHu, XWb, YDb, nB, ypad;   // XHu: rows that carry useful taps (<= XHb)
+    int x_sd, x_sc, x_spar, x_sh, x_nw;      // X stage strides (cells): slice, chunk, w-parity plane set (stride 2), row; voxels per row
     uint32_t x_bytes, stage_bytes, tmem_cols;
     int stages;
 };
@@ -69,6 +70,7 @@ struct Region {
     int GD, GH, GW, C;    // tensor bounds and channels per voxel
     int nd, nc, nh, nw;   // extents: slices, chunks, rows, voxels per row
     int lgp;              // log2(planes per chunk)
+    int s2, spar;         // stride-2 source: voxel w goes to parity plane set (w & 1) at index w >> 1
     int sd, sc, sh, sp;   // shared-memory strides in cells: slice, chunk, row, plane (voxel stride = 1)
     FastDiv by_cnh, by_nh;
 };
@@ -80,7 +82,8 @@ __device__ __forceinline__ void gather_region(const Region& r, uint32_t dst_base
     const int P = 1 << r.lgp;
     const int pl = lane & (P - 1), wl = lane >> r.lgp, wps = 32 >> r.lgp;
     const int rows = r.nd * r.nc * r.nh;
-    const uint32_t lane_dst = (uint32_t)(pl * r.sp + wl) * 16u;
+    const uint32_t lane_dst = (uint32_t)(pl * r.sp + (r.s2 ? (wl & 1) * r.spar + (wl >> 1) : wl)) * 16u;
+    const uint32_t dst_step = (uint32_t)(r.s2 ? wps >> 1 : wps) * 16u;
     const int lane_src = wl * r.C + pl * 8;
     for (int row = warp; row < rows; row += WG_NPROD / 32) {
         const uint32_t d = r.by_cnh.div(row), rem = row - d * (r.nc * r.nh);
@@ -95,7 +98,7 @@ __device__ __forceinline__ void gather_region(const Region& r, uint32_t dst_base
             const bool ok = rowok && (unsigned)(r.gw0 + w) < (unsigned)r.GW;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(ok ? src : r.g), "r"(ok ? 16 : 0) : "memory");
             src += wstep_src;
-            dst += (uint32_t)wps * 16u;
+            dst += dst_step;
         }
     }
 }
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
         td_min = min(td_min, td); thb_min = min(thb_min, thb); tw_min = min(tw_min, tw);
     }
     if (fold) td_min = 0;
+    const int tw_org = p.st == 2 ? (tw_min & ~1) : tw_min;   // stride 2: keep the parity of the taps
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; s++) {
@@ -182,7 +186,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
             const int q = q0 + i;
             const int tw = q % p.K, thb = (q / p.K) % p.nth, td = fold ? 0 : q / (p.K * p.nth);
             for (int c = 0; c < p.NCH; c++)
-                s_aoff[i * p.NCH + c] = ((((td - td_min) * p.NCH + c) * p.XHb + (thb - thb_min) * p.R) * p.PLC) * p.XWb + (tw - tw_min);
+                s_aoff[i * p.NCH + c] = (td - td_min) * p.x_sd + c * p.x_sc + (thb - thb_min) * p.R * p.x_sh +
+                                        (p.st == 2 ? ((tw - tw_org) & 1) * p.x_spar + ((tw - tw_org) >> 1) : tw - tw_org);
         }
     }
     // zero the stages once: the dY pad slices (td-fold) are never written again
@@ -202,11 +207,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
         while ((1 << lgx) < p.PLC) lgx++;
         while ((1 << lgy) < p.NPLy) lgy++;
         rx.GD = p.XD; rx.GH = p.XH; rx.GW = p.XW; rx.C = p.Cx;
-        rx.nd = p.XDb; rx.nc = p.NCH; rx.nh = p.XHu; rx.nw = p.XWb; rx.lgp = lgx;
-        rx.sd = p.NCH * p.XHb * p.PLC * p.XWb; rx.sc = p.XHb * p.PLC * p.XWb; rx.sh = p.PLC * p.XWb; rx.sp = p.XWb;
+        rx.nd = p.XDb; rx.nc = p.NCH; rx.nh = p.XHu; rx.nw = p.x_nw; rx.lgp = lgx;
+        rx.sd = p.x_sd; rx.sc = p.x_sc; rx.sh = p.x_sh; rx.sp = p.XWb; rx.s2 = p.st == 2; rx.spar = p.x_spar;
         rx.by_cnh = FastDiv(rx.nc * rx.nh); rx.by_nh = FastDiv(rx.nh);
         ry.GD = p.OD; ry.GH = p.OH; ry.GW = p.OW; ry.C = p.Cy;
         ry.nd = p.BDo; ry.nc = 1; ry.nh = p.BHo; ry.nw = WG_KW; ry.lgp = lgy;
+        ry.s2 = 0; ry.spar = 0;
         ry.sd = p.NPLy * WG_YP; ry.sc = 0; ry.sh = p.YDb * p.NPLy * WG_YP; ry.sp = WG_YP;
         ry.by_cnh = FastDiv(ry.nh); ry.by_nh = FastDiv(ry.nh);
         int stage = 0, prev_stage = -1;
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
             const int bd = b % p.bd_tiles;
             const int n = b / p.bd_tiles;
             rx.g = p.x + (size_t)n * p.XD * p.XH * p.XW * p.Cx + (size_t)cib * p.CB;
-            rx.gd0 = bd * p.BDo + td_min; rx.gh0 = bh * p.BHo + thb_min * p.R; rx.gw0 = bw * WG_KW + tw_min;
+            rx.gd0 = bd * p.BDo * p.st + td_min; rx.gh0 = bh * p.BHo * p.st + thb_min * p.R; rx.gw0 = bw * WG_KW * p.st + tw_org;
             ry.g = p.dy + (size_t)n * p.OD * p.OH * p.OW * p.Cy + (size_t)cob * p.CO;
             ry.gd0 = bd * p.BDo; ry.gh0 = bh * p.BHo; ry.gw0 = bw * WG_KW;
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
         c.leader = elect_one();
         c.a_desc0 = ((uint64_t)((uint32_t)p.XWb | (1u << 14)) << 32) | (8u << 16);   // SBO = X plane pitch | version ; LBO = 128 B
         c.b_desc0 = ((uint64_t)((uint32_t)WG_YP | (1u << 14)) << 32) | (8u << 16);   // SBO = dY plane pitch
-        c.a_sd = p.NCH * p.XHb * p.PLC * p.XWb; c.a_sh = p.PLC * p.XWb;
+        c.a_sd = p.st * p.x_sd; c.a_sh = p.st * p.x_sh;
         c.b_sd = p.NPLy * WG_YP; c.b_sh = p.YDb * p.NPLy * WG_YP;
         c.nB = p.nB; c.BHo = p.BHo; c.Nmma = p.Nmma; c.tmem_base = tmem_base;
         c.sbase16 = sbase >> 4; c.stage16 = p.stage_bytes >> 4; c.x16 = p.x_bytes >> 4; c.stages = p.stages;
@@ -330,11 +336,12 @@ unsigned long long g_vg_wg_tc_launches = 0;
 
 // dw[K,K,K,Cx,Cy] += X^T * dY on tcgen05 (stride 1).  Returns VG_ERR_UNSUPPORTED when the shape does not fit.
 int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, int XH, int XW, int Cx, int OD, int OH, int OW, int Cy,
-                    int K, cudaStream_t stream) {
-    if (Cx % 16 || Cy % 16 || K < 1 || K > 4) return VG_ERR_UNSUPPORTED;
+                    int K, int stride, cudaStream_t stream) {
+    if (Cx % 16 || Cy % 16 || K < 1 || K > 4 || stride < 1 || stride > 2) return VG_ERR_UNSUPPORTED;
+    if (stride == 2 && K < 2) return VG_ERR_UNSUPPORTED;   // k1 s2 would stage 8x the voxels it uses
     WgParams p{};
     p.x = x; p.dy = dy; p.dw = dw;
-    p.Nb = Nb; p.XD = XD; p.XH = XH; p.XW = XW; p.Cx = Cx; p.OD = OD; p.OH = OH; p.OW = OW; p.Cy = Cy; p.K = K;
+    p.Nb = Nb; p.XD = XD; p.XH = XH; p.XW = XW; p.Cx = Cx; p.OD = OD; p.OH = OH; p.OW = OW; p.Cy = Cy; p.K = K; p.st = stride;
     const int ccs[4] = {128, 64, 32, 16};
     p.CC = largest_div(Cx, ccs, 4);
     p.M = p.CC == 16 ? 64 : 128;
@@ -343,7 +350,7 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
     const int cos[5] = {256, 128, 64, 32, 16};
     p.CO = largest_div(Cy, cos, 5);
     p.NPLy = p.CO / 8;
-    p.NF = (K > 1 && K * p.CO <= 256) ? K : 1;
+    p.NF = (stride == 1 && K > 1 && K * p.CO <= 256) ? K : 1;
     p.Nmma = p.NF * p.CO;
     if (p.M == 128 && p.Nmma % 16) return VG_ERR_UNSUPPORTED;
     p.nth = (K + p.R - 1) / p.R;
@@ -385,10 +392,10 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
             const int bdo = cand[ci][0], bho = cand[ci][1];
             if (bdo > 1 && bdo >= 2 * OD) continue;
             if (bho > 1 && bho >= 2 * OH) continue;
-            const int xdb = p.NF > 1 ? bdo + K - 1 : bdo + tdspan;
-            const int xhb = bho + thspan * p.R + p.R - 1;
+            const int xdb = p.NF > 1 ? bdo + K - 1 : (bdo - 1) * stride + tdspan + 1;
+            const int xhb = (bho - 1) * stride + thspan * p.R + p.R;
             const int ydb = p.NF > 1 ? bdo + 2 * (K - 1) : bdo;
-            const size_t xb = (size_t)xdb * p.NCH * xhb * p.PLC * p.XWb * 16;
+            const size_t xb = (size_t)xdb * p.NCH * stride * xhb * p.PLC * p.XWb * 16;
             const size_t yb = (size_t)bho * ydb * p.NPLy * WG_YP * 16;
             if (2 * (xb + yb) + 256 > smem_cap) continue;
             const long long nbr = (long long)Nb * ((OD + bdo - 1) / bdo) * ((OH + bho - 1) / bho) * ((OW + WG_KW - 1) / WG_KW);
@@ -397,13 +404,15 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
         }
         if (best < 0) continue;
         p.BDo = cand[best][0]; p.BHo = cand[best][1];
-        p.XDb = p.NF > 1 ? p.BDo + K - 1 : p.BDo + tdspan;
-        p.XHb = p.BHo + thspan * p.R + p.R - 1;
-        p.XHu = p.BHo + thspan * p.R + (p.R < K ? p.R : K) - 1;
+        p.XDb = p.NF > 1 ? p.BDo + K - 1 : (p.BDo - 1) * stride + tdspan + 1;
+        p.XHb = (p.BHo - 1) * stride + thspan * p.R + p.R;
+        p.XHu = (p.BHo - 1) * stride + thspan * p.R + (p.R < K ? p.R : K);
+        p.x_sh = p.PLC * p.XWb; p.x_spar = p.XHb * p.x_sh; p.x_sc = stride * p.x_spar; p.x_sd = p.NCH * p.x_sc;
+        p.x_nw = stride == 2 ? 2 * (WG_KW + 1) : p.XWb;
         p.YDb = p.NF > 1 ? p.BDo + 2 * (K - 1) : p.BDo;
         p.ypad = p.NF > 1 ? K - 1 : 0;
         p.nB = p.NF > 1 ? p.BDo + K - 1 : p.BDo;
-        p.x_bytes = (uint32_t)((size_t)p.XDb * p.NCH * p.XHb * p.PLC * p.XWb * 16);
+        p.x_bytes = (uint32_t)((size_t)p.XDb * p.x_sd * 16);
         const uint32_t yb = (uint32_t)((size_t)p.BHo * p.YDb * p.NPLy * WG_YP * 16);
         p.stage_bytes = (p.x_bytes + yb + 127) & ~127u;
         p.stages = (int)((smem_cap - 256) / p.stage_bytes);
