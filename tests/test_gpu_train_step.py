@@ -233,4 +233,6 @@ def test_test_step_and_determinism(cuda):
         assert abs(res_t[k] - float(res_o[k])) <= 2e-2 * abs(float(res_o[k])) + 1e-4, k
     _, r1 = _cuda_step(S, b, 1, init, real_I, real_S, rand)
     _, r2 = _cuda_step(S, b, 1, init, real_I, real_S, rand)
-    assert r1 == r2
+    # the loss sums are accumulated with fp64 atomics: identical up to the summation order
+    for k in r1:
+        assert abs(r1[k] - r2[k]) <= 1e-12 * abs(r1[k]), k
