@@ -51,6 +51,8 @@ typedef struct {
     int x_dtype;    /* VG_BF16, or VG_F32 when Cin == 1 */
     int y_dtype;    /* VG_BF16, or VG_F32 when Cout == 1 */
     int act;        /* VG_ACT_NONE or VG_ACT_TANH (forward epilogue) */
+    int dx_lo, dx_hi; /* dgrad only: dx is needed for spatial indices [dx_lo, I - dx_hi) of every dimension; the rest
+                         (zero 'same' padding, whose gradient nobody reads) may be left unwritten.  0,0 = everything */
 } vg_conv3d_desc;
 
 /* bytes of the bf16 operand copies of one layer's weights: forward pack and dgrad pack */

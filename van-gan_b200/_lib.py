@@ -24,7 +24,8 @@ class VgError(RuntimeError):
 
 class ConvDesc(C.Structure):
     _fields_ = [("N", C.c_int), ("ID", C.c_int), ("IH", C.c_int), ("IW", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
-                ("K", C.c_int), ("stride", C.c_int), ("x_dtype", C.c_int), ("y_dtype", C.c_int), ("act", C.c_int)]
+                ("K", C.c_int), ("stride", C.c_int), ("x_dtype", C.c_int), ("y_dtype", C.c_int), ("act", C.c_int),
+                ("dx_lo", C.c_int), ("dx_hi", C.c_int)]
 
 
 class InDesc(C.Structure):
@@ -84,9 +85,19 @@ class Profiler:
     """Optional per-family device timing (CUDA events on the launching stream) used by bench.py to
     report the dominant kernel's achieved FLOP/s / bytes/s.  `track`: set of ABI names."""
 
-    def __init__(self, track):
+    def __init__(self, track, detail=False):
         self.track = set(track)
         self.records = {}
+        self.detail = detail   # key records by (name, descriptor shape) instead of name only
+
+    def key(self, name, args):
+        if self.detail and args:
+            a = args[0]
+            if isinstance(a, ConvDesc):
+                return "%s %d->%d k%ds%d in%d N%d" % (name, a.Cin, a.Cout, a.K, a.stride, a.ID, a.N)
+            if isinstance(a, InDesc):
+                return "%s C%d S%d N%d" % (name, a.C, a.D, a.N)
+        return name
 
     def summary(self):
         torch.cuda.synchronize()
@@ -135,12 +146,12 @@ def call(name, *args, work=0.0):
     global LAUNCHES
     conv = [(_ptr(a) if (a is None or torch.is_tensor(a)) else a) for a in args]
     prof = PROFILER
-    if prof is not None and name in prof.track:
+    if prof is not None and (name in prof.track or prof.detail):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(lib(), name)(*conv, _stream())
         e1.record()
-        prof.records.setdefault(name, []).append((e0, e1, work))
+        prof.records.setdefault(prof.key(name, args), []).append((e0, e1, work))
     else:
         rc = getattr(lib(), name)(*conv, _stream())
     LAUNCHES += 1

@@ -472,83 +472,166 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, bf16* __restrict_
 inline int class_taps(int K, int stride, int a) { return K <= a ? 0 : (K - a + stride - 1) / stride; }
 
 // ------------------------------------------------------------------------------------------ direct kernels (Cin==1 / Cout==1)
-// forward, Cin == 1: x fp32 [N,ID,IH,IW], w fp32 [T][Cout], y bf16 [N,OD,OH,OW,Cout]
-__global__ void __launch_bounds__(256) cin1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// forward, Cin == 1: x fp32 [N,ID,IH,IW], w fp32 [T][Cout], y bf16 [N,OD,OH,OW,Cout].
+// Register tile: a thread owns VW output voxels and 16 output channels (64 accumulators); every weight vector (16 floats,
+// broadcast from shared memory) feeds 16*VW FMAs.  The VW voxels of a thread are 32 apart in the flattened (oh, ow) plane, so
+// the 32 lanes of a warp always touch consecutive voxels: input loads are coalesced and each output voxel row (16 channels =
+// one 32-byte sector) leaves as a single 256-bit store, 1 KB contiguous per warp instruction when Cout == 16.
+template <int K, int S>
+__global__ void __launch_bounds__(128) cin1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, bf16* __restrict__ y, int N, int ID,
-                                                       int IH, int IW, int OD, int OH, int OW, int Cout, int K, int stride) {
+                                                       int IH, int IW, int OD, int OH, int OW, int Cout) {
+    constexpr int VW = 4, T = K * K * K;
     extern __shared__ float sw[];  // [T][Cout] + bias[Cout]
-    const int T = K * K * K;
-    for (int i = threadIdx.x; i < T * Cout; i += 256) sw[i] = w[i];
-    for (int i = threadIdx.x; i < Cout; i += 256) sw[T * Cout + i] = bias ? bias[i] : 0.f;
+    for (int i = threadIdx.x; i < T * Cout; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[T * Cout + i] = bias ? bias[i] : 0.f;
     __syncthreads();
-    const int cg = Cout / 8;
-    size_t total = (size_t)N * OD * OH * OW * cg;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-        int c8 = (int)(i % cg);
-        size_t v = i / cg;
-        int ow = (int)(v % OW), oh = (int)((v / OW) % OH), od = (int)((v / ((size_t)OW * OH)) % OD);
-        int n = (int)(v / ((size_t)OW * OH * OD));
-        float a[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int ncg = Cout / 16, plane = OH * OW, nfb = (plane + 32 * VW - 1) / (32 * VW);
+    const long long total = (long long)N * OD * nfb * ncg;
+    for (long long i = (long long)blockIdx.x * nwarp + wid; i < total; i += (long long)gridDim.x * nwarp) {
+        const int cg = (int)(i % ncg);
+        long long r = i / ncg;
+        const int fb = (int)(r % nfb); r /= nfb;
+        const int od = (int)(r % OD);
+        const int n = (int)(r / OD);
+        int xoff[VW];
+        bool ok[VW];
 #pragma unroll
-        for (int k = 0; k < 8; k++) a[k] = sw[T * Cout + c8 * 8 + k];
-        const float* xb = x + (((size_t)n * ID + od * stride) * IH + oh * stride) * IW + ow * stride;
-        int t = 0;
+        for (int v = 0; v < VW; v++) {
+            const int f = fb * 32 * VW + v * 32 + lane;
+            ok[v] = f < plane;
+            const int fc = ok[v] ? f : 0;
+            const int oh = fc / OW, ow = fc - oh * OW;
+            xoff[v] = oh * S * IW + ow * S;
+        }
+        float acc[VW][16];
+#pragma unroll
+        for (int v = 0; v < VW; v++)
+#pragma unroll
+            for (int k = 0; k < 16; k++) acc[v][k] = sw[T * Cout + cg * 16 + k];
+        const float* xb = x + ((size_t)n * ID + od * S) * IH * IW;
+#pragma unroll 1
         for (int kd = 0; kd < K; kd++)
-            for (int kh = 0; kh < K; kh++)
-                for (int kw = 0; kw < K; kw++, t++) {
-                    float xv = __ldg(xb + ((size_t)kd * IH + kh) * IW + kw);
-                    const float* wr = sw + t * Cout + c8 * 8;
+#pragma unroll 1
+            for (int kh = 0; kh < K; kh++) {
+                const float* xr = xb + ((size_t)kd * IH + kh) * IW;
+                float xv[VW][K];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) a[k] = fmaf(xv, wr[k], a[k]);
+                for (int v = 0; v < VW; v++)
+#pragma unroll
+                    for (int kw = 0; kw < K; kw++) xv[v][kw] = __ldg(xr + xoff[v] + kw);
+                const float* wr = sw + ((kd * K + kh) * K) * Cout + cg * 16;
+#pragma unroll
+                for (int kw = 0; kw < K; kw++) {
+                    float wv[16];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(wr + kw * Cout + q * 4);
+                        wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
+                    }
+#pragma unroll
+                    for (int v = 0; v < VW; v++)
+#pragma unroll
+                        for (int k = 0; k < 16; k++) acc[v][k] = fmaf(xv[v][kw], wv[k], acc[v][k]);
                 }
-        store8<bf16>(y + i * 8, a);
+            }
+        bf16* yo = y + (((size_t)n * OD + od) * plane + (size_t)fb * 32 * VW + lane) * Cout + cg * 16;
+#pragma unroll
+        for (int v = 0; v < VW; v++)
+            if (ok[v]) {
+                uint32_t o[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[v][2 * j], acc[v][2 * j + 1]);
+                    o[j] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(yo + (size_t)v * 32 * Cout), "r"(o[0]),
+                             "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+            }
     }
 }
 
-// wgrad, Cin == 1: dw[t][co] += sum_o x[o*s+t] * dy[o][co]
-// A task is (tap, 8 output channels); thread = (task, voxel lane).  Per voxel a thread issues one scalar
-// load of x, one 128-bit load of dy and 8 FMAs; lanes are reduced through shared memory and each block
-// finishes with one atomicAdd per output.
-__global__ void __launch_bounds__(256) cin1_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
-                                                         float* __restrict__ dw, int N, int ID, int IH, int IW, int OD, int OH,
-                                                         int OW, int Cout, int K, int stride, int per_block) {
-    extern __shared__ float sred[];   // [lanes][ntasks_pass * 8]
-    const int T = K * K * K, cg = Cout / 8, ntasks = T * cg;
-    const size_t V = (size_t)N * OD * OH * OW;
-    const size_t v0 = (size_t)blockIdx.x * per_block, v1 = v0 + per_block < V ? v0 + per_block : V;
-    for (int task0 = 0; task0 < ntasks; task0 += 256) {
-        const int tp = ntasks - task0 < 256 ? ntasks - task0 : 256;   // tasks in this pass
-        const int lanes = 256 / tp;
-        const int task = task0 + (int)threadIdx.x % tp, lane = (int)threadIdx.x / tp;
-        float acc[8];
+// wgrad, Cin == 1: dw[t][co] += sum_o x[o*s+t] * dy[o][co];  dbias[co] += sum_o dy[o][co] (optional, fused).
+// A task is (kd, kh, 16 output channels) and belongs to one WARP; the 32 lanes are 32 consecutive voxels of the flattened
+// (oh, ow) plane, so the dy load (one 32-byte sector per lane, a 256-bit load) and the K input loads are coalesced, and the
+// warps of a block -- which walk the same voxels with different tasks -- share dy through L1.  K*16 accumulators per lane,
+// reduced over the lanes by shuffles once at the end, then one atomicAdd per (warp, output).
+template <int K, int S>
+__global__ void __launch_bounds__(K >= 4 ? 512 : 288, K >= 4 ? 1 : 2)
+    cin1_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw, float* __restrict__ dbias,
+                      int N, int ID, int IH, int IW, int OD, int OH, int OW, int Cout) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int ncg = Cout / 16;
+    const int task = blockIdx.y * wpb + wid;          // host guarantees gridDim.y * wpb == K*K*ncg
+    const int cg = task % ncg, kh = (task / ncg) % K, kd = task / (ncg * K);
+    const int rows = N * OD * OH;
+    float acc[K][16], bsum[16];
 #pragma unroll
-        for (int k = 0; k < 8; k++) acc[k] = 0.f;
-        if (lane < lanes) {
-            const int t = task / cg, c8 = task % cg;
-            const int kw = t % K, kh = (t / K) % K, kd = t / (K * K);
-            size_t v = v0 + lane;
-            int ow = (int)(v % OW), oh = (int)((v / OW) % OH), od = (int)((v / ((size_t)OW * OH)) % OD);
-            int n = (int)(v / ((size_t)OW * OH * OD));
-            for (; v < v1; v += lanes) {
-                const float xv = __ldg(x + (((size_t)n * ID + od * stride + kd) * IH + oh * stride + kh) * IW + ow * stride + kw);
-                float f[8];
-                load8<bf16>(dy + v * Cout + c8 * 8, f);
+    for (int k = 0; k < 16; k++) {
+        bsum[k] = 0.f;
 #pragma unroll
-                for (int k = 0; k < 8; k++) acc[k] = fmaf(xv, f[k], acc[k]);
-                ow += lanes;
-                while (ow >= OW) { ow -= OW; if (++oh == OH) { oh = 0; if (++od == OD) { od = 0; n++; } } }
+        for (int q = 0; q < K; q++) acc[q][k] = 0.f;
+    }
+    const bool do_bias = dbias != nullptr && kd == 0 && kh == 0;
+    constexpr int U = K >= 3 ? 2 : 4;   // 32-voxel chunks of one output row in flight (all loads issued before any FMA)
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int oh = row % OH, r = row / OH;
+        const int od = r % OD, n = r / OD;
+        const float* xr = x + (((size_t)n * ID + od * S + kd) * IH + oh * S + kh) * IW + lane * S;
+        const bf16* dp = dy + ((size_t)row * OW + lane) * Cout + cg * 16;
+        for (int w0 = 0; w0 < OW; w0 += 32 * U) {
+            float xw[U][K];
+            uint32_t raw[U][8];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int ow = w0 + u * 32;
+                if (ow + lane < OW) {
+#pragma unroll
+                    for (int q = 0; q < K; q++) xw[u][q] = __ldg(xr + ow * S + q);
+                    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                                 : "=r"(raw[u][0]), "=r"(raw[u][1]), "=r"(raw[u][2]), "=r"(raw[u][3]), "=r"(raw[u][4]), "=r"(raw[u][5]),
+                                   "=r"(raw[u][6]), "=r"(raw[u][7])
+                                 : "l"(dp + (size_t)ow * Cout));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < K; q++) xw[u][q] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) raw[u][j] = 0u;
+                }
             }
 #pragma unroll
-            for (int k = 0; k < 8; k++) sred[((size_t)lane * tp + (threadIdx.x % tp)) * 8 + k] = acc[k];
+            for (int u = 0; u < U; u++) {
+                float g[16];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    g[2 * j] = __uint_as_float(raw[u][j] << 16);
+                    g[2 * j + 1] = __uint_as_float(raw[u][j] & 0xffff0000u);
+                }
+#pragma unroll
+                for (int q = 0; q < K; q++)
+#pragma unroll
+                    for (int k = 0; k < 16; k++) acc[q][k] = fmaf(xw[u][q], g[k], acc[q][k]);
+                if (do_bias) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) bsum[k] += g[k];
+                }
+            }
         }
-        __syncthreads();
-        for (int o = threadIdx.x; o < tp * 8; o += 256) {
-            float sum = 0.f;
-            for (int l = 0; l < lanes; l++) sum += sred[(size_t)l * tp * 8 + o];
-            int tk = task0 + o / 8;
-            atomicAdd(dw + (size_t)(tk / cg) * Cout + (tk % cg) * 8 + (o % 8), sum);
+    }
+#pragma unroll
+    for (int q = 0; q < K; q++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const float v = warp_sum(acc[q][k]);
+            if (lane == 0) atomicAdd(dw + (size_t)((kd * K + kh) * K + q) * Cout + cg * 16 + k, v);
         }
-        __syncthreads();
+    if (do_bias) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const float v = warp_sum(bsum[k]);
+            if (lane == 0) atomicAdd(dbias + cg * 16 + k, v);
+        }
     }
 }
 
@@ -671,6 +754,7 @@ inline bool desc_ok(const vg_conv3d_desc* d) {
     if (d->Cin == 1 ? d->x_dtype != VG_F32 : (d->x_dtype != VG_BF16 || d->Cin % 16)) return false;
     if (d->Cout == 1 ? d->y_dtype != VG_F32 : (d->y_dtype != VG_BF16 || d->Cout % 16)) return false;
     if (d->Cin == 1 && d->Cout == 1) return false;
+    if (d->dx_lo < 0 || d->dx_hi < 0 || d->dx_lo + d->dx_hi >= d->ID) return false;
     return true;
 }
 inline int odim(int I, int K, int s) { return (I - K) / s + 1; }
@@ -720,7 +804,7 @@ inline size_t rup256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" {
 
-int vg_abi_version(void) { return 1; }
+int vg_abi_version(void) { return 2; }
 
 size_t vg_conv3d_packed_bytes(const vg_conv3d_desc* d, int for_dgrad) {
     if (!desc_ok(d)) return 0;
@@ -778,12 +862,22 @@ int vg_conv3d_fwd(const vg_conv3d_desc* d, const void* x, const void* w_fwd, con
     cudaStream_t st = (cudaStream_t)stream;
     const int OD = odim(d->ID, d->K, d->stride), OH = odim(d->IH, d->K, d->stride), OW = odim(d->IW, d->K, d->stride);
     if (d->Cin == 1) {
-        VG_REQUIRE(d->Cout % 8 == 0 && d->act == VG_ACT_NONE);
+        VG_REQUIRE(d->Cout % 16 == 0 && d->act == VG_ACT_NONE);
         int T = d->K * d->K * d->K;
         size_t smem = ((size_t)T * d->Cout + d->Cout) * sizeof(float);
-        size_t total = (size_t)d->N * OD * OH * OW * (d->Cout / 8);
-        cin1_fwd_kernel<<<vg_grid_for(total, 256, 16), 256, smem, st>>>((const float*)x, (const float*)w_fwd, bias, (bf16*)y, d->N,
-                                                                       d->ID, d->IH, d->IW, OD, OH, OW, d->Cout, d->K, d->stride); VG_LAUNCHED(1);
+        size_t total = (size_t)d->N * OD * ((OH * OW + 127) / 128) * (d->Cout / 16);   // warp items
+        int grid = vg_grid_for(total, 4, 8);
+#define VG_CIN1_FWD(KK, SS)                                                                                                       \
+    cin1_fwd_kernel<KK, SS><<<grid, 128, smem, st>>>((const float*)x, (const float*)w_fwd, bias, (bf16*)y, d->N, d->ID, d->IH, d->IW, \
+                                                     OD, OH, OW, d->Cout)
+        if (d->K == 1 && d->stride == 1) VG_CIN1_FWD(1, 1);
+        else if (d->K == 3 && d->stride == 1) VG_CIN1_FWD(3, 1);
+        else if (d->K == 4 && d->stride == 2) VG_CIN1_FWD(4, 2);
+        else if (d->K == 3 && d->stride == 2) VG_CIN1_FWD(3, 2);
+        else if (d->K == 4 && d->stride == 1) VG_CIN1_FWD(4, 1);
+        else return VG_ERR_UNSUPPORTED;
+#undef VG_CIN1_FWD
+        VG_LAUNCHED(1);
         VG_CHECK_LAUNCH();
         return VG_OK;
     }
@@ -839,9 +933,11 @@ int vg_conv3d_dgrad(const vg_conv3d_desc* d, const void* dy, const void* w_dgrad
                 if (use_tc) {
                     const bf16* wt = (const bf16*)wtc;
                     wtc += rup256(tc_dgrad_class_elems(d, ad, ah, aw) * 2);
+                    // stride 1: only the cropped region [dx_lo, I - dx_hi) is computed (zero-padded inputs)
+                    const int crop = s == 1 ? d->dx_lo + d->dx_hi : 0, goff = s == 1 ? d->dx_lo : 0;
                     int rc = vg_tc_launch((const bf16*)dy, d->N, OD, OH, OW, d->Cout, wt, dx, nullptr, d->ID, d->IH, d->IW, d->Cin,
-                                          (d->ID - ad + s - 1) / s, (d->IH - ah + s - 1) / s, (d->IW - aw + s - 1) / s, td, th, tw, -1, s,
-                                          ad, ah, aw, VG_ACT_NONE, st);
+                                          (d->ID - crop - ad + s - 1) / s, (d->IH - crop - ah + s - 1) / s, (d->IW - crop - aw + s - 1) / s, td,
+                                          th, tw, -1, s, ad, ah, aw, VG_ACT_NONE, st, goff);
                     if (rc == VG_OK) { woff += cnt; continue; }
                     if (rc != VG_ERR_UNSUPPORTED) return rc;
                 }
@@ -867,6 +963,32 @@ int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, floa
     cudaStream_t st = (cudaStream_t)stream;
     const int OD = odim(d->ID, d->K, d->stride), OH = odim(d->IH, d->K, d->stride), OW = odim(d->IW, d->K, d->stride);
     const size_t rows = (size_t)d->N * OD * OH * OW;
+    if (d->Cin == 1) {
+        VG_REQUIRE(d->Cout % 16 == 0);
+        const int ntask = d->K * d->K * (d->Cout / 16);
+        int wpb = ntask;                       // warps per block: all tasks when they fit, else the largest divisor <= 16
+        while (wpb > 16) wpb = (wpb % 2 == 0) ? wpb / 2 : 1;
+        VG_REQUIRE(wpb >= 1 && ntask % wpb == 0);
+        const int ntg = ntask / wpb;
+        const int items = d->N * OD * OH;
+        int gx = (148 * 16 / wpb + ntg - 1) / ntg;   // ~16 resident warps per SM
+        if (gx > items) gx = items;
+        if (gx < 1) gx = 1;
+        const dim3 grid(gx, ntg);
+#define VG_CIN1_WG(KK, SS)                                                                                                     \
+    cin1_wgrad_kernel<KK, SS><<<grid, wpb * 32, 0, st>>>((const float*)x, (const bf16*)dy, dw, dbias, d->N, d->ID, d->IH, d->IW, OD, \
+                                                         OH, OW, d->Cout)
+        if (d->K == 1 && d->stride == 1) VG_CIN1_WG(1, 1);
+        else if (d->K == 3 && d->stride == 1) VG_CIN1_WG(3, 1);
+        else if (d->K == 4 && d->stride == 2) VG_CIN1_WG(4, 2);
+        else if (d->K == 3 && d->stride == 2) VG_CIN1_WG(3, 2);
+        else if (d->K == 4 && d->stride == 1) VG_CIN1_WG(4, 1);
+        else return VG_ERR_UNSUPPORTED;
+#undef VG_CIN1_WG
+        VG_LAUNCHED(1);
+        VG_CHECK_LAUNCH();
+        return VG_OK;
+    }
     if (dbias) {
         if (d->Cout == 1) {
             channel_sum_kernel<float><<<vg_grid_for(rows, 256, 2), 256, 32 * sizeof(float), st>>>((const float*)dy, rows, 1, dbias); VG_LAUNCHED(1);
@@ -875,15 +997,6 @@ int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, floa
             channel_sum_kernel<bf16><<<vg_grid_for(rows, 32, 2), 256, (size_t)(256 / (d->Cout / 8)) * d->Cout * sizeof(float), st>>>(
                 (const bf16*)dy, rows, d->Cout, dbias); VG_LAUNCHED(1);
         }
-    }
-    if (d->Cin == 1) {
-        VG_REQUIRE(d->Cout % 8 == 0);
-        int per_block = (int)((rows + 148 * 8 - 1) / (148 * 8));
-        if (per_block < 256) per_block = 256;
-        cin1_wgrad_kernel<<<vg_cdiv(rows, per_block), 256, 256 * 8 * sizeof(float), st>>>((const float*)x, (const bf16*)dy, dw, d->N, d->ID, d->IH, d->IW,
-                                                                   OD, OH, OW, d->Cout, d->K, d->stride, per_block); VG_LAUNCHED(1);
-        VG_CHECK_LAUNCH();
-        return VG_OK;
     }
     if (d->Cout == 1) {
         VG_REQUIRE(d->stride == 1 && d->Cin % 8 == 0 && d->Cin <= 2048);

@@ -35,11 +35,12 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
-constexpr int TC_THREADS = 288;
+constexpr int TC_THREADS = 416;   // 4 producer warps + 1 MMA warp + 8 epilogue warps
+constexpr int TC_TAIL = 2560;      // barriers, TMEM slot, bias copy
 constexpr int NPROD = 128;   // producer threads (warps 0-3)
 constexpr int MH = 16, MW = 8;
 
@@ -54,11 +55,13 @@ struct TcParams {
     int oso, ood, ooh, oow;
     int BD, NCTA, nblk;
     int ED, EH, EW;
+    int goff;   // origin of the output grid inside the output tensor (cropped dgrad); applied to source and output coordinates
     int stages, act, use_tma, dbg;   // dbg: bit0 = skip brick/weight loads, bit1 = skip MMA issue (timing experiments only)
     const bf16* x;        // source tensor (gather loader)
     int XD, XH, XW, Cx;
     int bd_tiles, bh_tiles, bw_tiles, nwork;
     uint32_t plane_bytes, plane_box_bytes, wstage_bytes, stage_bytes, tmem_cols;
+    tcp::FastDiv by_ehw, by_ew;   // halo voxel index -> (d, h, w)
 };
 
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,6 +127,24 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
         : "memory");
 }
 
+// split TMEM load: issue now, wait later.  The wait names the destination registers as read-write operands so that no use of
+// them can be scheduled above it.
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait16(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
+
 template <int BD>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -133,15 +154,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_base + 16 * p.stages + 32);
     const uint32_t sbase = s_addr(smem);
+    float* sbias = reinterpret_cast<float*>(bar_base + 128);   // bias of all nblk * NCTA (padded) output columns
+    for (int i = threadIdx.x; i < p.nblk * p.NCTA; i += TC_THREADS) sbias[i] = (p.bias && i < p.Cy) ? p.bias[i] : 0.f;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; s++) {
-            mbar_init(full0 + 8 * s, p.use_tma ? 1 : NPROD + 1);
+            mbar_init(full0 + 8 * s, p.use_tma == 1 ? 1 : NPROD + 1);
             mbar_init(empty0 + 8 * s, 1);
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(tfull0 + 8 * b, 1);
-            mbar_init(tempty0 + 8 * b, 128);
+            mbar_init(tempty0 + 8 * b, 256);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -162,7 +185,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         const size_t wstage_elems = p.wstage_bytes / 2;
         const int EV = p.ED * p.EH * p.EW, EHW = p.EH * p.EW;
         const int tid = threadIdx.x;
-        if (p.use_tma && tid != 0) goto producers_done;
+        uint32_t prev_full = 0;   // cp.async loader: full barrier of the stage still in flight
+        if (p.use_tma == 1 && tid != 0) goto producers_done;
         for (int wk = blockIdx.x; wk < p.nwork; wk += gridDim.x) {
             const int nb = wk % p.nblk;
             int brick = wk / p.nblk;
@@ -170,9 +194,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             const int bh = brick % p.bh_tiles; brick /= p.bh_tiles;
             const int bd = brick % p.bd_tiles;
             const int n = brick / p.bd_tiles;
-            const int sd0 = bd * BD - (p.st < 0 ? p.TD - 1 : 0);
-            const int sh0 = bh * MH - (p.st < 0 ? p.TH - 1 : 0);
-            const int sw0 = bw * MW - (p.st < 0 ? p.TW - 1 : 0);
+            const int sd0 = p.goff + bd * BD - (p.st < 0 ? p.TD - 1 : 0);
+            const int sh0 = p.goff + bh * MH - (p.st < 0 ? p.TH - 1 : 0);
+            const int sw0 = p.goff + bw * MW - (p.st < 0 ? p.TW - 1 : 0);
             const bf16* xn = p.x + (size_t)n * p.XD * p.XH * p.XW * p.Cx;
             for (int c = 0; c < p.nchunks; c++) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -180,15 +204,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 const uint32_t dst = sbase + stage * p.stage_bytes;
                 if (p.dbg & 1) {
                     mbar_arrive(full);
-                    if (tid == 0 && !p.use_tma) mbar_arrive(full);
+                    if (tid == 0 && p.use_tma != 1) mbar_arrive(full);
                 } else {
                 if (tid == 0) {
-                    mbar_expect_tx(full, p.wstage_bytes + (p.use_tma ? 2 * p.plane_box_bytes : 0));
+                    mbar_expect_tx(full, p.wstage_bytes + (p.use_tma == 1 ? 2 * p.plane_box_bytes : 0));
                     bulk_load(dst + 2 * p.plane_bytes, p.w + ((size_t)nb * p.nchunks + c) * wstage_elems, p.wstage_bytes, full);
                 }
-                if (p.use_tma) {
+                if (p.use_tma == 1) {
                     tma_load_5d(dst, &tmap, c * 16, sw0, sh0, sd0, n, full);
                     tma_load_5d(dst + p.plane_bytes, &tmap, c * 16 + 8, sw0, sh0, sd0, n, full);
+                } else if (p.use_tma == 2) {
+                    // cp.async gather: 16-byte copies straight into the two planes (zero fill outside the tensor), no register
+                    // staging, so a whole stage (or two) is in flight per SM; published one stage late (see below)
+                    const bf16* xc = xn + c * 16;
+                    for (int v = tid; v < EV; v += NPROD) {
+                        const int ld = (int)p.by_ehw.div((uint32_t)v), rem = v - ld * EHW;
+                        const int lh = (int)p.by_ew.div((uint32_t)rem), lw = rem - lh * p.EW;
+                        const int sd = sd0 + ld, sh = sh0 + lh, sw = sw0 + lw;
+                        const bool ok = (unsigned)sd < (unsigned)p.XD && (unsigned)sh < (unsigned)p.XH && (unsigned)sw < (unsigned)p.XW;
+                        const bf16* src = ok ? xc + (((size_t)sd * p.XH + sh) * p.XW + sw) * p.Cx : xc;
+                        const uint32_t d0 = dst + (uint32_t)v * 16;
+                        const int nbytes = ok ? 16 : 0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d0), "l"(src), "r"(nbytes) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d0 + p.plane_bytes), "l"(src + 8), "r"(nbytes) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;\n" ::: "memory");
+                    if (p.stages >= 3) {
+                        if (prev_full) {
+                            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+                            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                            mbar_arrive(prev_full);
+                        }
+                        prev_full = full;
+                    } else {
+                        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                        mbar_arrive(full);
+                    }
                 } else {
                     // each thread: voxels tid, tid+128, ...; 4 voxels (8 x 128-bit loads) in flight
                     for (int v0 = tid; v0 < EV; v0 += 4 * NPROD) {
@@ -226,6 +278,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
+        }
+        if (prev_full) {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            mbar_arrive(prev_full);
         }
     producers_done:;
     } else if (warp == 4) {
@@ -287,10 +344,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             if (leader) tc_commit(tfull0 + 8 * buf);
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 5..8)
+        // ------------------------------------------------------------------ epilogue (warps 5..12, two warpgroups)
+        // Work unit = (tile m, 16-column block); the two warpgroups take alternate units.  TMEM loads are software-pipelined
+        // (the next unit's tcgen05.ld is in flight while this one is converted and stored); bias comes from shared memory;
+        // every thread owns one voxel row = one full 32-byte sector per unit, written with a single 256-bit store.
         const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int grp = (warp - 5) >> 2;      // warpgroup 0 / 1
         const int r = q * 32 + lane;          // tile row -> (lh, lw)
         const int lh = r >> 3, lw = r & 7;
+        const int nb16 = p.NCTA >> 4, units = BD * nb16;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         int it = 0;
         for (int wk = blockIdx.x; wk < p.nwork; wk += gridDim.x, it++) {
             const int nb = wk % p.nblk;
@@ -305,27 +368,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             const int gh = bh * MH + lh, gw = bw * MW + lw;
             const int yh = gh * p.oso + p.ooh, yw = gw * p.oso + p.oow;
             const bool row_ok = gh < p.GH && gw < p.GW && yh < p.YH && yw < p.YW;
-            for (int m = 0; m < BD; m++) {
-                const int gd = bd * BD + m;
-                const int yd = gd * p.oso + p.ood;
-                const bool ok = row_ok && gd < p.GD && yd < p.YD;
-                for (int n0 = 0; n0 < p.NCTA; n0 += 16) {
-                    uint32_t v[16];
-                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * BD + m) * p.NCTA + n0), v);
-                    const int col0 = nb * p.NCTA + n0;
-                    if (ok && col0 < p.Cy) {
-                        float f[16];
+            const uint32_t tbuf = lane_base + (uint32_t)(buf * BD * p.NCTA);
+            bf16* yrow = (bf16*)p.y + (((size_t)n * p.YD * p.YH + yh) * p.YW + yw) * p.Cy + nb * p.NCTA;
+            const size_t ydstride = (size_t)p.YH * p.YW * p.Cy;
+            auto finish = [&](int u, const uint32_t* v) {
+                const int m = u / nb16, n0 = (u - m * nb16) << 4;
+                const int gd = bd * BD + m, yd = gd * p.oso + p.ood;
+                const int col0 = nb * p.NCTA + n0;
+                if (!(row_ok && gd < p.GD && yd < p.YD && col0 < p.Cy)) return;
+                float f[16];
+                const float4* sb = reinterpret_cast<const float4*>(sbias + col0);
 #pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            f[j] = __uint_as_float(v[j]);
-                            if (p.bias) f[j] += p.bias[col0 + j];
-                            if (p.act == VG_ACT_TANH) f[j] = tanhf(f[j]);
-                        }
-                        bf16* o = (bf16*)p.y + ((((size_t)n * p.YD + yd) * p.YH + yh) * p.YW + yw) * p.Cy + col0;
-                        store8<bf16>(o, f);
-                        store8<bf16>(o + 8, f + 8);
-                    }
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const float4 b4 = sb[j4];
+                    f[4 * j4] = __uint_as_float(v[4 * j4]) + b4.x; f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b4.y;
+                    f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b4.z; f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b4.w;
                 }
+                if (p.act == VG_ACT_TANH) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) f[j] = tanhf(f[j]);
+                }
+                uint32_t o[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                    o[j] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                bf16* dst = yrow + (size_t)yd * ydstride + n0;
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                             "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+            };
+            uint32_t va[16], vb[16];
+            int u = grp;
+            if (u < units) tc_ld16_issue(tbuf + (uint32_t)(u << 4), va);
+            while (u < units) {
+                tc_ld_wait16(va);
+                int un = u + 2;
+                if (un < units) tc_ld16_issue(tbuf + (uint32_t)(un << 4), vb);
+                finish(u, va);
+                u = un;
+                if (u >= units) break;
+                tc_ld_wait16(vb);
+                un = u + 2;
+                if (un < units) tc_ld16_issue(tbuf + (uint32_t)(un << 4), va);
+                finish(u, vb);
+                u = un;
             }
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * buf);
@@ -390,16 +477,16 @@ size_t vg_tc_pack_elems(int ncols, int K_total, int T) {
 // Returns VG_ERR_UNSUPPORTED when the shape does not fit (caller falls back to the mma.sync path).
 int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf16* wpack, void* y, const float* bias, int YD, int YH,
                  int YW, int Cy, int GD, int GH, int GW, int TD, int TH, int TW, int st, int oso, int ood, int ooh, int oow, int act,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, int goff) {
     const int T = TD * TH * TW;
     const int ncta = vg_tc_ncta(Cy, T);
     if (!ncta || Cx % 16) return VG_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
     if (!enc) return VG_ERR_UNSUPPORTED;
-    static int loader = -1;   // 0 = gather (default), 1 = tma
+    static int loader = -1;   // 2 = cp.async gather (default), 1 = tma, 0 = ld/st gather
     if (loader < 0) {
         const char* e = getenv("VG_TC_LOADER");
-        loader = (e && e[0] == 't') ? 1 : 0;
+        loader = (e && e[0] == 't') ? 1 : (e && e[0] == 'g') ? 0 : 2;
     }
     static int dbg = -1;
     if (dbg < 0) {
@@ -415,7 +502,8 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
     p.YD = YD; p.YH = YH; p.YW = YW; p.Cy = Cy;
     p.GD = GD; p.GH = GH; p.GW = GW;
     p.TD = TD; p.TH = TH; p.TW = TW; p.st = st;
-    p.oso = oso; p.ood = ood; p.ooh = ooh; p.oow = oow;
+    p.goff = goff;
+    p.oso = oso; p.ood = ood + goff * oso; p.ooh = ooh + goff * oso; p.oow = oow + goff * oso;
     p.NCTA = ncta; p.nblk = (Cy + ncta - 1) / ncta;
     p.act = act;
     p.EH = MH + TH - 1; p.EW = MW + TW - 1;
@@ -429,7 +517,7 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
         p.plane_box_bytes = (uint32_t)p.ED * p.EH * p.EW * 16;
         p.plane_bytes = (p.plane_box_bytes + 127) & ~127u;
         p.stage_bytes = 2 * p.plane_bytes + p.wstage_bytes;
-        p.stages = (int)((smem_cap - 256) / p.stage_bytes);
+        p.stages = (int)((smem_cap - TC_TAIL) / p.stage_bytes);
         if (p.stages > 4) p.stages = 4;
         if (p.stages >= 2 && 2 * BD * ncta <= 512) break;
         if (BD == 1) return VG_ERR_UNSUPPORTED;
@@ -437,6 +525,7 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * p.BD * ncta)) cols <<= 1;
     p.tmem_cols = cols;
+    p.by_ehw = tcp::FastDiv((uint32_t)(p.EH * p.EW)); p.by_ew = tcp::FastDiv((uint32_t)p.EW);
     p.bd_tiles = (GD + p.BD - 1) / p.BD; p.bh_tiles = (GH + MH - 1) / MH; p.bw_tiles = (GW + MW - 1) / MW;
     const long long nwork = (long long)p.bd_tiles * p.bh_tiles * p.bw_tiles * Nb * p.nblk;
     if (nwork > 0x7fffffff) return VG_ERR_UNSUPPORTED;
@@ -452,7 +541,7 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return VG_ERR_UNSUPPORTED;
 
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 256;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + TC_TAIL;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||

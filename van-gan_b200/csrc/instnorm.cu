@@ -249,13 +249,15 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_partial_kernel(const T* __restri
     const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
     const int PD = g.D + g.pad_lo + g.pad_hi, PH = g.H + g.pad_lo + g.pad_hi, PW = g.W + g.pad_lo + g.pad_hi;
     const int M = PD * PH * PW;
-    float mu[8], rs[8], ga[8], be[8], dr[8], s1[8], s2[8];
+    // per-channel constants kept to three (register budget = loads in flight): z = x*sc + sh decides act', and the sums are
+    // taken of g' = dy*act' and g'*(x - mu); the channel factors drop and drop*rstd are applied once at the end
+    float mu[8], sc[8], sh[8], s1[8], s2[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const int c = c8 * 8 + k;
-        mu[k] = a.mean[n * C + c]; rs[k] = a.rstd[n * C + c];
-        ga[k] = a.gamma[c]; be[k] = a.beta[c];
-        dr[k] = a.drop ? a.drop[n * C + c] : 1.f;
+        mu[k] = a.mean[n * C + c];
+        sc[k] = a.gamma[c] * a.rstd[n * C + c];
+        sh[k] = a.beta[c] - mu[k] * sc[k];
         s1[k] = s2[k] = 0.f;
     }
     const T* xn = x + (size_t)n * g.D * g.H * g.W * C + c8 * 8;
@@ -289,16 +291,20 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_partial_kernel(const T* __restri
                 unpack_raw(rg[u], gy);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    float xh = (f[k] - mu[k]) * rs[k];
-                    float gg = gy[k] * dr[k] * act_grad(fmaf(xh, ga[k], be[k]), a.act, a.slope);
+                    float gg = gy[k] * act_grad(fmaf(f[k], sc[k], sh[k]), a.act, a.slope);
                     s1[k] += gg;
-                    s2[k] += gg * xh;
+                    s2[k] = fmaf(gg, f[k] - mu[k], s2[k]);
                 }
             }
     }
     float* row = sm + ((size_t)vl * C + c8 * 8) * 2;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { row[2 * k] = s1[k]; row[2 * k + 1] = s2[k]; }
+    for (int k = 0; k < 8; k++) {
+        const int c = c8 * 8 + k;
+        const float dr = a.drop ? a.drop[n * C + c] : 1.f;
+        row[2 * k] = s1[k] * dr;
+        row[2 * k + 1] = s2[k] * dr * a.rstd[n * C + c];
+    }
     __syncthreads();
     float* out = partial + ((size_t)n * gridDim.x + blockIdx.x) * C * 2;
     for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
@@ -345,15 +351,18 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_kernel(const T* __restrict
     const int V = g.D * g.H * g.W;
     const float invV = 1.f / (float)V;
     const bool refl = g.pad_mode == VG_PAD_REFLECT && (g.pad_lo | g.pad_hi);
-    float mu[8], rs[8], ga[8], be[8], dr[8], c1[8], c2[8];
+    // dx = P*act'(z)*dy - Q - R*x with z = x*sc + sh:  sc = gamma*rstd, sh = beta - mean*sc, P = sc*drop,
+    // R = sc*rstd*S2/V, Q = sc*S1/V - R*mean  (five per-channel constants instead of seven: registers buy loads in flight)
+    float sc[8], sh[8], cP[8], cQ[8], cR[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const int c = c8 * 8 + k, sc = n * C + c;
-        mu[k] = a.mean[sc]; rs[k] = a.rstd[sc];
-        ga[k] = a.gamma[c]; be[k] = a.beta[c];
-        dr[k] = a.drop ? a.drop[sc] : 1.f;
-        c1[k] = sums[2 * sc] * invV;
-        c2[k] = sums[2 * sc + 1] * invV;
+        const int c = c8 * 8 + k, sci = n * C + c;
+        const float mu = a.mean[sci], rs = a.rstd[sci];
+        sc[k] = a.gamma[c] * rs;
+        sh[k] = a.beta[c] - mu * sc[k];
+        cP[k] = sc[k] * (a.drop ? a.drop[sci] : 1.f);
+        cR[k] = sc[k] * rs * sums[2 * sci + 1] * invV;
+        cQ[k] = sc[k] * sums[2 * sci] * invV - cR[k] * mu;
     }
     const T* xn = x + (size_t)n * V * C + c8 * 8;
     const T* dyn = dy + (size_t)n * PD * PH * PW * C + c8 * 8;
@@ -407,9 +416,8 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_kernel(const T* __restrict
             if (accumulate_dx) load8<T>(dxn + (size_t)vv * C, o);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                float xh = (f[k] - mu[k]) * rs[k];
-                float gg = gy[k] * dr[k] * act_grad(fmaf(xh, ga[k], be[k]), a.act, a.slope);
-                float val = ga[k] * rs[k] * (gg - c1[k] - xh * c2[k]);
+                float gg = gy[k] * act_grad(fmaf(f[k], sc[k], sh[k]), a.act, a.slope);
+                float val = fmaf(cP[k], gg, -fmaf(cR[k], f[k], cQ[k]));
                 o[k] = accumulate_dx ? o[k] + val : val;
             }
             store8<T>(dxn + (size_t)vv * C, o);

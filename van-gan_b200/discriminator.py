@@ -37,7 +37,7 @@ class DiscriminatorModel(E.Network):
         self.norm1 = E.InstanceNorm(self, "d1.in", 2 * f)
         self.conv2 = E.Conv3D(self, "d2.conv", 4, 2, 2 * f, 4 * f, use_bias=False)
         self.norm2 = E.InstanceNorm(self, "d2.in", 4 * f)
-        self.conv3 = E.Conv3D(self, "d3.conv", 4, 1, 4 * f, 8 * f, use_bias=False)
+        self.conv3 = E.Conv3D(self, "d3.conv", 4, 1, 4 * f, 8 * f, use_bias=False, dx_crop=(1, 2))   # TF 'same' zeros
         self.norm3 = E.InstanceNorm(self, "d3.in", 8 * f)
         self.convo = E.Conv3D(self, "dout.conv", 3, 1, 8 * f, 1)
         self.rng_step = 0

@@ -206,7 +206,9 @@ def default_init(shapes, seed):
 class Conv3D:
     """keras.layers.Conv3D(filters, k, strides, padding='valid') over an explicitly padded input."""
 
-    def __init__(self, net, name, k, stride, cin, cout, use_bias=True, act=ACT_NONE):
+    def __init__(self, net, name, k, stride, cin, cout, use_bias=True, act=ACT_NONE, dx_crop=(0, 0)):
+        """dx_crop=(lo, hi): the input carries `lo`/`hi` voxels of ZERO padding per side, so dgrad may skip them."""
+        self.dx_crop = dx_crop
         self.w = net.params[name + ".w"]
         self.b = net.params[name + ".b"] if use_bias else None
         self.k, self.stride, self.cin, self.cout, self.act = k, stride, cin, cout, act
@@ -220,7 +222,8 @@ class Conv3D:
         net.convs.append(self)
 
     def desc(self, n, d, h, w):
-        return ConvDesc(n, d, h, w, self.cin, self.cout, self.k, self.stride, self.x_dtype, self.y_dtype, self.act)
+        return ConvDesc(n, d, h, w, self.cin, self.cout, self.k, self.stride, self.x_dtype, self.y_dtype, self.act,
+                        self.dx_crop[0], self.dx_crop[1])
 
     def repack(self):
         if self.wf is not None or self.wd is not None:
