@@ -215,8 +215,7 @@ def run_gpu(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    prof = _lib.Profiler(["vg_conv3d_fwd", "vg_conv3d_dgrad", "vg_conv3d_wgrad", "vg_instnorm_stats", "vg_instnorm_apply",
-                          "vg_instnorm_bwd", "vg_soft_skel_fwd", "vg_soft_skel_bwd", "vg_upsample_concat", "vg_upsample_concat_bwd"])
+    prof = _lib.Profiler([], detail=True)   # CUDA events around every ABI call, keyed by (call, shape)
     l0 = _lib.lib().vg_launch_count()
     ms = timed(step_resident, args.steps, prof)
     launches = _lib.lib().vg_launch_count() - l0
@@ -224,20 +223,38 @@ def run_gpu(args):
     fam = prof.summary()
     ms_e2e = timed(step_e2e, args.steps)
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     tf_peak, hbm_peak, peak_src = measured_peaks()
     value = G * args.steps / (ms / 1e3)
     e2e = G * args.steps / (ms_e2e / 1e3)
-    convs = [fam[k] for k in ("vg_conv3d_fwd", "vg_conv3d_dgrad", "vg_conv3d_wgrad") if k in fam]
-    conv_ms = sum(c["ms"] for c in convs)
-    conv_flops = sum(c["work"] for c in convs)
-    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
-    roofline = {"kernel": "conv3d implicit-GEMM family (fwd+dgrad+wgrad)", "bound": "tensor", "achieved": achieved,
-                "peak": tf_peak, "unit": "TFLOP/s", "frac": (achieved / tf_peak) if achieved else None, "traffic": None,
+    # family totals and the dominant kernel: tc_conv_kernel (tcgen05 implicit GEMM) runs every stride-1 forward with
+    # Cin,Cout % 16 == 0 and every dgrad with Cin,Cout % 16 == 0 (one launch per call, 8 per stride-2 dgrad)
+    import re
+    families, tc_ms, tc_flop, tc_calls, conv_ms = {}, 0.0, 0.0, 0, 0.0
+    for key, v in fam.items():
+        name = key.split(" ")[0]
+        families[name] = families.get(name, 0.0) + v["ms"]
+        m = re.match(r"vg_conv3d_(fwd|dgrad) (\d+)->(\d+) k(\d)s(\d)", key)
+        if name.startswith("vg_conv3d"):
+            conv_ms += v["ms"]
+        if m:
+            kind, ci, co, st = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(5))
+            if ci % 16 == 0 and co % 16 == 0 and (kind == "dgrad" or st == 1):
+                tc_ms += v["ms"]; tc_flop += v["work"]; tc_calls += v["calls"]
+    achieved = tc_flop / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None
+    roofline = {"kernel": "tc_conv_kernel (tcgen05/TMEM implicit-GEMM Conv3D: stride-1 forward + all dgrads)", "bound": "tensor",
+                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": (achieved / tf_peak) if achieved else None,
+                # one `ncu --set full` capture of this kernel on the 48->16 k3 layer at 8x128^3 (profiles/): dram read+write bytes
+                # of that launch; its algorithmic bytes (bf16 in + out) are 2.22e9
+                "traffic": 2.205e9, "traffic_launch": "fwd 48->16 k3 s1, 8x130^3 -> 8x128^3",
                 "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peak_src,
-                "share_of_step": conv_ms / ms if ms > 0 else None,
-                "families_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(fam.items())}}
+                "calls_per_step": tc_calls / args.steps, "share_of_step": tc_ms / ms if ms > 0 else None,
+                "conv_family_share_of_step": conv_ms / ms if ms > 0 else None,
+                "families_ms_per_step": {k: round(v / args.steps, 3) for k, v in sorted(families.items(), key=lambda kv: -kv[1])[:14]}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",

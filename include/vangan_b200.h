@@ -25,6 +25,10 @@ extern "C" {
 
 enum { VG_OK = 0, VG_ERR_INVALID = -1, VG_ERR_UNSUPPORTED = -2, VG_ERR_WORKSPACE = -3, VG_ERR_CUDA = -4 };
 enum { VG_F32 = 0, VG_BF16 = 1 };
+/* OR-ed into the dtype of the vg_instnorm_* calls: the tensor being normalised is relu(x) — the producer was a
+ * Conv3D(activation='relu') (vnet_model.py:118-126,133-141) whose ReLU is applied on load, and whose gradient mask is
+ * applied to dx */
+enum { VG_IN_RELU_INPUT = 0x100 };
 enum { VG_ACT_NONE = 0, VG_ACT_RELU = 1, VG_ACT_LEAKY = 2, VG_ACT_TANH = 3 };
 enum { VG_PAD_ZERO = 0, VG_PAD_REFLECT = 1 };
 
@@ -113,6 +117,21 @@ int vg_pad_fold(const float* dy, float* dx, int N, int D, int H, int W, int accu
 int vg_accumulate(void* a, const void* b, size_t n, int dtype, void* stream);
 /* out = dy * (1 - y*y) */
 int vg_tanh_bwd(const float* dy, const float* y, float* out, size_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * V-Net generator variant (vnet_model.py:80-146,199-264): MaxPooling3D(2), UpSampling3D(2), concatenate,
+ * ReflectionPadding3D and TF 'same' zero padding, each fused with the padding of the convolution that consumes it.  bf16.
+ * ------------------------------------------------------------------------------------------- */
+/* out[N,D+2p,H+2p,W+2p,C0+C1] = pad_p(concat(upsample_up(a[N,D/up,H/up,W/up,C0]), b[N,D,H,W,C1])); up in {1,2}; C0 or C1 may be 0 */
+int vg_gather_pad(const void* a, const void* b, void* out, int N, int D, int H, int W, int C0, int C1, int up, int pad, int pad_mode,
+                  void* stream);
+/* da = up^3 block-sum of fold_p(dout[..., :C0]); db = fold_p(dout[..., C0:]) (either may be NULL) */
+int vg_gather_pad_bwd(const void* dout, void* da, void* db, int N, int D, int H, int W, int C0, int C1, int up, int pad, int pad_mode,
+                      void* stream);
+/* y[N,D/2+2p,H/2+2p,W/2+2p,C] = pad_p(maxpool2(x[N,D,H,W,C])) */
+int vg_maxpool2_pad(const void* x, void* y, int N, int D, int H, int W, int C, int pad, int pad_mode, void* stream);
+/* dx = fold_p(dy) routed to the first maximum of every 2x2x2 window (scan order d,h,w), zero elsewhere */
+int vg_maxpool2_pad_bwd(const void* x, const void* dy, void* dx, int N, int D, int H, int W, int C, int pad, int pad_mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * clDice soft skeleton (clDice_func.py:8-80).  x: [N,D,H,W] fp32.

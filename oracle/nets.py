@@ -288,3 +288,70 @@ def disc_forward(p, x, noise=None, masks=None, taps=None):
         taps["d3"] = h
     h = _qa(nz(4, h))                                                 # :105-114
     return conv3d(h, p["dout.conv.w"], p["dout.conv.b"], padding="same")
+
+
+# --------------------------------------------------------------------------- V-Net (gen_IS variant)
+def vnet_param_shapes(filters=32, num_layers=4, cin=1):
+    """Trainable variables of custom_vnet(use_batch_norm=False, upsample_mode='upsample') in call order
+    (vnet_model.py:199-264 with the arguments at vangan.py:97-110)."""
+    P = OrderedDict()
+
+    def conv(name, k, ci, co):
+        P[name + ".w"] = (k, k, k, ci, co)
+        P[name + ".b"] = (co,)
+
+    def block(name, ci, co):
+        conv(name + ".c1.conv", 3, ci, co); P[name + ".c1.in.gamma"] = (co,); P[name + ".c1.in.beta"] = (co,)
+        conv(name + ".c2.conv", 3, co, co); P[name + ".c2.in.gamma"] = (co,); P[name + ".c2.in.beta"] = (co,)
+
+    f, ci = filters, cin
+    for l in range(num_layers):
+        block("enc%d" % l, ci, f)
+        ci, f = f, f * 2
+    block("bridge", ci, f)
+    for l in reversed(range(num_layers)):
+        f //= 2
+        conv("dec%d.up.conv" % l, 3, 2 * f, f)
+        block("dec%d" % l, 2 * f, f)
+    conv("head", 1, f, 1)
+    return P
+
+
+def make_vnet_masks(rng, n, filters=32, num_layers=4, rate=0.5, dtype=torch.float32):
+    """SpatialDropout3D(0.5) masks (one per encoder block + bottleneck), scaled by 1/(1-rate) (vnet_model.py:131-132)."""
+    return [torch.tensor((rng.random((n, 1, 1, 1, filters * 2 ** l)) >= rate) / (1.0 - rate), dtype=dtype)
+            for l in range(num_layers + 1)]
+
+
+def _vnet_block(p, name, x, mask=None):
+    """conv3d_block (vnet_model.py:80-146): pad -> Conv3D(relu) -> InstanceNorm -> [SpatialDropout3D] -> pad ->
+    Conv3D(relu) -> InstanceNorm."""
+    c = torch.relu(conv3d(reflect_pad(x), p[name + ".c1.conv.w"], p[name + ".c1.conv.b"]))
+    c = instance_norm(c, p[name + ".c1.in.gamma"], p[name + ".c1.in.beta"])
+    if mask is not None:
+        c = c * mask
+    c = _qa(c)
+    c = torch.relu(conv3d(reflect_pad(c), p[name + ".c2.conv.w"], p[name + ".c2.conv.b"]))
+    return _qa(instance_norm(c, p[name + ".c2.in.gamma"], p[name + ".c2.in.beta"]))
+
+
+def vnet_forward(p, x, num_layers=4, masks=None, taps=None):
+    """custom_vnet(..., use_batch_norm=False, upsample_mode='upsample', dropout=0.5, filters=F, num_layers=4,
+    output_activation='tanh') (vnet_model.py:199-264).  masks=None is inference mode (dropout inactive)."""
+    down = []
+    for l in range(num_layers):
+        x = _vnet_block(p, "enc%d" % l, x, None if masks is None else masks[l])
+        down.append(x)
+        if taps is not None:
+            taps["enc%d" % l] = x
+        x = _ndhwc(F.max_pool3d(_ncdhw(x), 2))                      # MaxPooling3D((2,2,2))
+    x = _vnet_block(p, "bridge", x, None if masks is None else masks[num_layers])
+    if taps is not None:
+        taps["bridge"] = x
+    for l in reversed(range(num_layers)):
+        x = conv3d(upsample2(x), p["dec%d.up.conv.w" % l], p["dec%d.up.conv.b" % l], padding="same")
+        x = torch.cat([x, down[l]], dim=-1)
+        x = _vnet_block(p, "dec%d" % l, x)
+        if taps is not None:
+            taps["dec%d" % l] = x
+    return torch.tanh(conv3d(x, p["head.w"], p["head.b"], padding="same"))

@@ -179,3 +179,17 @@ def test_dp_emulation_sums_replica_gradients():
     assert abs(res["total_IS_loss"] - float(r0["total_IS_loss"]) - float(r1["total_IS_loss"])) < 1e-5
     n = "dec0.cb1.conv.w"
     assert torch.allclose(grads["gen_IS"][n], g0["gen_IS"][n] + g1["gen_IS"][n], rtol=1e-5, atol=1e-7)
+
+
+def test_vnet_oracle_matches_reference_parameter_count_and_shapes():
+    """custom_vnet gen_IS variant (vangan.py:97-110): 25 888 737 trainable parameters, output shape =
+    input shape, inference mode (masks=None) is deterministic and differs from a dropout draw."""
+    from oracle import nets as ON
+    assert sum(int(np.prod(s)) for s in ON.vnet_param_shapes(32, 4, 1).values()) == 25888737
+    P = ON.to_torch(ON.init_params(ON.vnet_param_shapes(16, 3, 1), 3, 0.05), requires_grad=False)
+    x = torch.tensor(np.random.default_rng(0).standard_normal((1, 16, 16, 16, 1)), dtype=torch.float32)
+    y0 = ON.vnet_forward(P, x, 3)
+    y1 = ON.vnet_forward(P, x, 3)
+    ym = ON.vnet_forward(P, x, 3, masks=ON.make_vnet_masks(np.random.default_rng(1), 1, 16, 3))
+    assert y0.shape == x.shape and torch.equal(y0, y1) and float(y0.abs().max()) <= 1.0
+    assert not torch.allclose(y0, ym)

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvangan_b200.so")
 
 VG_F32, VG_BF16 = 0, 1
+IN_RELU_INPUT = 0x100
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT = 0, 1
 _ERR = {-1: "invalid argument", -2: "unsupported shape", -3: "workspace too small", -4: "CUDA error"}
@@ -53,6 +54,10 @@ SIGNATURES = {
     "vg_instnorm_bwd": (_I, [_ID, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
     "vg_upsample_concat": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vg_upsample_concat_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vg_gather_pad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vg_gather_pad_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vg_maxpool2_pad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vg_maxpool2_pad_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_pad_noise": (_I, [_P, _P, _I, _I, _I, _I, _P, _F, _ULL, _P]),
     "vg_pad_fold": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "vg_accumulate": (_I, [_P, _P, _Z, _I, _P]),

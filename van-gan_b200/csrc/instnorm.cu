@@ -18,6 +18,7 @@ constexpr float IN_EPS = 1e-3f;
 struct Geo {
     int N, D, H, W, C;
     int pad_lo, pad_hi, pad_mode;  // output (fwd) / incoming-gradient (bwd) padding
+    int relu_in;                   // the normalised tensor is relu(x) (Conv3D(activation='relu') -> norm, vnet_model.py:118-130)
 };
 
 __device__ __forceinline__ float act_fwd(float z, int act, float slope) {
@@ -77,7 +78,7 @@ struct VoxIter {
 // shift_c = x[n,0,c] (keeps E[x^2]-E[x]^2 well conditioned)
 template <typename T>
 __global__ void __launch_bounds__(NT) in_stats_partial_kernel(const T* __restrict__ x, int V, int C,
-                                                              float* __restrict__ partial) {
+                                                              float* __restrict__ partial, int relu_in) {
     extern __shared__ float sm[];  // [vlanes][C][2]
     const int n = blockIdx.y, cg = C / 8;
     const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
@@ -85,7 +86,10 @@ __global__ void __launch_bounds__(NT) in_stats_partial_kernel(const T* __restric
     float shift[8], s1[8], s2[8];
     load8<T>(xn, shift);
 #pragma unroll
-    for (int k = 0; k < 8; k++) s1[k] = s2[k] = 0.f;
+    for (int k = 0; k < 8; k++) {
+        s1[k] = s2[k] = 0.f;
+        if (relu_in) shift[k] = fmaxf(shift[k], 0.f);
+    }
     const int S = gridDim.x * nvl;
     for (int v = blockIdx.x * nvl + vl; v < V; v += U * S) {
         Raw<T> raw[U];
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(NT) in_stats_partial_kernel(const T* __restric
                 unpack_raw(raw[u], f);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    float d = f[k] - shift[k];
+                    float d = (relu_in ? fmaxf(f[k], 0.f) : f[k]) - shift[k];
                     s1[k] += d;
                     s2[k] += d * d;
                 }
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(NT) in_stats_partial_kernel(const T* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) in_stats_final_kernel(const T* __restrict__ x, const float* __restrict__ partial,
                                                              size_t V, int C, int nblk, int N, float* __restrict__ mean,
-                                                             float* __restrict__ rstd) {
+                                                             float* __restrict__ rstd, int relu_in) {
     int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= N * C) return;
     int n = i / C, c = i % C;
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(256) in_stats_final_kernel(const T* __restrict
     s2 = warp_sum_d(s2);
     if (lane == 0) {
         double shift = (double)(float)x[(size_t)n * V * C + c];
+        if (relu_in && shift < 0) shift = 0;
         double m = s1 / (double)V;
         double var = s2 / (double)V - m * m;
         if (var < 0) var = 0;
@@ -203,7 +208,8 @@ __global__ void __launch_bounds__(NT, 2) in_apply_kernel(const T* __restrict__ x
                 float f[8];
                 unpack_raw(rx[u], f);
 #pragma unroll
-                for (int k = 0; k < 8; k++) o[k] = act_fwd(fmaf(f[k], scale[k], shift[k]), a.act, a.slope) * drop[k];
+                for (int k = 0; k < 8; k++)
+                    o[k] = act_fwd(fmaf(g.relu_in ? fmaxf(f[k], 0.f) : f[k], scale[k], shift[k]), a.act, a.slope) * drop[k];
                 if (rn) {
                     unpack_raw(rr[u], f);
 #pragma unroll
@@ -291,9 +297,10 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_partial_kernel(const T* __restri
                 unpack_raw(rg[u], gy);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    float gg = gy[k] * act_grad(fmaf(f[k], sc[k], sh[k]), a.act, a.slope);
+                    const float xr = g.relu_in ? fmaxf(f[k], 0.f) : f[k];
+                    float gg = gy[k] * act_grad(fmaf(xr, sc[k], sh[k]), a.act, a.slope);
                     s1[k] += gg;
-                    s2[k] = fmaf(gg, f[k] - mu[k], s2[k]);
+                    s2[k] = fmaf(gg, xr - mu[k], s2[k]);
                 }
             }
     }
@@ -416,8 +423,10 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_kernel(const T* __restrict
             if (accumulate_dx) load8<T>(dxn + (size_t)vv * C, o);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                float gg = gy[k] * act_grad(fmaf(f[k], sc[k], sh[k]), a.act, a.slope);
-                float val = fmaf(cP[k], gg, -fmaf(cR[k], f[k], cQ[k]));
+                const float xr = g.relu_in ? fmaxf(f[k], 0.f) : f[k];
+                float gg = gy[k] * act_grad(fmaf(xr, sc[k], sh[k]), a.act, a.slope);
+                float val = fmaf(cP[k], gg, -fmaf(cR[k], xr, cQ[k]));
+                if (g.relu_in && !(f[k] > 0.f)) val = 0.f;   // gradient through the producer's ReLU
                 o[k] = accumulate_dx ? o[k] + val : val;
             }
             store8<T>(dxn + (size_t)vv * C, o);
@@ -436,15 +445,16 @@ inline int pick_grid(long long vox, int N, int C) {
 }
 
 template <typename T>
-int stats_impl(const T* x, int N, int D, int H, int W, int C, float* mean, float* rstd, void* ws, size_t ws_bytes, cudaStream_t st) {
+int stats_impl(const T* x, int N, int D, int H, int W, int C, float* mean, float* rstd, void* ws, size_t ws_bytes, cudaStream_t st,
+               int relu_in) {
     const long long V = (long long)D * H * W;
     if (V * C >= (1LL << 31)) return VG_ERR_UNSUPPORTED;
     const int nblk = pick_grid(V, N, C), nthr = block_threads(C);
     size_t need = (size_t)N * nblk * C * 2 * sizeof(float);
     if (ws_bytes < need) return VG_ERR_WORKSPACE;
     size_t smem = (size_t)(nthr / (C / 8)) * C * 2 * sizeof(float);
-    in_stats_partial_kernel<T><<<dim3(nblk, N), nthr, smem, st>>>(x, (int)V, C, (float*)ws); VG_LAUNCHED(1);
-    in_stats_final_kernel<T><<<vg_cdiv(N * C, 8), 256, 0, st>>>(x, (const float*)ws, (size_t)V, C, nblk, N, mean, rstd); VG_LAUNCHED(1);
+    in_stats_partial_kernel<T><<<dim3(nblk, N), nthr, smem, st>>>(x, (int)V, C, (float*)ws, relu_in); VG_LAUNCHED(1);
+    in_stats_final_kernel<T><<<vg_cdiv(N * C, 8), 256, 0, st>>>(x, (const float*)ws, (size_t)V, C, nblk, N, mean, rstd, relu_in); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -463,8 +473,10 @@ int vg_instnorm_stats(const void* x, int dtype, int N, int D, int H, int W, int 
                       size_t ws_bytes, void* stream) {
     VG_REQUIRE(x && mean && rstd && ws && N > 0 && C % 8 == 0 && C >= 8 && C <= 8 * NT);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == VG_BF16) return stats_impl<bf16>((const bf16*)x, N, D, H, W, C, mean, rstd, ws, ws_bytes, st);
-    if (dtype == VG_F32) return stats_impl<float>((const float*)x, N, D, H, W, C, mean, rstd, ws, ws_bytes, st);
+    const int relu_in = (dtype & VG_IN_RELU_INPUT) ? 1 : 0;
+    dtype &= ~VG_IN_RELU_INPUT;
+    if (dtype == VG_BF16) return stats_impl<bf16>((const bf16*)x, N, D, H, W, C, mean, rstd, ws, ws_bytes, st, relu_in);
+    if (dtype == VG_F32) return stats_impl<float>((const float*)x, N, D, H, W, C, mean, rstd, ws, ws_bytes, st, relu_in);
     return VG_ERR_INVALID;
 }
 
@@ -475,7 +487,8 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
     VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT && d->pad_lo >= 0 && d->pad_hi >= 0);
     if (d->pad_mode == VG_PAD_REFLECT && (d->pad_lo || d->pad_hi))
         VG_REQUIRE(d->pad_lo == 1 && d->pad_hi == 1 && d->D >= 2 && d->H >= 2 && d->W >= 2);
-    Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode};
+    const int dtype = d->dtype & ~VG_IN_RELU_INPUT;
+    Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode, (d->dtype & VG_IN_RELU_INPUT) ? 1 : 0};
     ApplyArgs a{mean, rstd, gamma, beta, drop, noise, d->slope, d->noise_std, d->act, d->seed};
     const int pp = d->pad_lo + d->pad_hi;
     const long long M = (long long)(d->D + pp) * (d->H + pp) * (d->W + pp);
@@ -483,9 +496,9 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
     dim3 grid(pick_grid(M, d->N, d->C), d->N);
     const int nthr = block_threads(d->C);
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->dtype == VG_BF16) {
+    if (dtype == VG_BF16) {
         in_apply_kernel<bf16><<<grid, nthr, 0, st>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, g, a); VG_LAUNCHED(1);
-    } else if (d->dtype == VG_F32) {
+    } else if (dtype == VG_F32) {
         in_apply_kernel<float><<<grid, nthr, 0, st>>>((const float*)x, (const float*)residual, (float*)y, g, a); VG_LAUNCHED(1);
     } else {
         return VG_ERR_INVALID;
@@ -501,7 +514,8 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
     VG_REQUIRE(d && dy && x && mean && rstd && gamma && beta && dx && ws);
     VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT);
-    Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode};
+    const int dtype = d->dtype & ~VG_IN_RELU_INPUT;
+    Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode, (d->dtype & VG_IN_RELU_INPUT) ? 1 : 0};
     BwdArgs a{mean, rstd, gamma, beta, drop, d->slope, d->act};
     const int pp = d->pad_lo + d->pad_hi;
     const long long M = (long long)(d->D + pp) * (d->H + pp) * (d->W + pp);
@@ -515,12 +529,12 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
     size_t smem = (size_t)(nthr / (d->C / 8)) * d->C * 2 * sizeof(float);
     dim3 grid2(pick_grid((long long)d->D * d->H * d->W, d->N, d->C), d->N);
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->dtype == VG_BF16) {
+    if (dtype == VG_BF16) {
         in_bwd_partial_kernel<bf16><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial); VG_LAUNCHED(1);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta); VG_LAUNCHED(1);
         in_bwd_apply_kernel<bf16><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres,
                                                          accumulate_dx); VG_LAUNCHED(1);
-    } else if (d->dtype == VG_F32) {
+    } else if (dtype == VG_F32) {
         in_bwd_partial_kernel<float><<<dim3(nblk, d->N), nthr, smem, st>>>((const float*)dy, (const float*)x, g, a, partial); VG_LAUNCHED(1);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta); VG_LAUNCHED(1);
         in_bwd_apply_kernel<float><<<grid2, nthr, 0, st>>>((const float*)dy, (const float*)x, g, a, sums, (float*)dx, (float*)dres,

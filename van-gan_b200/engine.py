@@ -268,10 +268,12 @@ class InstanceNorm:
         self.c = c
 
     def __call__(self, tape, x, act=ACT_NONE, slope=0.2, residual=None, pad=(0, 0, PAD_ZERO), drop=None, noise=None,
-                 noise_std=0.0, seed=0):
+                 noise_std=0.0, seed=0, relu_input=False):
+        """relu_input: x is the PRE-activation output of a Conv3D(activation='relu') (vnet_model.py:118-126); the ReLU is
+        applied on load and its gradient mask on dx, so the convolution kernels never see the activation."""
         n, d, h, w, c = x.shape
         assert c == self.c
-        dt = dtype_code(x.data)
+        dt = dtype_code(x.data) | (_lib.IN_RELU_INPUT if relu_input else 0)
         ws_bytes = _lib.lib().vg_instnorm_workspace_bytes(n, d, h, w, c)
         ws = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
         mean = torch.empty(n * c, dtype=torch.float32, device=DEV)
@@ -338,4 +340,51 @@ def pad_noise(tape, x, noise=None, noise_std=0.0, seed=0):
             accumulate(x, dx)
 
     tape.record([x], [out], [], bwd, "pad_noise")
+    return out
+
+
+def gather_pad(tape, a, b, up=1, pad=0, mode=PAD_ZERO):
+    """out = pad(concat(upsample_up(a), b)) — UpSampling3D / concatenate / ReflectionPadding3D / TF-'same' zeros in one pass
+    (vnet_model.py:116,132,247-252).  `a` or `b` may be None."""
+    src = a if a is not None else b
+    n = src.shape[0]
+    if a is not None:
+        d, h, w = [s * up for s in a.shape[1:4]]
+    else:
+        d, h, w = b.shape[1:4]
+    c0 = a.shape[-1] if a is not None else 0
+    c1 = b.shape[-1] if b is not None else 0
+    y = torch.empty((n, d + 2 * pad, h + 2 * pad, w + 2 * pad, c0 + c1), dtype=torch.bfloat16, device=DEV)
+    call("vg_gather_pad", a.data if a is not None else None, b.data if b is not None else None, y, n, d, h, w, c0, c1, up, pad, mode)
+    out = Var(y)
+    ins = [v for v in (a, b) if v is not None]
+
+    def bwd(in_needs, p_needs):
+        need = dict(zip([id(v) for v in ins], in_needs))
+        da = torch.empty_like(a.data) if (a is not None and need[id(a)]) else None
+        db = torch.empty_like(b.data) if (b is not None and need[id(b)]) else None
+        call("vg_gather_pad_bwd", out.grad, da, db, n, d, h, w, c0, c1, up, pad, mode)
+        if da is not None:
+            accumulate(a, da)
+        if db is not None:
+            accumulate(b, db)
+
+    tape.record(ins, [out], [], bwd, "gather_pad")
+    return out
+
+
+def maxpool_pad(tape, x, pad=0, mode=PAD_ZERO):
+    """pad(MaxPooling3D(2)(x)) (vnet_model.py:223 followed by the ReflectionPadding3D at :116)."""
+    n, d, h, w, c = x.shape
+    y = torch.empty((n, d // 2 + 2 * pad, h // 2 + 2 * pad, w // 2 + 2 * pad, c), dtype=torch.bfloat16, device=DEV)
+    call("vg_maxpool2_pad", x.data, y, n, d, h, w, c, pad, mode)
+    out = Var(y)
+
+    def bwd(in_needs, p_needs):
+        if in_needs[0]:
+            dx = torch.empty_like(x.data)
+            call("vg_maxpool2_pad_bwd", x.data, out.grad, dx, n, d, h, w, c, pad, mode)
+            accumulate(x, dx)
+
+    tape.record([x], [out], [], bwd, "maxpool_pad")
     return out

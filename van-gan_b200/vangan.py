@@ -15,6 +15,7 @@ from .distribute import Strategy
 from .loss_functions import (LossContext, cycle_loss, cycle_reconstruction, cycle_seg_loss, discriminator_loss_fn,
                              generator_loss_fn)
 from .resunet_model import ResUNet
+from .vnet_model import VNetModel, custom_vnet
 
 RESULT_KEYS = ("total_IS_loss", "total_SI_loss", "D_I_loss", "D_S_loss", "gen_IS_loss", "gen_SI_loss",
                "cycle_gen_SIS_loss", "cycle_gen_ISI_loss", "seg_loss", "reconstruction_loss_I")
@@ -60,12 +61,19 @@ class VanGan:
         self.keep_last = False   # tests set this to inspect fake/cycled volumes after a step
 
         with self.strategy.scope():
-            if gen_i2s != 'resUnet' or gen_s2i != 'resUnet':
-                raise NotImplementedError("generators: only 'resUnet' (what main.py:196-200 selects) is built; "
-                                          "'resnet'/'vnet' are listed under next steps in DESIGN.md")
-            self.gen_IS = ResUNet(input_shape=self.subvol_patch_size, upsample_mode='simple', dropout=0.1,
-                                  dropout_change_per_layer=0.1, dropout_type='none', use_attention_gate=False,
-                                  filters=16, num_layers=4, name='generator_IS', seed=seed)
+            if gen_i2s not in ('resUnet', 'vnet') or gen_s2i != 'resUnet':
+                raise NotImplementedError("generators: 'resUnet' (what main.py:196-200 selects) for both, and 'vnet' for "
+                                          "gen_i2s (vangan.py:97-110) are built; 'resnet' and the BatchNorm/deconv 'vnet' "
+                                          "gen_s2i variant are listed under next steps in DESIGN.md")
+            if gen_i2s == 'vnet':
+                self.gen_IS = custom_vnet(input_shape=self.subvol_patch_size, activation='relu', use_batch_norm=False,
+                                          upsample_mode='upsample', dropout=0.5, dropout_change_per_layer=0.0,
+                                          dropout_type='spatial', use_dropout_on_upsampling=False, use_attention_gate=False,
+                                          filters=32, num_layers=4, output_activation='tanh', name='generator_IS', seed=seed)
+            else:
+                self.gen_IS = ResUNet(input_shape=self.subvol_patch_size, upsample_mode='simple', dropout=0.1,
+                                      dropout_change_per_layer=0.1, dropout_type='none', use_attention_gate=False,
+                                      filters=16, num_layers=4, name='generator_IS', seed=seed)
             self.gen_SI = ResUNet(input_shape=self.seg_subvol_patch_size, upsample_mode='simple', dropout=0.1,
                                   dropout_change_per_layer=0.1, dropout_type='none', use_attention_gate=False,
                                   filters=16, num_layers=4, use_input_noise=False, name='generator_SI', seed=seed + 1)
@@ -89,6 +97,12 @@ class VanGan:
             t = t.to(E.DEV, non_blocking=True)
         return E.Var(t.to(torch.float32).contiguous())
 
+    def _gen(self, net, tape, x, training, app):
+        """One generator application; the V-Net variant draws its SpatialDropout3D masks per (step, application)."""
+        if isinstance(net, VNetModel):
+            return net.forward(tape, x, training=training, seed=self.step * 4 + app)
+        return net.forward(tape, x)
+
     def _disc(self, net, tape, x, training, rand, key, app):
         noise, masks = (None, None) if rand is None else rand[key]
         return net.forward(tape, x, training=training, noise=noise, masks=masks, seed=self.step * 4 + app)
@@ -102,12 +116,12 @@ class VanGan:
         self.tape = tape
         self.loss_ctx = LossContext()
         real_I, real_S = self._as_var(real_I), self._as_var(real_S)
-        fake_S = self.gen_IS.forward(tape, real_I)
-        fake_I = self.gen_SI.forward(tape, real_S)
-        cycled_S = self.gen_IS.forward(tape, fake_I)
+        fake_S = self._gen(self.gen_IS, tape, real_I, training, 0)
+        fake_I = self._gen(self.gen_SI, tape, real_S, training, 1)
+        cycled_S = self._gen(self.gen_IS, tape, fake_I, training, 2)
         cycle_loss_I = self.cycle_loss_fn(self, real_S, cycled_S, typ="bce")
         seg_loss = self.seg_loss_fn(self, real_S, cycled_S, iters=self.cldice_iters)
-        cycled_I = self.gen_SI.forward(tape, fake_S)
+        cycled_I = self._gen(self.gen_SI, tape, fake_S, training, 3)
         cycle_loss_S = self.cycle_loss_fn(self, real_I, cycled_I, typ='mse')
         reconstruction_loss = self.reconstruction_loss(self, real_I, cycled_I)
 
