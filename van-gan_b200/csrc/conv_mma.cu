@@ -790,8 +790,12 @@ inline size_t mma_dgrad_elems(const vg_conv3d_desc* d) {
                 tot += (size_t)class_taps(d->K, d->stride, a) * class_taps(d->K, d->stride, b) * class_taps(d->K, d->stride, c);
     return tot * rup(d->Cin, NPAD) * d->Cout;
 }
+// stride 2 (K = 3 or 4): run as 8 parity classes of 2x2x2 taps over strided views of x (K = 3 is zero-padded to 4)
+inline bool tc_fwd_s2(const vg_conv3d_desc* d) { return d->stride == 2 && d->K >= 3; }
+inline int tc_fwd_taps(const vg_conv3d_desc* d) { return tc_fwd_s2(d) ? 8 : d->K * d->K * d->K; }
+inline int tc_fwd_kdim(const vg_conv3d_desc* d) { return tc_fwd_s2(d) ? 8 * d->Cin : d->Cin; }
 inline bool tc_fwd_ok(const vg_conv3d_desc* d) {
-    return d->stride == 1 && d->Cin % 16 == 0 && d->Cout % 16 == 0 && vg_tc_ncta(d->Cout, d->K * d->K * d->K) > 0;
+    return (d->stride == 1 || tc_fwd_s2(d)) && d->Cin % 16 == 0 && d->Cout % 16 == 0 && vg_tc_ncta(d->Cout, tc_fwd_taps(d)) > 0;
 }
 inline bool tc_dgrad_ok(const vg_conv3d_desc* d) { return d->Cin % 16 == 0 && d->Cout % 16 == 0; }
 inline size_t tc_dgrad_class_elems(const vg_conv3d_desc* d, int a, int b, int c) {
@@ -811,7 +815,7 @@ size_t vg_conv3d_packed_bytes(const vg_conv3d_desc* d, int for_dgrad) {
     // layout: [ mma.sync operand pack | (256-byte aligned) tcgen05 operand pack ]
     if (!for_dgrad) {
         size_t bytes = rup256(mma_fwd_elems(d) * 2);
-        if (tc_fwd_ok(d)) bytes += vg_tc_pack_elems(d->Cout, d->Cin, d->K * d->K * d->K) * 2;
+        if (tc_fwd_ok(d)) bytes += vg_tc_pack_elems(d->Cout, tc_fwd_kdim(d), tc_fwd_taps(d)) * 2;
         return bytes;
     }
     size_t bytes = rup256(mma_dgrad_elems(d) * 2);
@@ -837,7 +841,9 @@ int vg_conv3d_pack_weights(const vg_conv3d_desc* d, const float* w, void* w_fwd,
     }
     if (w_fwd && tc_fwd_ok(d)) {
         bf16* dst = (bf16*)((char*)w_fwd + rup256(mma_fwd_elems(d) * 2));
-        if (vg_tc_pack(w, dst, d->K, 1, d->Cin, d->Cout, 0, 0, 0, 0, d->K, d->K, d->K, st) != VG_OK) return VG_ERR_CUDA;
+        if (tc_fwd_s2(d)) {
+            if (vg_tc_pack(w, dst, d->K, 2, d->Cin, d->Cout, 2, 0, 0, 0, 2, 2, 2, st) != VG_OK) return VG_ERR_CUDA;
+        } else if (vg_tc_pack(w, dst, d->K, 1, d->Cin, d->Cout, 0, 0, 0, 0, d->K, d->K, d->K, st) != VG_OK) return VG_ERR_CUDA;
     }
     if (w_dgrad && tc_dgrad_ok(d)) {
         char* dst = (char*)w_dgrad + rup256(mma_dgrad_elems(d) * 2);
@@ -883,8 +889,9 @@ int vg_conv3d_fwd(const vg_conv3d_desc* d, const void* x, const void* w_fwd, con
     }
     if (tc_enabled() && tc_fwd_ok(d) && d->y_dtype == VG_BF16) {
         const bf16* wt = (const bf16*)((const char*)w_fwd + rup256(mma_fwd_elems(d) * 2));
-        int rc = vg_tc_launch((const bf16*)x, d->N, d->ID, d->IH, d->IW, d->Cin, wt, y, bias, OD, OH, OW, d->Cout, OD, OH, OW, d->K, d->K,
-                              d->K, +1, 1, 0, 0, 0, d->act, st);
+        const int kt = tc_fwd_s2(d) ? 2 : d->K;
+        int rc = vg_tc_launch((const bf16*)x, d->N, d->ID, d->IH, d->IW, d->Cin, wt, y, bias, OD, OH, OW, d->Cout, OD, OH, OW, kt, kt, kt,
+                              +1, 1, 0, 0, 0, d->act, st, 0, d->stride);
         if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
         if (rc != VG_ERR_UNSUPPORTED) return rc;
     }

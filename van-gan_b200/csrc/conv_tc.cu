@@ -55,6 +55,7 @@ struct TcParams {
     int oso, ood, ooh, oow;
     int BD, NCTA, nblk;
     int ED, EH, EW;
+    int ss, cpc;   // source stride (1, or 2 = stride-2 forward as 8 parity classes of 2x2x2 taps) and 16-channel chunks per class
     int goff;   // origin of the output grid inside the output tensor (cropped dgrad); applied to source and output coordinates
     int stages, act, use_tma, dbg;   // dbg: bit0 = skip brick/weight loads, bit1 = skip MMA issue (timing experiments only)
     const bf16* x;        // source tensor (gather loader)
@@ -216,11 +217,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 } else if (p.use_tma == 2) {
                     // cp.async gather: 16-byte copies straight into the two planes (zero fill outside the tensor), no register
                     // staging, so a whole stage (or two) is in flight per SM; published one stage late (see below)
-                    const bf16* xc = xn + c * 16;
+                    // stride-2 forward: chunk c = (parity class, 16-channel chunk); the class reads the strided view x[2i + a]
+                    const int cls = p.ss == 2 ? c / p.cpc : 0, cc = p.ss == 2 ? c - cls * p.cpc : c;
+                    const int oa = (cls >> 2) & 1, ob = (cls >> 1) & 1, oc = cls & 1;
+                    const bf16* xc = xn + cc * 16;
                     for (int v = tid; v < EV; v += NPROD) {
                         const int ld = (int)p.by_ehw.div((uint32_t)v), rem = v - ld * EHW;
                         const int lh = (int)p.by_ew.div((uint32_t)rem), lw = rem - lh * p.EW;
-                        const int sd = sd0 + ld, sh = sh0 + lh, sw = sw0 + lw;
+                        const int sd = p.ss * (sd0 + ld) + oa, sh = p.ss * (sh0 + lh) + ob, sw = p.ss * (sw0 + lw) + oc;
                         const bool ok = (unsigned)sd < (unsigned)p.XD && (unsigned)sh < (unsigned)p.XH && (unsigned)sw < (unsigned)p.XW;
                         const bf16* src = ok ? xc + (((size_t)sd * p.XH + sh) * p.XW + sw) * p.Cx : xc;
                         const uint32_t d0 = dst + (uint32_t)v * 16;
@@ -477,7 +481,7 @@ size_t vg_tc_pack_elems(int ncols, int K_total, int T) {
 // Returns VG_ERR_UNSUPPORTED when the shape does not fit (caller falls back to the mma.sync path).
 int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf16* wpack, void* y, const float* bias, int YD, int YH,
                  int YW, int Cy, int GD, int GH, int GW, int TD, int TH, int TW, int st, int oso, int ood, int ooh, int oow, int act,
-                 cudaStream_t stream, int goff) {
+                 cudaStream_t stream, int goff, int ss) {
     const int T = TD * TH * TW;
     const int ncta = vg_tc_ncta(Cy, T);
     if (!ncta || Cx % 16) return VG_ERR_UNSUPPORTED;
@@ -494,11 +498,12 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
         dbg = e ? atoi(e) : 0;
     }
     TcParams p{};
-    p.use_tma = loader;
+    p.use_tma = ss == 2 ? 2 : loader;   // the strided view is only implemented by the cp.async gather
     p.dbg = dbg;
     p.x = x; p.XD = XD; p.XH = XH; p.XW = XW; p.Cx = Cx;
     p.w = wpack; p.y = y; p.bias = bias;
-    p.Nb = Nb; p.nchunks = Cx / 16;
+    p.ss = ss; p.cpc = Cx / 16;
+    p.Nb = Nb; p.nchunks = (ss == 2 ? 8 : 1) * (Cx / 16);
     p.YD = YD; p.YH = YH; p.YW = YW; p.Cy = Cy;
     p.GD = GD; p.GH = GH; p.GW = GW;
     p.TD = TD; p.TH = TH; p.TW = TW; p.st = st;
@@ -562,11 +567,13 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
 // pack kernel for the tensor-core layout: out[nb][c][t][kh][n][j] = src(t, k = c*16+kh*8+j, col = nb*NCTA+n)
 // fwd:   src(t,k,col) = w[t][k][col]            (K = Cin, cols = Cout)
 // dgrad: src(t',k,col) = w[tap(t')][col][k]      (K = Cout, cols = Cin), taps restricted to one stride-parity class
+// fwd stride 2 (dgrad == 2): chunk c = (parity class a,b,c ; 16-channel chunk), taps t' in 2x2x2, src = w[2t'+a][k][col] (0 if >= K)
 __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int K, int stride, int Cin, int Cout, int dgrad,
                                int ad, int ah, int aw, int td, int th, int tw, int ncta, int nblk) {
     const int T = td * th * tw;
-    const int Kt = dgrad ? Cout : Cin, ncols = dgrad ? Cin : Cout;
-    const int nchunks = Kt / 16;
+    const int Kt = dgrad == 1 ? Cout : Cin, ncols = dgrad == 1 ? Cin : Cout;
+    const int cpc = Kt / 16;
+    const int nchunks = (dgrad == 2 ? 8 : 1) * cpc;
     size_t total = (size_t)nblk * nchunks * T * 2 * ncta * 8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
@@ -576,12 +583,21 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ o
         int t = (int)(r % T); r /= T;
         int c = (int)(r % nchunks);
         int nb = (int)(r / nchunks);
-        int k = c * 16 + kh * 8 + j, col = nb * ncta + n;
+        int col = nb * ncta + n;
         int w_ = t % tw, h_ = (t / tw) % th, d_ = t / (tw * th);
-        int kd = dgrad ? ad + stride * d_ : d_, kh2 = dgrad ? ah + stride * h_ : h_, kw = dgrad ? aw + stride * w_ : w_;
+        int k, kd, kh2, kw;
+        if (dgrad == 2) {
+            const int cls = c / cpc, cc = c - cls * cpc;
+            k = cc * 16 + kh * 8 + j;
+            kd = 2 * d_ + ((cls >> 2) & 1); kh2 = 2 * h_ + ((cls >> 1) & 1); kw = 2 * w_ + (cls & 1);
+        } else {
+            k = c * 16 + kh * 8 + j;
+            kd = dgrad ? ad + stride * d_ : d_; kh2 = dgrad ? ah + stride * h_ : h_; kw = dgrad ? aw + stride * w_ : w_;
+        }
         int tap = (kd * K + kh2) * K + kw;
         float v = 0.f;
-        if (col < ncols) v = dgrad ? w[((size_t)tap * Cin + col) * Cout + k] : w[((size_t)tap * Cin + k) * Cout + col];
+        if (col < ncols && kd < K && kh2 < K && kw < K)
+            v = dgrad == 1 ? w[((size_t)tap * Cin + col) * Cout + k] : w[((size_t)tap * Cin + k) * Cout + col];
         out[i] = __float2bfloat16(v);
     }
 }
@@ -589,11 +605,11 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ o
 int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, int dgrad, int ad, int ah, int aw, int td, int th,
                int tw, cudaStream_t st) {
     const int T = td * th * tw;
-    const int ncols = dgrad ? Cin : Cout;
+    const int ncols = dgrad == 1 ? Cin : Cout;
     const int ncta = vg_tc_ncta(ncols, T);
     if (!ncta) return VG_ERR_UNSUPPORTED;
     const int nblk = (ncols + ncta - 1) / ncta;
-    size_t total = vg_tc_pack_elems(ncols, dgrad ? Cout : Cin, T);
+    size_t total = vg_tc_pack_elems(ncols, dgrad == 1 ? Cout : (dgrad == 2 ? 8 * Cin : Cin), T);
     tc_pack_kernel<<<vg_grid_for((long long)total, 256, 4), 256, 0, st>>>(w, out, K, stride, Cin, Cout, dgrad, ad, ah, aw, td, th, tw, ncta,
                                                                           nblk);
     VG_LAUNCHED(1);
