@@ -266,3 +266,42 @@ def test_clip_adam(cuda):
         opt.apply(P, {k: torch.tensor(v) for k, v in g.items()})
         for k in shapes:
             assert torch.allclose(net.params[k].w.cpu(), P[k], rtol=1e-5, atol=1e-6), (it, k)
+
+
+@pytest.mark.parametrize("sp,C,S", [(1, 16, 12), (1, 48, 8), (2, 16, 12), (2, 64, 6)])
+def test_instnorm_specialised_generator_cases(cuda, sp, C, S):
+    """The two compile-time-specialised InstanceNorm instances of the generator hot path (bf16, no dropout / noise):
+    sp=1 InstanceNorm -> ReLU -> ReflectionPadding3D (resunet_model.py:42-66); sp=2 InstanceNorm + residual Add
+    (resunet_model.py:96-100,133-143).  Forward and all gradients against the fp32 oracle on bf16-valued inputs."""
+    from collections import OrderedDict
+    from oracle import nets as ON
+    from van_gan_b200 import engine as E
+    from van_gan_b200._lib import ACT_NONE, ACT_RELU, PAD_REFLECT, PAD_ZERO
+    rng = np.random.default_rng(17 + sp)
+    N = 2
+    x = _bf(torch.tensor(rng.standard_normal((N, S, S + 1, S + 2, C)) * 1.5 + 0.7, dtype=torch.float32))
+    res = _bf(torch.tensor(rng.standard_normal(x.shape), dtype=torch.float32))
+    gamma = torch.tensor(1 + 0.2 * rng.standard_normal(C), dtype=torch.float32)
+    beta = torch.tensor(0.2 * rng.standard_normal(C), dtype=torch.float32)
+    xr, rr = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = ON.instance_norm(xr, gr, br)
+    y = ON.reflect_pad(torch.relu(y)) if sp == 1 else y + rr
+    gout = _bf(torch.tensor(rng.standard_normal(y.shape), dtype=torch.float32))
+    y.backward(gout)
+    net = E.Network("t", OrderedDict([("n.gamma", (C,)), ("n.beta", (C,))]))
+    net.load({"n.gamma": gamma.numpy(), "n.beta": beta.numpy()})
+    layer = E.InstanceNorm(net, "n", C)
+    tape = E.Tape()
+    xv, rv = E.Var(x.to(torch.bfloat16).cuda()), E.Var(res.to(torch.bfloat16).cuda())
+    if sp == 1:
+        out = layer(tape, xv, act=ACT_RELU, pad=(1, 1, PAD_REFLECT))
+    else:
+        out = layer(tape, xv, act=ACT_NONE, residual=rv)
+    assert rel_l2(out.data.float(), y.detach()) < 1.5e-2
+    tape.backward([(out, gout.to(torch.bfloat16).cuda())], net.trainable_variables, wrt_vars=[xv, rv] if sp == 2 else [xv])
+    assert rel_l2(xv.grad.float(), xr.grad) < 2e-2
+    if sp == 2:
+        assert rel_l2(rv.grad.float(), rr.grad) < 2e-2
+    assert rel_l2(net.params["n.gamma"].grad, gr.grad) < 2e-2
+    assert rel_l2(net.params["n.beta"].grad, br.grad) < 2e-2

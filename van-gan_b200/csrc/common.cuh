@@ -73,23 +73,21 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh) {
 // reflect index for pad-1 REFLECT padding: -1 -> 1, n -> n-2
 __device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
-// 8 x bf16 <-> 8 x float through one 128-bit access
-struct __align__(16) bf16x8 {
-    __nv_bfloat162 v[4];
-};
+// 8 x bf16 <-> 8 x float through one 128-bit access.  The packet is a plain uint4: nvcc only emits LDG.128 / STG.128 for
+// the built-in vector types (a struct of four __nv_bfloat162 is copied member-wise, i.e. as four 32-bit accesses).
+typedef uint4 bf16x8;
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float2 t = __bfloat1622float2(p.v[i]);
-        f[2 * i] = t.x;
-        f[2 * i + 1] = t.y;
-    }
+    f[0] = __uint_as_float(p.x << 16); f[1] = __uint_as_float(p.x & 0xffff0000u);
+    f[2] = __uint_as_float(p.y << 16); f[3] = __uint_as_float(p.y & 0xffff0000u);
+    f[4] = __uint_as_float(p.z << 16); f[5] = __uint_as_float(p.z & 0xffff0000u);
+    f[6] = __uint_as_float(p.w << 16); f[7] = __uint_as_float(p.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h2);
 }
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
-    bf16x8 p;
-#pragma unroll
-    for (int i = 0; i < 4; i++) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    return p;
+    return make_uint4(pack2_bf16(f[0], f[1]), pack2_bf16(f[2], f[3]), pack2_bf16(f[4], f[5]), pack2_bf16(f[6], f[7]));
 }
 
 // generic 8-wide load/store on either float or bf16 storage
@@ -97,7 +95,7 @@ template <typename T>
 __device__ __forceinline__ void load8(const T* p, float* f);
 template <>
 __device__ __forceinline__ void load8<bf16>(const bf16* p, float* f) {
-    bf16x8 v = *reinterpret_cast<const bf16x8*>(p);
+    const bf16x8 v = *reinterpret_cast<const uint4*>(p);   // plain load: some callers read-modify-write the same buffer
     unpack8(v, f);
 }
 template <>

@@ -44,7 +44,7 @@ template <typename T> struct Raw;
 template <> struct Raw<bf16> { bf16x8 v; };
 template <> struct Raw<float> { float4 a, b; };
 template <typename T> __device__ __forceinline__ void load_raw(const T* p, Raw<T>& r);
-template <> __device__ __forceinline__ void load_raw<bf16>(const bf16* p, Raw<bf16>& r) { r.v = *reinterpret_cast<const bf16x8*>(p); }
+template <> __device__ __forceinline__ void load_raw<bf16>(const bf16* p, Raw<bf16>& r) { r.v = *reinterpret_cast<const uint4*>(p); }
 template <> __device__ __forceinline__ void load_raw<float>(const float* p, Raw<float>& r) {
     r.a = reinterpret_cast<const float4*>(p)[0];
     r.b = reinterpret_cast<const float4*>(p)[1];
@@ -434,6 +434,275 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_kernel(const T* __restrict
     }
 }
 
+// ================================================================== specialised instances (generator hot path)
+// Same arithmetic as the generic kernels above with the options fixed at compile time, so the unrolled inner loops are
+// straight-line code: SP = 1: InstanceNorm -> ReLU -> ReflectionPadding3D (conv_block, resunet_model.py:42-66);
+// SP = 2: InstanceNorm + residual Add, no padding (resunet_model.py:96-100,133-143).  bf16, no dropout / noise.
+// SP: 0 = generic (all options read at run time); 1 = InstanceNorm -> ReLU -> ReflectionPadding3D (conv_block, resunet_model.py:42-66);
+// 2 = InstanceNorm + residual Add, no padding (resunet_model.py:96-100,133-143).  The specialised instances have a
+// straight-line inner loop (the generic one carries ~200 branches per unrolled body).
+template <typename T, int SP>
+__global__ void __launch_bounds__(NT, 2) in_apply_sp_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                                      Geo g, ApplyArgs a) {
+    const int act = SP == 0 ? a.act : (SP == 1 ? VG_ACT_RELU : VG_ACT_NONE);
+    const int pad_lo = SP == 0 ? g.pad_lo : (SP == 1 ? 1 : 0), pad_hi = SP == 0 ? g.pad_hi : (SP == 1 ? 1 : 0);
+    const int pad_mode = SP == 0 ? pad_mode : VG_PAD_REFLECT;
+    const bool relu_in = SP == 0 && g.relu_in, has_drop = SP == 0 && a.drop != nullptr;
+    const int n = blockIdx.y, cg = g.C / 8;
+    const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
+    const int PD = g.D + pad_lo + pad_hi, PH = g.H + pad_lo + pad_hi, PW = g.W + pad_lo + pad_hi;
+    const int M = PD * PH * PW;
+    float scale[8], shift[8], drop[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = c8 * 8 + k, sc = n * g.C + c;
+        scale[k] = a.gamma[c] * a.rstd[sc];
+        shift[k] = a.beta[c] - a.mean[sc] * scale[k];
+        drop[k] = has_drop ? a.drop[sc] : 1.f;
+    }
+    const size_t in_sample = (size_t)g.D * g.H * g.W * g.C;
+    const T* xn = x + (size_t)n * in_sample + c8 * 8;
+    const T* rn = (SP == 0 ? res != nullptr : SP == 2) ? res + (size_t)n * in_sample + c8 * 8 : nullptr;
+    T* yn = y + (size_t)n * M * g.C + c8 * 8;
+    const int S = gridDim.x * nvl;
+    VoxIter it;
+    it.init(blockIdx.x * nvl + vl, S, PH, PW);
+    for (int v = blockIdx.x * nvl + vl; v < M; v += U * S) {
+        Raw<T> rx[U], rr[U];
+        int src[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            src[u] = -1;
+            if (v + u * S < M) {
+                int d = it.pd - pad_lo, h = it.ph - pad_lo, w = it.pw - pad_lo;
+                const bool oob = (unsigned)d >= (unsigned)g.D || (unsigned)h >= (unsigned)g.H || (unsigned)w >= (unsigned)g.W;
+                if (!(oob && pad_mode == VG_PAD_ZERO)) {
+                    if (oob) { d = reflect1(d, g.D); h = reflect1(h, g.H); w = reflect1(w, g.W); }
+                    src[u] = (d * g.H + h) * g.W + w;
+                    load_raw<T>(xn + (size_t)src[u] * g.C, rx[u]);
+                    if (SP == 2 || (SP == 0 && rn)) load_raw<T>(rn + (size_t)src[u] * g.C, rr[u]);
+                }
+            }
+            it.next();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int vv = v + u * S;
+            if (vv >= M) continue;
+            float o[8];
+            if (src[u] < 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) o[k] = 0.f;
+            } else {
+                float f[8];
+                unpack_raw(rx[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    o[k] = act_fwd(fmaf(relu_in ? fmaxf(f[k], 0.f) : f[k], scale[k], shift[k]), act, a.slope) * (SP == 0 ? drop[k] : 1.f);
+                if (SP == 2 || (SP == 0 && rn)) {
+                    unpack_raw(rr[u], f);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) o[k] += f[k];
+                }
+                if (SP == 0 && a.noise) {
+                    // explicit noise tensor: padded layout for REFLECT (noise is added after the pad layer),
+                    // unpadded layout for ZERO ('same' convs pad after the noise layer)
+                    const float* np = pad_mode == VG_PAD_REFLECT ? a.noise + ((size_t)n * M + vv) * g.C + c8 * 8
+                                                                   : a.noise + (size_t)n * in_sample + (size_t)src[u] * g.C + c8 * 8;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) o[k] += np[k];
+                } else if (SP == 0 && a.noise_std > 0.f) {
+                    const unsigned long long i = ((unsigned long long)n * M + vv) * cg + c8;
+                    uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                    uint4 r0 = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0u, 0x56414e47u), key);
+                    uint4 r1 = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 1u, 0x56414e47u), key);
+                    float2 n0 = box_muller(r0.x, r0.y), n1 = box_muller(r0.z, r0.w), n2 = box_muller(r1.x, r1.y),
+                           n3 = box_muller(r1.z, r1.w);
+                    o[0] += a.noise_std * n0.x; o[1] += a.noise_std * n0.y; o[2] += a.noise_std * n1.x; o[3] += a.noise_std * n1.y;
+                    o[4] += a.noise_std * n2.x; o[5] += a.noise_std * n2.y; o[6] += a.noise_std * n3.x; o[7] += a.noise_std * n3.y;
+                }
+            }
+            store8<T>(yn + (size_t)vv * g.C, o);
+        }
+    }
+}
+
+template <typename T, int SP>
+__global__ void __launch_bounds__(NT, 2) in_bwd_partial_sp_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g,
+                                                            BwdArgs a, float* __restrict__ partial) {
+    const int act = SP == 0 ? a.act : (SP == 1 ? VG_ACT_RELU : VG_ACT_NONE);
+    const int pad_lo = SP == 0 ? g.pad_lo : (SP == 1 ? 1 : 0), pad_hi = SP == 0 ? g.pad_hi : (SP == 1 ? 1 : 0);
+    const int pad_mode = SP == 0 ? pad_mode : VG_PAD_REFLECT;
+    const bool relu_in = SP == 0 && relu_in;
+    extern __shared__ float sm[];
+    const int n = blockIdx.y, C = g.C, cg = C / 8;
+    const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
+    const int PD = g.D + pad_lo + pad_hi, PH = g.H + pad_lo + pad_hi, PW = g.W + pad_lo + pad_hi;
+    const int M = PD * PH * PW;
+    // per-channel constants kept to three (register budget = loads in flight): z = x*sc + sh decides act', and the sums are
+    // taken of g' = dy*act' and g'*(x - mu); the channel factors drop and drop*rstd are applied once at the end
+    float mu[8], sc[8], sh[8], s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = c8 * 8 + k;
+        mu[k] = a.mean[n * C + c];
+        sc[k] = a.gamma[c] * a.rstd[n * C + c];
+        sh[k] = a.beta[c] - mu[k] * sc[k];
+        s1[k] = s2[k] = 0.f;
+    }
+    const T* xn = x + (size_t)n * g.D * g.H * g.W * C + c8 * 8;
+    const T* dyn = dy + (size_t)n * M * C + c8 * 8;
+    const int S = gridDim.x * nvl;
+    VoxIter it;
+    it.init(blockIdx.x * nvl + vl, S, PH, PW);
+    for (int v = blockIdx.x * nvl + vl; v < M; v += U * S) {
+        Raw<T> rx[U], rg[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            ok[u] = false;
+            if (v + u * S < M) {
+                int d = it.pd - pad_lo, h = it.ph - pad_lo, w = it.pw - pad_lo;
+                const bool oob = (unsigned)d >= (unsigned)g.D || (unsigned)h >= (unsigned)g.H || (unsigned)w >= (unsigned)g.W;
+                if (!(oob && pad_mode == VG_PAD_ZERO)) {
+                    if (oob) { d = reflect1(d, g.D); h = reflect1(h, g.H); w = reflect1(w, g.W); }
+                    ok[u] = true;
+                    load_raw<T>(xn + (size_t)((d * g.H + h) * g.W + w) * C, rx[u]);
+                    load_raw<T>(dyn + (size_t)(v + u * S) * C, rg[u]);
+                }
+            }
+            it.next();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (ok[u]) {
+                float f[8], gy[8];
+                unpack_raw(rx[u], f);
+                unpack_raw(rg[u], gy);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float xr = relu_in ? fmaxf(f[k], 0.f) : f[k];
+                    float gg = gy[k] * act_grad(fmaf(xr, sc[k], sh[k]), act, a.slope);
+                    s1[k] += gg;
+                    s2[k] = fmaf(gg, xr - mu[k], s2[k]);
+                }
+            }
+    }
+    float* row = sm + ((size_t)vl * C + c8 * 8) * 2;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = c8 * 8 + k;
+        const float dr = (SP == 0 && a.drop) ? a.drop[n * C + c] : 1.f;
+        row[2 * k] = s1[k] * dr;
+        row[2 * k + 1] = s2[k] * dr * a.rstd[n * C + c];
+    }
+    __syncthreads();
+    float* out = partial + ((size_t)n * gridDim.x + blockIdx.x) * C * 2;
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+        float acc = 0.f;
+        for (int l = 0; l < nvl; l++) acc += sm[(size_t)l * C * 2 + i];
+        out[i] = acc;
+    }
+}
+
+// gy += every halo position of the padded gradient whose reflection is voxel (d,h,w)
+template <typename T>
+__device__ __noinline__ void shell_fold(const T* __restrict__ dyn, const Geo& g, int PH, int PW, int C, int d, int h, int w, float* gy) {
+    int dd[3], hh[3], ww[3], nd = 1, nh = 1, nw = 1;
+    dd[0] = d + 1; hh[0] = h + 1; ww[0] = w + 1;
+    if (d == 1) dd[nd++] = 0;
+    if (d == g.D - 2) dd[nd++] = g.D + 1;
+    if (h == 1) hh[nh++] = 0;
+    if (h == g.H - 2) hh[nh++] = g.H + 1;
+    if (w == 1) ww[nw++] = 0;
+    if (w == g.W - 2) ww[nw++] = g.W + 1;
+    for (int i0 = 0; i0 < nd; i0++)
+        for (int i1 = 0; i1 < nh; i1++)
+            for (int i2 = 0; i2 < nw; i2++) {
+                if (i0 + i1 + i2 == 0) continue;
+                float t[8];
+                load8<T>(dyn + (size_t)((dd[i0] * PH + hh[i1]) * PW + ww[i2]) * C, t);
+#pragma unroll
+                for (int k = 0; k < 8; k++) gy[k] += t[k];
+            }
+}
+
+// dx = gamma*rstd*(g - S1/V - xhat*S2/V) with g = fold(dy)*drop*act'(z); dres = fold(dy) (optional).
+// fold: REFLECT -> every padded position whose mirror is this voxel (1 for interior voxels, up to 8 on the
+// shell); ZERO -> the interior only.
+template <typename T, int SP>
+__global__ void __launch_bounds__(NT, 2) in_bwd_apply_sp_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g, BwdArgs a,
+                                                          const float* __restrict__ sums, T* __restrict__ dx,
+                                                          T* __restrict__ dres, int accumulate_dx) {
+    const int act = SP == 0 ? a.act : (SP == 1 ? VG_ACT_RELU : VG_ACT_NONE);
+    const int pad_lo = SP == 0 ? g.pad_lo : (SP == 1 ? 1 : 0), pad_hi = SP == 0 ? g.pad_hi : (SP == 1 ? 1 : 0);
+    const int pad_mode = SP == 0 ? pad_mode : VG_PAD_REFLECT;
+    const bool relu_in = SP == 0 && relu_in;
+    if (SP != 0) accumulate_dx = 0;
+    const int n = blockIdx.y, C = g.C, cg = C / 8;
+    const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
+    const int PH = g.H + pad_lo + pad_hi, PW = g.W + pad_lo + pad_hi, PD = g.D + pad_lo + pad_hi;
+    const int V = g.D * g.H * g.W;
+    const float invV = 1.f / (float)V;
+    const bool refl = pad_mode == VG_PAD_REFLECT && (pad_lo | pad_hi);
+    // dx = P*act'(z)*dy - Q - R*x with z = x*sc + sh:  sc = gamma*rstd, sh = beta - mean*sc, P = sc*drop,
+    // R = sc*rstd*S2/V, Q = sc*S1/V - R*mean  (five per-channel constants instead of seven: registers buy loads in flight)
+    float sc[8], sh[8], cP[8], cQ[8], cR[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = c8 * 8 + k, sci = n * C + c;
+        const float mu = a.mean[sci], rs = a.rstd[sci];
+        sc[k] = a.gamma[c] * rs;
+        sh[k] = a.beta[c] - mu * sc[k];
+        cP[k] = sc[k] * ((SP == 0 && a.drop) ? a.drop[sci] : 1.f);
+        cR[k] = sc[k] * rs * sums[2 * sci + 1] * invV;
+        cQ[k] = sc[k] * sums[2 * sci] * invV - cR[k] * mu;
+    }
+    const T* xn = x + (size_t)n * V * C + c8 * 8;
+    const T* dyn = dy + (size_t)n * PD * PH * PW * C + c8 * 8;
+    T* dxn = dx + (size_t)n * V * C + c8 * 8;
+    T* drn = (SP == 0 ? dres != nullptr : SP == 2) ? dres + (size_t)n * V * C + c8 * 8 : nullptr;
+    const int S = gridDim.x * nvl;
+    VoxIter it;
+    it.init(blockIdx.x * nvl + vl, S, g.H, g.W);
+    for (int v = blockIdx.x * nvl + vl; v < V; v += U * S) {
+        Raw<T> rx[U], rg[U];
+        int cd[U], ch[U], cw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            cd[u] = it.pd; ch[u] = it.ph; cw[u] = it.pw;
+            if (v + u * S < V) {
+                load_raw<T>(xn + (size_t)(v + u * S) * C, rx[u]);
+                load_raw<T>(dyn + (size_t)(((cd[u] + pad_lo) * PH + ch[u] + pad_lo) * PW + cw[u] + pad_lo) * C, rg[u]);
+            }
+            it.next();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int vv = v + u * S;
+            if (vv >= V) continue;
+            float f[8], gy[8];
+            unpack_raw(rx[u], f);
+            unpack_raw(rg[u], gy);
+            const int d = cd[u], h = ch[u], w = cw[u];
+            if (refl && (d == 1 || d == g.D - 2 || h == 1 || h == g.H - 2 || w == 1 || w == g.W - 2))
+                shell_fold<T>(dyn, g, PH, PW, C, d, h, w, gy);   // shell voxel: add the mirrored halo positions (rare, not inlined)
+            if (drn) store8<T>(drn + (size_t)vv * C, gy);
+            float o[8];
+            if (accumulate_dx) load8<T>(dxn + (size_t)vv * C, o);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float xr = relu_in ? fmaxf(f[k], 0.f) : f[k];
+                float gg = gy[k] * act_grad(fmaf(xr, sc[k], sh[k]), act, a.slope);
+                float val = fmaf(cP[k], gg, -fmaf(cR[k], xr, cQ[k]));
+                if (relu_in && !(f[k] > 0.f)) val = 0.f;   // gradient through the producer's ReLU
+                o[k] = accumulate_dx ? o[k] + val : val;
+            }
+            store8<T>(dxn + (size_t)vv * C, o);
+        }
+    }
+}
+
 inline int block_threads(int C) { int cg = C / 8; return (NT / cg) * cg; }
 // blocks per sample for a pass over `vox` voxels: ~8 waves of 148 SMs over the whole batch, at least U voxels per lane
 inline int pick_grid(long long vox, int N, int C) {
@@ -496,7 +765,16 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
     dim3 grid(pick_grid(M, d->N, d->C), d->N);
     const int nthr = block_threads(d->C);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == VG_BF16) {
+    int sp = 0;
+    if (dtype == VG_BF16 && !noise && !(d->noise_std > 0.f) && !drop && !g.relu_in) {
+        if (d->act == VG_ACT_RELU && d->pad_lo == 1 && d->pad_hi == 1 && d->pad_mode == VG_PAD_REFLECT && !residual) sp = 1;
+        else if (d->act == VG_ACT_NONE && d->pad_lo == 0 && d->pad_hi == 0 && residual) sp = 2;
+    }
+    if (sp == 1) {
+        in_apply_sp_kernel<bf16, 1><<<grid, nthr, 0, st>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, g, a); VG_LAUNCHED(1);
+    } else if (sp == 2) {
+        in_apply_sp_kernel<bf16, 2><<<grid, nthr, 0, st>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, g, a); VG_LAUNCHED(1);
+    } else if (dtype == VG_BF16) {
         in_apply_kernel<bf16><<<grid, nthr, 0, st>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, g, a); VG_LAUNCHED(1);
     } else if (dtype == VG_F32) {
         in_apply_kernel<float><<<grid, nthr, 0, st>>>((const float*)x, (const float*)residual, (float*)y, g, a); VG_LAUNCHED(1);
@@ -529,7 +807,22 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
     size_t smem = (size_t)(nthr / (d->C / 8)) * d->C * 2 * sizeof(float);
     dim3 grid2(pick_grid((long long)d->D * d->H * d->W, d->N, d->C), d->N);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == VG_BF16) {
+    int sp = 0;
+    if (dtype == VG_BF16 && !drop && !g.relu_in && !accumulate_dx) {
+        if (d->act == VG_ACT_RELU && d->pad_lo == 1 && d->pad_hi == 1 && d->pad_mode == VG_PAD_REFLECT && !dres) sp = 1;
+        else if (d->act == VG_ACT_NONE && d->pad_lo == 0 && d->pad_hi == 0 && dres) sp = 2;
+    }
+    if (sp == 1) {
+        in_bwd_partial_sp_kernel<bf16, 1><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
+        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta);
+        in_bwd_apply_sp_kernel<bf16, 1><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, 0);
+        VG_LAUNCHED(3);
+    } else if (sp == 2) {
+        in_bwd_partial_sp_kernel<bf16, 2><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
+        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta);
+        in_bwd_apply_sp_kernel<bf16, 2><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, 0);
+        VG_LAUNCHED(3);
+    } else if (dtype == VG_BF16) {
         in_bwd_partial_kernel<bf16><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial); VG_LAUNCHED(1);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta); VG_LAUNCHED(1);
         in_bwd_apply_kernel<bf16><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres,

@@ -62,9 +62,7 @@ __global__ void __launch_bounds__(NT) gather_pad_kernel(const bf16* __restrict__
         const int n = (int)(v / ((size_t)PW * PH * PD));
         int d = pd - pad, h = ph - pad, w = pw - pad;
         const bool oob = (unsigned)d >= (unsigned)D || (unsigned)h >= (unsigned)H || (unsigned)w >= (unsigned)W;
-        bf16x8 val;
-#pragma unroll
-        for (int k = 0; k < 4; k++) val.v[k] = __floats2bfloat162_rn(0.f, 0.f);
+        bf16x8 val = make_uint4(0u, 0u, 0u, 0u);
         if (!(oob && mode == VG_PAD_ZERO)) {
             if (oob) { d = reflect1(d, D); h = reflect1(h, H); w = reflect1(w, W); }
             if (c8 < cg0)
