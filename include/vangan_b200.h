@@ -153,6 +153,12 @@ int vg_minmax_normalize_bwd(const float* x, const float* nrm, const float* mm, c
 int vg_sqdiff_sum(const float* a, const float* b, float target, size_t n, double* acc, void* stream);
 int vg_lincomb(float* out, size_t n, int accumulate, float c0, const float* x1, float c1, const float* x2, float c2,
                const float* x3, float c3, void* stream);
+/* as vg_lincomb with the coefficients {c0,c1,c2,c3} read from device memory */
+int vg_lincomb_dev(float* out, size_t n, int accumulate, const float* coef4, const float* x1, const float* x2, const float* x3,
+                   void* stream);
+/* coef8 (device) <- the six coefficients of the clDice/Dice backward from the seven sums of vg_cldice_sums, times k:
+ * d skel_pred = coef[0] + coef[1]*y_true;  d y_pred = coef[2] + coef[3]*y_true + coef[4]*skel_true + coef[5]*d0 */
+int vg_cldice_coeffs(const double* acc7, float alpha, float k, float* coef8, void* stream);
 int vg_bce_sum(const float* y_true, const float* y_pred, size_t n, double* acc, void* stream);
 int vg_bce_bwd(const float* y_true, const float* y_pred, float coef, float* g, size_t n, int accumulate, void* stream);
 int vg_cldice_sums(const float* y_true, const float* y_pred, const float* skel_true, const float* skel_pred, size_t n,

@@ -70,6 +70,8 @@ SIGNATURES = {
     "vg_minmax_normalize_bwd": (_I, [_P, _P, _P, _P, _P, _I, _Z, _P, _I, _P]),
     "vg_sqdiff_sum": (_I, [_P, _P, _F, _Z, _P, _P]),
     "vg_lincomb": (_I, [_P, _Z, _I, _F, _P, _F, _P, _F, _P, _F, _P]),
+    "vg_lincomb_dev": (_I, [_P, _Z, _I, _P, _P, _P, _P, _P]),
+    "vg_cldice_coeffs": (_I, [_P, _F, _F, _P, _P]),
     "vg_bce_sum": (_I, [_P, _P, _Z, _P, _P]),
     "vg_bce_bwd": (_I, [_P, _P, _F, _P, _Z, _I, _P]),
     "vg_cldice_sums": (_I, [_P, _P, _P, _P, _Z, _P, _P]),

@@ -70,19 +70,15 @@ def cldice_terms(ctx, y_true, y_pred, iters, alpha, scale0):
         return ((1.0 - alpha) * dice + alpha * cl) * scale0
 
     def grad(a, scale):
-        s0, s1, s2, s3, s4, den, P, R, cl, dice = parts(a)
-        k = scale * scale0
-        dcl_dP = -2.0 * R * R / (P + R) ** 2
-        dcl_dR = -2.0 * P * P / (P + R) ** 2
-        kc, kd = k * alpha, k * (1.0 - alpha)
+        # the coefficients depend on the seven sums: computed on the device, so the backward needs no host round trip
+        coef = torch.empty(8, dtype=torch.float32, device=E.DEV)
+        call("vg_cldice_coeffs", ctx.ptr(s), float(alpha), float(scale * scale0), coef)
         # seed for the skeleton backward: d loss / d skel_pred = kc * dcl/dP * dP/dskel
         gsk = torch.empty_like(y_pred)
-        call("vg_lincomb", gsk, gsk.numel(), 0, -kc * dcl_dP * (s0 + smooth) / (s1 + smooth) ** 2, y_true,
-             kc * dcl_dP / (s1 + smooth), None, 0.0, None, 0.0)
+        call("vg_lincomb_dev", gsk, gsk.numel(), 0, coef, y_true, None, None)
         d0 = skel_bwd(gsk)
         gn = torch.empty_like(y_pred)
-        call("vg_lincomb", gn, gn.numel(), 0, kd * (2.0 * s4 + smooth) / den ** 2, y_true, -2.0 * kd / den, skel_t,
-             kc * dcl_dR / (s3 + smooth), d0, 1.0)
+        call("vg_lincomb_dev", gn, gn.numel(), 0, coef[2:], y_true, skel_t, d0)
         return gn
 
     return value, grad

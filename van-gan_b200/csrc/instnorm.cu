@@ -638,7 +638,6 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_sp_kernel(const T* __restr
     const int pad_lo = SP == 0 ? g.pad_lo : (SP == 1 ? 1 : 0), pad_hi = SP == 0 ? g.pad_hi : (SP == 1 ? 1 : 0);
     const int pad_mode = SP == 0 ? pad_mode : VG_PAD_REFLECT;
     const bool relu_in = SP == 0 && relu_in;
-    if (SP != 0) accumulate_dx = 0;
     const int n = blockIdx.y, C = g.C, cg = C / 8;
     const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
     const int PH = g.H + pad_lo + pad_hi, PW = g.W + pad_lo + pad_hi, PD = g.D + pad_lo + pad_hi;
@@ -808,19 +807,19 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
     dim3 grid2(pick_grid((long long)d->D * d->H * d->W, d->N, d->C), d->N);
     cudaStream_t st = (cudaStream_t)stream;
     int sp = 0;
-    if (dtype == VG_BF16 && !drop && !g.relu_in && !accumulate_dx) {
+    if (dtype == VG_BF16 && !drop && !g.relu_in) {
         if (d->act == VG_ACT_RELU && d->pad_lo == 1 && d->pad_hi == 1 && d->pad_mode == VG_PAD_REFLECT && !dres) sp = 1;
         else if (d->act == VG_ACT_NONE && d->pad_lo == 0 && d->pad_hi == 0 && dres) sp = 2;
     }
     if (sp == 1) {
         in_bwd_partial_sp_kernel<bf16, 1><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta);
-        in_bwd_apply_sp_kernel<bf16, 1><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, 0);
+        in_bwd_apply_sp_kernel<bf16, 1><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
         VG_LAUNCHED(3);
     } else if (sp == 2) {
         in_bwd_partial_sp_kernel<bf16, 2><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta);
-        in_bwd_apply_sp_kernel<bf16, 2><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, 0);
+        in_bwd_apply_sp_kernel<bf16, 2><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
         VG_LAUNCHED(3);
     } else if (dtype == VG_BF16) {
         in_bwd_partial_kernel<bf16><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial); VG_LAUNCHED(1);

@@ -362,6 +362,41 @@ int vg_sqdiff_sum(const float* a, const float* b, float target, size_t n, double
     return VG_OK;
 }
 
+// out = c[0] + c[1]*x1 + c[2]*x2 + c[3]*x3 with the four coefficients read from DEVICE memory (so a backward pass whose
+// coefficients depend on reduced sums needs no host round trip)
+__global__ void __launch_bounds__(NT) lincomb_dev_kernel(float* __restrict__ out, size_t n, int accumulate, const float* __restrict__ c,
+                                                         const float* __restrict__ x1, const float* __restrict__ x2,
+                                                         const float* __restrict__ x3) {
+    const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n; i += (size_t)gridDim.x * NT) {
+        float v = c0;
+        if (x1) v += c1 * x1[i];
+        if (x2) v += c2 * x2[i];
+        if (x3) v += c3 * x3[i];
+        out[i] = accumulate ? out[i] + v : v;
+    }
+}
+
+// coefficients of the clDice / Dice backward from the seven sums (clDice_func.py:83-119), k = upstream scale:
+//   d skel_pred : coef[0] + coef[1]*y_true        d y_pred : coef[2] + coef[3]*y_true + coef[4]*skel_true + coef[5]*d0
+__global__ void cldice_coeffs_kernel(const double* __restrict__ a, float alpha, float k, float* __restrict__ coef) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double smooth = 1.0;
+    const double s0 = a[0], s1 = a[1], s2 = a[2], s3 = a[3], s4 = a[4], s5 = a[5], s6 = a[6];
+    const double P = (s0 + smooth) / (s1 + smooth), R = (s2 + smooth) / (s3 + smooth);
+    const double dcl_dP = -2.0 * R * R / ((P + R) * (P + R)), dcl_dR = -2.0 * P * P / ((P + R) * (P + R));
+    const double den = s5 + s6 + smooth;
+    const double kc = (double)k * alpha, kd = (double)k * (1.0 - alpha);
+    coef[0] = (float)(-kc * dcl_dP * (s0 + smooth) / ((s1 + smooth) * (s1 + smooth)));
+    coef[1] = (float)(kc * dcl_dP / (s1 + smooth));
+    coef[2] = (float)(kd * (2.0 * s4 + smooth) / (den * den));
+    coef[3] = (float)(-2.0 * kd / den);
+    coef[4] = (float)(kc * dcl_dR / (s3 + smooth));
+    coef[5] = 1.0f;
+    coef[6] = 0.f;
+    coef[7] = 0.f;
+}
+
 int vg_lincomb(float* out, size_t n, int accumulate, float c0, const float* x1, float c1, const float* x2, float c2,
                const float* x3, float c3, void* stream) {
     VG_REQUIRE(out);
@@ -410,6 +445,21 @@ int vg_ssim_bwd(const float* t, const float* p, const float* mA, const float* mB
     int tx = vg_cdiv(W, SX), ty = vg_cdiv(H, SY), tz = vg_cdiv(D, SZ);
     ssim_bwd_kernel<<<tx * ty * tz * N, NT, 0, (cudaStream_t)stream>>>(t, p, mA, mB, mC, D, H, W, make_taps(), coef, gp,
                                                                       accumulate, tx, ty, tz); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_lincomb_dev(float* out, size_t n, int accumulate, const float* coef4, const float* x1, const float* x2, const float* x3,
+                   void* stream) {
+    VG_REQUIRE(out && coef4);
+    lincomb_dev_kernel<<<vg_grid_for(n, NT * 4, 4), NT, 0, (cudaStream_t)stream>>>(out, n, accumulate, coef4, x1, x2, x3); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_cldice_coeffs(const double* acc7, float alpha, float k, float* coef8, void* stream) {
+    VG_REQUIRE(acc7 && coef8);
+    cldice_coeffs_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc7, alpha, k, coef8); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }

@@ -289,13 +289,15 @@ class InstanceNorm:
 
         def bwd(in_needs, p_needs):
             dy = out.grad
-            dx = torch.empty_like(x.data)
+            # x already has a gradient from another consumer: add into it in the same pass (no extra accumulate kernel)
+            fuse = in_needs[0] and x.grad is not None and x.grad.dtype == x.data.dtype
+            dx = x.grad if fuse else torch.empty_like(x.data)
             need_res = residual is not None and in_needs[1]
             dres = torch.empty_like(x.data) if need_res else None
             ws2 = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
-            call("vg_instnorm_bwd", desc, dy, x.data, mean, rstd, self.gamma.w, self.beta.w, drop, dx, 0, dres,
+            call("vg_instnorm_bwd", desc, dy, x.data, mean, rstd, self.gamma.w, self.beta.w, drop, dx, 1 if fuse else 0, dres,
                  self.gamma.grad if p_needs else None, self.beta.grad if p_needs else None, ws2, ws_bytes)
-            if in_needs[0]:
+            if in_needs[0] and not fuse:
                 accumulate(x, dx)
             if need_res:
                 accumulate(residual, dres)
@@ -314,11 +316,12 @@ def upsample_concat(tape, lo, skip):
 
     def bwd(in_needs, p_needs):
         dlo = torch.empty_like(lo.data)
-        dsk = torch.empty_like(skip.data)
-        call("vg_upsample_concat_bwd", out.grad, dlo, dsk, 0, n, d, h, w, c0, c1)
+        fuse = in_needs[1] and skip.grad is not None     # add the skip gradient into the existing one in the same pass
+        dsk = skip.grad if fuse else torch.empty_like(skip.data)
+        call("vg_upsample_concat_bwd", out.grad, dlo, dsk, 1 if fuse else 0, n, d, h, w, c0, c1)
         if in_needs[0]:
             accumulate(lo, dlo)
-        if in_needs[1]:
+        if in_needs[1] and not fuse:
             accumulate(skip, dsk)
 
     tape.record([lo, skip], [out], [], bwd, "upcat")

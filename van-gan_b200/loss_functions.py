@@ -91,7 +91,9 @@ class Scalar:
         return float(self)
 
     def seeds(self, scale=1.0):
-        a = self.ctx.values()
+        """Launches the backward kernels of every term.  No host synchronisation: coefficients that depend on reduced sums
+        are computed on the device (vg_cldice_coeffs), so `a` (the host copy of the accumulators) is not needed."""
+        a = None
         out = []
         for f in self.grad_fns:
             out += f(a, scale)
