@@ -86,6 +86,8 @@ typedef struct {
     int pad_lo, pad_hi, pad_mode; /* padding written around the output (0/0 = none) */
     float noise_std;   /* >0 and noise==NULL: Philox noise generated in-kernel from `seed` */
     unsigned long long seed;
+    const unsigned long long* seed_dev; /* optional DEVICE pointer: per-step offset added to `seed` (lets a captured CUDA
+                                           graph draw fresh noise on every replay); NULL = none */
 } vg_instnorm_desc;
 
 size_t vg_instnorm_workspace_bytes(int N, int D, int H, int W, int C);
@@ -110,7 +112,10 @@ int vg_upsample_concat_bwd(const void* dcat, void* dlo, void* dskip, int accumul
                            int C1, void* stream);
 /* y[N,D+2,H+2,W+2] = reflect_pad(x) + noise  (fp32, one channel).  noise may be NULL (then noise_std/seed) */
 int vg_pad_noise(const float* x, float* y, int N, int D, int H, int W, const float* noise, float noise_std,
-                 unsigned long long seed, void* stream);
+                 unsigned long long seed, const unsigned long long* seed_dev, void* stream);
+/* SpatialDropout3D mask (discriminator.py:106, building_blocks.py:195): out[n] = (u >= rate) / (1 - rate), Philox keyed on
+ * seed + *seed_dev (seed_dev optional, device) */
+int vg_dropout_mask(float* out, int n, float rate, unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 /* dx[N,D,H,W] (+)= fold of dy[N,D+2,H+2,W+2] through the reflect padding */
 int vg_pad_fold(const float* dy, float* dx, int N, int D, int H, int W, int accumulate, void* stream);
 /* a += b  (dtype VG_BF16 or VG_F32) */
@@ -175,6 +180,10 @@ int vg_ssim_bwd(const float* t, const float* p, const float* mA, const float* mB
  * ------------------------------------------------------------------------------------------- */
 int vg_clip_adam_step(float* w, const float* g, float* m, float* v, const long long* seg_offsets, int nseg, long long total,
                       float lr_t, float beta1, float beta2, float eps, float clipnorm, double* norm_ws, void* stream);
+/* same, with the bias-corrected step size lr_t read from device memory (it changes every step; a captured graph cannot
+ * carry it as a launch argument) */
+int vg_clip_adam_step_dev(float* w, const float* g, float* m, float* v, const long long* seg_offsets, int nseg, long long total,
+                          const float* lr_t_dev, float beta1, float beta2, float eps, float clipnorm, double* norm_ws, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Sliding-window stitching (custom_callback.py:123,165-166,177-183,192,202).

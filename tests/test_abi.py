@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(names) >= 35
     for n in names:
         assert hasattr(lib, n), "missing export: %s" % n
-    assert lib.vg_abi_version() == 2
+    assert lib.vg_abi_version() == 3
 
 
 def test_ctypes_table_matches_header():
@@ -56,7 +56,7 @@ def test_no_cpu_fallback_paths():
 def test_descriptor_struct_layouts():
     from van_gan_b200 import _lib
     assert ctypes.sizeof(_lib.ConvDesc) == 13 * 4
-    assert ctypes.sizeof(_lib.InDesc) == 56     # 12 x 4 bytes + 8-byte seed (aligned)
+    assert ctypes.sizeof(_lib.InDesc) == 64     # 12 x 4 bytes + 8-byte seed (aligned) + 8-byte seed_dev pointer
     lib = _lib.lib()
     d = _lib.ConvDesc(1, 10, 10, 10, 16, 16, 3, 1, _lib.VG_BF16, _lib.VG_BF16, 0)
     assert lib.vg_conv3d_packed_bytes(d, 0) > 27 * 16 * 16 * 2

@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
 class InDesc(C.Structure):
     _fields_ = [("N", C.c_int), ("D", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("dtype", C.c_int),
                 ("act", C.c_int), ("slope", C.c_float), ("pad_lo", C.c_int), ("pad_hi", C.c_int), ("pad_mode", C.c_int),
-                ("noise_std", C.c_float), ("seed", C.c_ulonglong)]
+                ("noise_std", C.c_float), ("seed", C.c_ulonglong), ("seed_dev", C.c_void_p)]
 
 
 _P, _I, _F, _Z, _LL, _ULL = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong, C.c_ulonglong
@@ -58,7 +58,8 @@ SIGNATURES = {
     "vg_gather_pad_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_maxpool2_pad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_maxpool2_pad_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "vg_pad_noise": (_I, [_P, _P, _I, _I, _I, _I, _P, _F, _ULL, _P]),
+    "vg_pad_noise": (_I, [_P, _P, _I, _I, _I, _I, _P, _F, _ULL, _P, _P]),
+    "vg_dropout_mask": (_I, [_P, _I, _F, _ULL, _P, _P]),
     "vg_pad_fold": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "vg_accumulate": (_I, [_P, _P, _Z, _I, _P]),
     "vg_tanh_bwd": (_I, [_P, _P, _P, _Z, _P]),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "vg_ssim_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "vg_ssim_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P]),
     "vg_clip_adam_step": (_I, [_P, _P, _P, _P, _P, _I, _LL, _F, _F, _F, _F, _F, _P, _P]),
+    "vg_clip_adam_step_dev": (_I, [_P, _P, _P, _P, _P, _I, _LL, _P, _F, _F, _F, _F, _P, _P]),
     "vg_stitch_gather": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     "vg_stitch_accumulate": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_stitch_finalize": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

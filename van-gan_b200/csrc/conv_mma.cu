@@ -808,7 +808,7 @@ inline size_t rup256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" {
 
-int vg_abi_version(void) { return 2; }
+int vg_abi_version(void) { return 3; }
 
 size_t vg_conv3d_packed_bytes(const vg_conv3d_desc* d, int for_dgrad) {
     if (!desc_ok(d)) return 0;

@@ -154,6 +154,7 @@ struct ApplyArgs {
     float slope, noise_std;
     int act;
     unsigned long long seed;
+    const unsigned long long* seed_dev;   // optional per-step seed offset in device memory
 };
 
 template <typename T>
@@ -224,7 +225,8 @@ __global__ void __launch_bounds__(NT, 2) in_apply_kernel(const T* __restrict__ x
                     for (int k = 0; k < 8; k++) o[k] += np[k];
                 } else if (a.noise_std > 0.f) {
                     const unsigned long long i = ((unsigned long long)n * M + vv) * cg + c8;
-                    uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                    const unsigned long long sd_ = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
+                    uint2 key = make_uint2((uint32_t)sd_, (uint32_t)(sd_ >> 32));
                     uint4 r0 = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0u, 0x56414e47u), key);
                     uint4 r1 = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 1u, 0x56414e47u), key);
                     float2 n0 = box_muller(r0.x, r0.y), n1 = box_muller(r0.z, r0.w), n2 = box_muller(r1.x, r1.y),
@@ -513,7 +515,8 @@ __global__ void __launch_bounds__(NT, 2) in_apply_sp_kernel(const T* __restrict_
                     for (int k = 0; k < 8; k++) o[k] += np[k];
                 } else if (SP == 0 && a.noise_std > 0.f) {
                     const unsigned long long i = ((unsigned long long)n * M + vv) * cg + c8;
-                    uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                    const unsigned long long sd_ = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
+                    uint2 key = make_uint2((uint32_t)sd_, (uint32_t)(sd_ >> 32));
                     uint4 r0 = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0u, 0x56414e47u), key);
                     uint4 r1 = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 1u, 0x56414e47u), key);
                     float2 n0 = box_muller(r0.x, r0.y), n1 = box_muller(r0.z, r0.w), n2 = box_muller(r1.x, r1.y),
@@ -757,7 +760,7 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
         VG_REQUIRE(d->pad_lo == 1 && d->pad_hi == 1 && d->D >= 2 && d->H >= 2 && d->W >= 2);
     const int dtype = d->dtype & ~VG_IN_RELU_INPUT;
     Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode, (d->dtype & VG_IN_RELU_INPUT) ? 1 : 0};
-    ApplyArgs a{mean, rstd, gamma, beta, drop, noise, d->slope, d->noise_std, d->act, d->seed};
+    ApplyArgs a{mean, rstd, gamma, beta, drop, noise, d->slope, d->noise_std, d->act, d->seed, d->seed_dev};
     const int pp = d->pad_lo + d->pad_hi;
     const long long M = (long long)(d->D + pp) * (d->H + pp) * (d->W + pp);
     VG_REQUIRE(M * d->C < (1LL << 31));

@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(NT) upsample_concat_bwd_skip_kernel(const bf16
 
 __global__ void __launch_bounds__(NT) pad_noise_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int D, int H,
                                                        int W, const float* __restrict__ noise, float noise_std,
-                                                       unsigned long long seed) {
+                                                       unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev) seed += *seed_dev;   // per-step offset kept in device memory (CUDA-graph replays draw fresh noise)
     const int PD = D + 2, PH = H + 2, PW = W + 2;
     size_t total = (size_t)N * PD * PH * PW;
     for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
@@ -178,7 +179,8 @@ __global__ void __launch_bounds__(NT) seg_sqnorm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(NT) clip_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
                                                        float* __restrict__ v, const long long* __restrict__ off, int nseg,
                                                        const double* __restrict__ norms, float lr_t, float b1, float b2,
-                                                       float eps, float clip, long long total) {
+                                                       float eps, float clip, long long total, const float* __restrict__ lr_t_dev) {
+    if (lr_t_dev) lr_t = *lr_t_dev;    // bias-corrected step size kept in device memory (changes every step under graph replay)
     for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
         int lo = find_seg(off, nseg, i);
         float nrm = (float)sqrt(norms[lo]);
@@ -190,6 +192,17 @@ __global__ void __launch_bounds__(NT) clip_adam_kernel(float* __restrict__ w, co
         v[i] = vi;
         w[i] -= lr_t * mi / (sqrtf(vi) + eps);
     }
+}
+
+// SpatialDropout3D mask: out[i] = (u_i >= rate) / (1 - rate), u_i from Philox keyed on seed (+ *seed_dev)
+__global__ void dropout_mask_kernel(float* __restrict__ out, int n, float rate, unsigned long long seed,
+                                    const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev) seed += *seed_dev;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 r = philox4x32(make_uint4((uint32_t)i, 0u, 3u, 0x56414e47u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u = r.x * 2.3283064365386963e-10f;
+    out[i] = u >= rate ? 1.f / (1.f - rate) : 0.f;
 }
 
 // ------------------------------------------------------------------ stitching
@@ -291,10 +304,10 @@ int vg_upsample_concat_bwd(const void* dcat, void* dlo, void* dskip, int accumul
 }
 
 int vg_pad_noise(const float* x, float* y, int N, int D, int H, int W, const float* noise, float noise_std,
-                 unsigned long long seed, void* stream) {
+                 unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
     VG_REQUIRE(x && y && D >= 2 && H >= 2 && W >= 2);
     size_t total = (size_t)N * (D + 2) * (H + 2) * (W + 2);
-    pad_noise_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(x, y, N, D, H, W, noise, noise_std, seed); VG_LAUNCHED(1);
+    pad_noise_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(x, y, N, D, H, W, noise, noise_std, seed, seed_dev); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
@@ -331,14 +344,33 @@ int vg_tanh_bwd(const float* dy, const float* y, float* out, size_t n, void* str
 }
 
 // norm_ws: nseg doubles (zeroed here)
-int vg_clip_adam_step(float* w, const float* g, float* m, float* v, const long long* seg_offsets, int nseg, long long total,
-                      float lr_t, float beta1, float beta2, float eps, float clipnorm, double* norm_ws, void* stream) {
+static int clip_adam_impl(float* w, const float* g, float* m, float* v, const long long* seg_offsets, int nseg, long long total,
+                          float lr_t, const float* lr_t_dev, float beta1, float beta2, float eps, float clipnorm, double* norm_ws,
+                          void* stream) {
     VG_REQUIRE(w && g && m && v && seg_offsets && nseg > 0 && total > 0 && norm_ws);
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(norm_ws, 0, (size_t)nseg * sizeof(double), st) != cudaSuccess) return VG_ERR_CUDA;
     seg_sqnorm_kernel<<<vg_grid_for(total / 4 + 1, NT, 8), NT, 0, st>>>(g, seg_offsets, nseg, norm_ws, total); VG_LAUNCHED(1);
     clip_adam_kernel<<<vg_grid_for(total, NT, 16), NT, 0, st>>>(w, g, m, v, seg_offsets, nseg, norm_ws, lr_t, beta1, beta2, eps,
-                                                               clipnorm, total); VG_LAUNCHED(1);
+                                                               clipnorm, total, lr_t_dev); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_clip_adam_step(float* w, const float* g, float* m, float* v, const long long* seg_offsets, int nseg, long long total,
+                      float lr_t, float beta1, float beta2, float eps, float clipnorm, double* norm_ws, void* stream) {
+    return clip_adam_impl(w, g, m, v, seg_offsets, nseg, total, lr_t, nullptr, beta1, beta2, eps, clipnorm, norm_ws, stream);
+}
+
+int vg_clip_adam_step_dev(float* w, const float* g, float* m, float* v, const long long* seg_offsets, int nseg, long long total,
+                          const float* lr_t_dev, float beta1, float beta2, float eps, float clipnorm, double* norm_ws, void* stream) {
+    VG_REQUIRE(lr_t_dev);
+    return clip_adam_impl(w, g, m, v, seg_offsets, nseg, total, 0.f, lr_t_dev, beta1, beta2, eps, clipnorm, norm_ws, stream);
+}
+
+int vg_dropout_mask(float* out, int n, float rate, unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
+    VG_REQUIRE(out && n > 0 && rate >= 0.f && rate < 1.f);
+    dropout_mask_kernel<<<vg_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(out, n, rate, seed, seed_dev); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }

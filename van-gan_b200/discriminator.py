@@ -44,9 +44,9 @@ class DiscriminatorModel(E.Network):
         if seed is not None:
             self.load(E.default_init({n: p.shape for n, p in self.params.items()}, seed))
 
-    def forward(self, tape, x, training=True, noise=None, masks=None, seed=0):
+    def forward(self, tape, x, training=True, noise=None, masks=None, seed=0, seed_dev=None):
         """x: Var (N,D,H,W,1) fp32.  noise / masks: explicit tensors (parity mode; oracle layout) or None
-        -> in-kernel Philox noise and torch-generated channel masks keyed on `seed`."""
+        -> in-kernel Philox noise and channel masks keyed on `seed` (+ the per-step offset *seed_dev, a device scalar)."""
         n = x.shape[0]
         std = self.noise_std if training else 0.0
 
@@ -58,24 +58,21 @@ class DiscriminatorModel(E.Network):
                 return None
             if masks is not None:
                 return masks[i].reshape(n * c).contiguous()
-            g = torch.Generator(device=E.DEV)
-            g.manual_seed(seed * 7 + i)
-            keep = torch.rand(n * c, device=E.DEV, generator=g) >= self.rate
-            return keep.to(torch.float32) / (1.0 - self.rate)
+            return E.dropout_mask(n * c, self.rate, seed * 16 + 8 + i, seed_dev)
 
-        h = E.pad_noise(tape, x, noise=nz(0), noise_std=std, seed=seed * 16 + 0)
+        h = E.pad_noise(tape, x, noise=nz(0), noise_std=std, seed=seed * 16 + 0, seed_dev=seed_dev)
         h = self.conv0(tape, h)
-        h = self.norm0(tape, h, act=ACT_LEAKY, pad=(1, 1, PAD_REFLECT), noise=nz(1), noise_std=std, seed=seed * 16 + 1)
+        h = self.norm0(tape, h, act=ACT_LEAKY, pad=(1, 1, PAD_REFLECT), noise=nz(1), noise_std=std, seed=seed * 16 + 1, seed_dev=seed_dev)
         h = self.conv1(tape, h)
         h = self.norm1(tape, h, act=ACT_LEAKY, pad=(1, 1, PAD_REFLECT), drop=mask(0, self.norm1.c), noise=nz(2),
-                       noise_std=std, seed=seed * 16 + 2)
+                       noise_std=std, seed=seed * 16 + 2, seed_dev=seed_dev)
         h = self.conv2(tape, h)
         # next conv is k4 s1 'same': TF pads 1 before / 2 after with zeros, AFTER the noise layer
         h = self.norm2(tape, h, act=ACT_LEAKY, pad=(1, 2, PAD_ZERO), drop=mask(1, self.norm2.c), noise=nz(3),
-                       noise_std=std, seed=seed * 16 + 3)
+                       noise_std=std, seed=seed * 16 + 3, seed_dev=seed_dev)
         h = self.conv3(tape, h)
         h = self.norm3(tape, h, act=ACT_LEAKY, pad=(1, 1, PAD_ZERO), drop=mask(2, self.norm3.c), noise=nz(4),
-                       noise_std=std, seed=seed * 16 + 4)
+                       noise_std=std, seed=seed * 16 + 4, seed_dev=seed_dev)
         return self.convo(tape, h)
 
     def __call__(self, x, training=False):

@@ -167,13 +167,22 @@ class Network:
     def zero_grad(self):
         self.g.zero_()
 
-    def adam_step(self, lr=2e-4, beta_1=0.5, beta_2=0.9, eps=1e-7, clipnorm=100.0):
-        """Keras OptimizerV2 Adam: per-variable clip_by_norm, lr_t = lr*sqrt(1-b2^t)/(1-b1^t)."""
-        self.step_count += 1
-        t = self.step_count
-        lr_t = lr * math.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t)
-        call("vg_clip_adam_step", self.w, self.g, self.m, self.v, self.seg, len(self.params), self.total, lr_t, beta_1,
-             beta_2, eps, clipnorm, self.norm_ws)
+    @staticmethod
+    def lr_t(t, lr=2e-4, beta_1=0.5, beta_2=0.9):
+        """Keras OptimizerV2 Adam step size at iteration t: lr*sqrt(1-b2^t)/(1-b1^t)."""
+        return lr * math.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t)
+
+    def adam_step(self, lr=2e-4, beta_1=0.5, beta_2=0.9, eps=1e-7, clipnorm=100.0, lr_t_dev=None):
+        """Keras OptimizerV2 Adam: per-variable clip_by_norm, lr_t = lr*sqrt(1-b2^t)/(1-b1^t).
+        lr_t_dev: optional 1-element device tensor already holding lr_t for THIS step (graph-replay mode: the caller owns
+        the step counter and uploads the value before every replay)."""
+        if lr_t_dev is not None:
+            call("vg_clip_adam_step_dev", self.w, self.g, self.m, self.v, self.seg, len(self.params), self.total, lr_t_dev, beta_1,
+                 beta_2, eps, clipnorm, self.norm_ws)
+        else:
+            self.step_count += 1
+            call("vg_clip_adam_step", self.w, self.g, self.m, self.v, self.seg, len(self.params), self.total,
+                 self.lr_t(self.step_count, lr, beta_1, beta_2), beta_1, beta_2, eps, clipnorm, self.norm_ws)
         self.repack()
 
 
@@ -268,7 +277,7 @@ class InstanceNorm:
         self.c = c
 
     def __call__(self, tape, x, act=ACT_NONE, slope=0.2, residual=None, pad=(0, 0, PAD_ZERO), drop=None, noise=None,
-                 noise_std=0.0, seed=0, relu_input=False):
+                 noise_std=0.0, seed=0, relu_input=False, seed_dev=None):
         """relu_input: x is the PRE-activation output of a Conv3D(activation='relu') (vnet_model.py:118-126); the ReLU is
         applied on load and its gradient mask on dx, so the convolution kernels never see the activation."""
         n, d, h, w, c = x.shape
@@ -279,7 +288,8 @@ class InstanceNorm:
         mean = torch.empty(n * c, dtype=torch.float32, device=DEV)
         rstd = torch.empty(n * c, dtype=torch.float32, device=DEV)
         call("vg_instnorm_stats", x.data, dt, n, d, h, w, c, mean, rstd, ws, ws_bytes)
-        desc = InDesc(n, d, h, w, c, dt, act, slope, pad[0], pad[1], pad[2], noise_std if noise is None else 0.0, seed)
+        desc = InDesc(n, d, h, w, c, dt, act, slope, pad[0], pad[1], pad[2], noise_std if noise is None else 0.0, seed,
+                      seed_dev.data_ptr() if seed_dev is not None else None)
         pp = pad[0] + pad[1]
         y = torch.empty((n, d + pp, h + pp, w + pp, c), dtype=x.data.dtype, device=DEV)
         call("vg_instnorm_apply", desc, x.data, residual.data if residual is not None else None, y, mean, rstd,
@@ -328,12 +338,12 @@ def upsample_concat(tape, lo, skip):
     return out
 
 
-def pad_noise(tape, x, noise=None, noise_std=0.0, seed=0):
+def pad_noise(tape, x, noise=None, noise_std=0.0, seed=0, seed_dev=None):
     """ReflectionPadding3D + GaussianNoise on a single-channel fp32 volume (discriminator.py:50-52)."""
     n, d, h, w, c = x.shape
     assert c == 1 and x.data.dtype == torch.float32
     y = torch.empty((n, d + 2, h + 2, w + 2, 1), dtype=torch.float32, device=DEV)
-    call("vg_pad_noise", x.data, y, n, d, h, w, noise, noise_std if noise is None else 0.0, seed)
+    call("vg_pad_noise", x.data, y, n, d, h, w, noise, noise_std if noise is None else 0.0, seed, seed_dev)
     out = Var(y)
 
     def bwd(in_needs, p_needs):
@@ -390,4 +400,11 @@ def maxpool_pad(tape, x, pad=0, mode=PAD_ZERO):
             accumulate(x, dx)
 
     tape.record([x], [out], [], bwd, "maxpool_pad")
+    return out
+
+
+def dropout_mask(n, rate, seed, seed_dev=None):
+    """SpatialDropout3D keep-mask / (1 - rate) for n (sample, channel) pairs, drawn on the device (Philox)."""
+    out = torch.empty(n, dtype=torch.float32, device=DEV)
+    call("vg_dropout_mask", out, n, float(rate), int(seed), seed_dev)
     return out

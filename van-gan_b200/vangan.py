@@ -6,6 +6,8 @@ Kept from the reference: the constructor signature, the attribute names the loss
 updates (vangan.py:426-438).  Only the LSGAN / resUnet configuration that main.py runs
 (main.py:196-200) is built; the other branches raise.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -86,6 +88,18 @@ class VanGan:
             # tf.keras.optimizers.Adam(2e-4, beta_1=0.5, beta_2=0.9, clipnorm=100) x4 (vangan.py:220-235)
             self.opt = dict(lr=2e-4, beta_1=0.5, beta_2=0.9, eps=1e-7, clipnorm=100.0)
         self.networks = {"gen_IS": self.gen_IS, "gen_SI": self.gen_SI, "disc_I": self.disc_I, "disc_S": self.disc_S}
+        # per-step state that lives in DEVICE memory so that a captured CUDA graph of the whole step can be replayed:
+        # the RNG seed offset of the discriminators' GaussianNoise / SpatialDropout3D and the four Adam step sizes lr_t
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=E.DEV)
+        self._lr_dev = torch.zeros(4, dtype=torch.float32, device=E.DEV)
+        self._h_seed = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._h_lr = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.seed = seed
+        # CUDA graph of one full train step (captured on the third eligible call; VG_GRAPH=0 disables)
+        self.use_graph = os.environ.get("VG_GRAPH", "1") != "0" and not isinstance(self.gen_IS, VNetModel)
+        self._graph = None
+        self._eager_steps = 0
+        self.launches_per_replay = 0
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
@@ -105,7 +119,8 @@ class VanGan:
 
     def _disc(self, net, tape, x, training, rand, key, app):
         noise, masks = (None, None) if rand is None else rand[key]
-        return net.forward(tape, x, training=training, noise=noise, masks=masks, seed=self.step * 4 + app)
+        # the seed is a per-application constant; the per-step part is the device-resident offset self._seed_dev
+        return net.forward(tape, x, training=training, noise=noise, masks=masks, seed=app, seed_dev=self._seed_dev)
 
     # ------------------------------------------------------------------ reference API
     def compute_losses(self, real_I, real_S, result, training=True, rand=None, tape=None):
@@ -146,32 +161,105 @@ class VanGan:
                          disc_fake_S=disc_fake_S, disc_real_I=disc_real_I, disc_fake_I=disc_fake_I)
         return result, total_loss_I, total_loss_S, disc_I_loss, disc_S_loss, fake_I, fake_S
 
-    def train_step(self, real_I, real_S, rand=None, apply=True):
-        """vangan.py:380-440: persistent tape around compute_losses, then one minimize per network
-        (gen_IS on total_loss_I, gen_SI on total_loss_S, disc_I, disc_S).  Each network's gradient
-        all-reduce (MirroredStrategy's, hidden inside `minimize`) is launched as soon as its sweep ends."""
+    def _plan(self, total_I, total_S, dI, dS):
+        return ((self.gen_IS, total_I), (self.gen_SI, total_S), (self.disc_I, dI), (self.disc_S, dS))
+
+    def _upload_step_state(self):
+        """Seed offset and the four Adam step sizes of THIS step -> device (async copies on the current stream)."""
+        self._h_seed[0] = (self.seed * 1000003 + self.step) * 64
+        for i, net in enumerate((self.gen_IS, self.gen_SI, self.disc_I, self.disc_S)):
+            self._h_lr[i] = E.Network.lr_t(net.step_count + 1, self.opt["lr"], self.opt["beta_1"], self.opt["beta_2"])
+        self._seed_dev.copy_(self._h_seed, non_blocking=True)
+        self._lr_dev.copy_(self._h_lr, non_blocking=True)
+
+    def _step_body(self, real_I, real_S, rand, apply):
+        """compute_losses + the four minimize calls (vangan.py:394-438), enqueue only: no host synchronisation inside."""
         result = {}
         result, total_I, total_S, dI, dS, _fI, _fS = self.compute_losses(real_I, real_S, result, training=True, rand=rand)
-        plan = ((self.gen_IS, total_I), (self.gen_SI, total_S), (self.disc_I, dI), (self.disc_S, dS))
+        plan = self._plan(total_I, total_S, dI, dS)
         handles = []
         for net, loss in plan:
             net.zero_grad()
             self.tape.backward(loss.seeds(), net.trainable_variables)
             handles.append(self.strategy.all_reduce_async(net.g))
+        for i, ((net, _), h) in enumerate(zip(plan, handles)):
+            if h is not None:
+                h.wait()
+            if apply:
+                net.adam_step(lr_t_dev=self._lr_dev[i:i + 1], beta_1=self.opt["beta_1"], beta_2=self.opt["beta_2"],
+                              eps=self.opt["eps"], clipnorm=self.opt["clipnorm"])
+        return result
+
+    def _finish_step(self, result, ctx, apply=True):
         if apply:
-            for (net, _), h in zip(plan, handles):
-                if h is not None:
-                    h.wait()
-                net.adam_step(**self.opt)
-        else:
-            for h in handles:
-                if h is not None:
-                    h.wait()
+            for net in self.networks.values():
+                net.step_count += 1
         self.step += 1
-        vals = self.loss_ctx.values()
-        out = {k: float(v.value_fn(vals)) for k, v in result.items()}
+        vals = ctx.values()            # the one device->host read of the step
+        return {k: float(v.value_fn(vals)) for k, v in result.items()}
+
+    def train_step(self, real_I, real_S, rand=None, apply=True):
+        """vangan.py:380-440: persistent tape around compute_losses, then one minimize per network
+        (gen_IS on total_loss_I, gen_SI on total_loss_S, disc_I, disc_S).  Each network's gradient
+        all-reduce (MirroredStrategy's, hidden inside `minimize`) is launched as soon as its sweep ends.
+
+        The whole step is enqueue-only (no host sync before the final read of the ten loss sums), so after two eager
+        steps it is captured ONCE into a CUDA graph and replayed: ~2 000 kernel launches become one graph launch, which is
+        what keeps a GPU busy when the per-GPU batch is 1 (8-GPU strong scaling).  `rand` (explicit noise tensors, parity
+        tests) and `apply=False` always run eagerly."""
+        graphable = self.use_graph and rand is None and apply
+        if graphable and self._graph is not None and self._graph["key"] == self._shape_key(real_I, real_S):
+            return self._replay(real_I, real_S)
+        if graphable and self._eager_steps >= 2 and self._graph is None:
+            try:
+                self._capture(real_I, real_S)
+                return self._replay(real_I, real_S)
+            except Exception as e:      # capture is an optimisation: fall back to eager launches, loudly
+                import warnings
+                warnings.warn("CUDA graph capture of train_step failed (%s: %s); running eagerly" % (type(e).__name__, e))
+                self.use_graph = False
+                self._graph = None
+                torch.cuda.synchronize()
+        self._upload_step_state()
+        result = self._step_body(real_I, real_S, rand, apply)
+        out = self._finish_step(result, self.loss_ctx, apply)
+        self._eager_steps += 1
         self._release()
         return out
+
+    @staticmethod
+    def _shape_key(real_I, real_S):
+        a = real_I.data if isinstance(real_I, E.Var) else real_I
+        b = real_S.data if isinstance(real_S, E.Var) else real_S
+        return (tuple(a.shape), tuple(b.shape))
+
+    def _capture(self, real_I, real_S):
+        from . import _lib
+        key = self._shape_key(real_I, real_S)
+        gI = torch.empty(key[0], dtype=torch.float32, device=E.DEV)
+        gS = torch.empty(key[1], dtype=torch.float32, device=E.DEV)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        l0 = _lib.lib().vg_launch_count()
+        with torch.cuda.graph(graph):
+            result = self._step_body(E.Var(gI), E.Var(gS), None, True)
+        self.launches_per_replay = int(_lib.lib().vg_launch_count() - l0)
+        ctx = self.loss_ctx
+        # the graph's private pool keeps every buffer the capture touched; the Python-side tape is not needed again
+        self.tape.clear()
+        self.tape, self.last = None, None
+        self._graph = dict(key=key, graph=graph, I=gI, S=gS, result=result, ctx=ctx)
+
+    def _replay(self, real_I, real_S):
+        g = self._graph
+        a = real_I.data if isinstance(real_I, E.Var) else torch.as_tensor(real_I)
+        b = real_S.data if isinstance(real_S, E.Var) else torch.as_tensor(real_S)
+        g["I"].copy_(a, non_blocking=True)        # H2D (pinned host batch) or D2D
+        g["S"].copy_(b, non_blocking=True)
+        self._upload_step_state()
+        g["graph"].replay()
+        g["ctx"].host = None
+        return self._finish_step(g["result"], g["ctx"], True)
 
     def _release(self):
         """Drop the step's tape, loss scratch and (unless keep_last) the generated volumes."""
