@@ -172,8 +172,8 @@ class VanGan:
         self._seed_dev.copy_(self._h_seed, non_blocking=True)
         self._lr_dev.copy_(self._h_lr, non_blocking=True)
 
-    def _step_body(self, real_I, real_S, rand, apply):
-        """compute_losses + the four minimize calls (vangan.py:394-438), enqueue only: no host synchronisation inside."""
+    def _body_losses_and_sweeps(self, real_I, real_S, rand, overlap_allreduce):
+        """compute_losses + the four backward sweeps (vangan.py:394-438), enqueue only.  Returns (result, plan, handles)."""
         result = {}
         result, total_I, total_S, dI, dS, _fI, _fS = self.compute_losses(real_I, real_S, result, training=True, rand=rand)
         plan = self._plan(total_I, total_S, dI, dS)
@@ -181,13 +181,23 @@ class VanGan:
         for net, loss in plan:
             net.zero_grad()
             self.tape.backward(loss.seeds(), net.trainable_variables)
-            handles.append(self.strategy.all_reduce_async(net.g))
-        for i, ((net, _), h) in enumerate(zip(plan, handles)):
+            # MirroredStrategy's gradient all-reduce: launched as soon as this network's sweep ends, overlapping the next sweep
+            handles.append(self.strategy.all_reduce_async(net.g) if overlap_allreduce else None)
+        return result, plan, handles
+
+    def _body_adam(self):
+        for i, net in enumerate((self.gen_IS, self.gen_SI, self.disc_I, self.disc_S)):
+            net.adam_step(lr_t_dev=self._lr_dev[i:i + 1], beta_1=self.opt["beta_1"], beta_2=self.opt["beta_2"],
+                          eps=self.opt["eps"], clipnorm=self.opt["clipnorm"])
+
+    def _step_body(self, real_I, real_S, rand, apply):
+        """One eager step: no host synchronisation inside."""
+        result, plan, handles = self._body_losses_and_sweeps(real_I, real_S, rand, True)
+        for h in handles:
             if h is not None:
                 h.wait()
-            if apply:
-                net.adam_step(lr_t_dev=self._lr_dev[i:i + 1], beta_1=self.opt["beta_1"], beta_2=self.opt["beta_2"],
-                              eps=self.opt["eps"], clipnorm=self.opt["clipnorm"])
+        if apply:
+            self._body_adam()
         return result
 
     def _finish_step(self, result, ctx, apply=True):
@@ -234,21 +244,25 @@ class VanGan:
         return (tuple(a.shape), tuple(b.shape))
 
     def _capture(self, real_I, real_S):
+        """Two graphs: (1) losses + four backward sweeps, (2) clip+Adam + operand repack.  The gradient all-reduce (world > 1)
+        runs between the two replays as ordinary NCCL calls: collectives are kept out of the capture on purpose."""
         from . import _lib
         key = self._shape_key(real_I, real_S)
         gI = torch.empty(key[0], dtype=torch.float32, device=E.DEV)
         gS = torch.empty(key[1], dtype=torch.float32, device=E.DEV)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         l0 = _lib.lib().vg_launch_count()
-        with torch.cuda.graph(graph):
-            result = self._step_body(E.Var(gI), E.Var(gS), None, True)
+        with torch.cuda.graph(g1, capture_error_mode="thread_local"):
+            result, _plan, _h = self._body_losses_and_sweeps(E.Var(gI), E.Var(gS), None, False)
+        with torch.cuda.graph(g2, pool=g1.pool(), capture_error_mode="thread_local"):
+            self._body_adam()
         self.launches_per_replay = int(_lib.lib().vg_launch_count() - l0)
         ctx = self.loss_ctx
-        # the graph's private pool keeps every buffer the capture touched; the Python-side tape is not needed again
+        # the graphs' private pool keeps every buffer the capture touched; the Python-side tape is not needed again
         self.tape.clear()
         self.tape, self.last = None, None
-        self._graph = dict(key=key, graph=graph, I=gI, S=gS, result=result, ctx=ctx)
+        self._graph = dict(key=key, g1=g1, g2=g2, I=gI, S=gS, result=result, ctx=ctx)
 
     def _replay(self, real_I, real_S):
         g = self._graph
@@ -257,7 +271,11 @@ class VanGan:
         g["I"].copy_(a, non_blocking=True)        # H2D (pinned host batch) or D2D
         g["S"].copy_(b, non_blocking=True)
         self._upload_step_state()
-        g["graph"].replay()
+        g["g1"].replay()
+        if self.strategy.num_replicas_in_sync > 1:
+            for net in (self.gen_IS, self.gen_SI, self.disc_I, self.disc_S):
+                self.strategy.reduce("SUM", net.g)
+        g["g2"].replay()
         g["ctx"].host = None
         return self._finish_step(g["result"], g["ctx"], True)
 
