@@ -23,6 +23,6 @@ tot = e0.elapsed_time(e1)
 summ = prof.summary()
 acc = sum(v["ms"] for v in summ.values())
 print("step %.1f ms; sum of ABI calls %.1f ms" % (tot, acc))
-for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:70]:
+for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:int(os.environ.get('VG_TOP', '70'))]:
     tf = (" %7.1f TFLOP/s" % (v["work"] / v["ms"] / 1e9)) if v["work"] else ""
     print("%-58s n=%3d %8.3f ms %5.1f%%%s" % (k, v["calls"], v["ms"], 100 * v["ms"] / tot, tf))

@@ -170,6 +170,9 @@ CONV_CASES = [
     (64, 128, 4, 2, (10, 10, 18), 1), (128, 256, 4, 2, (10, 10, 10), 1), (256, 512, 4, 1, (7, 7, 7), 1),
     (1, 16, 3, 1, (10, 10, 12), 2), (1, 64, 4, 2, (18, 18, 18), 1), (1, 16, 1, 1, (8, 8, 8), 1),
     (512, 1, 3, 1, (6, 6, 6), 2), (16, 1, 1, 1, (8, 8, 9), 2),
+    # streaming kernels of conv_small.cu: ragged voxel counts, every template instance, odd extents for the fused-parity dgrad
+    (48, 16, 1, 1, (5, 7, 9), 1), (96, 32, 1, 1, (8, 8, 10), 1), (32, 64, 1, 2, (8, 9, 12), 1), (16, 16, 1, 1, (7, 5, 3), 2),
+    (32, 32, 1, 1, (6, 6, 7), 1), (1, 64, 4, 2, (19, 21, 40), 2), (512, 1, 3, 1, (5, 6, 9), 1), (16, 1, 1, 1, (33, 5, 7), 1),
 ]
 
 

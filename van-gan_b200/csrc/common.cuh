@@ -149,3 +149,14 @@ int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, 
 // tensor-core (tcgen05) weight-gradient path, wgrad_tc.cu
 int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, int XH, int XW, int Cx, int OD, int OH, int OW, int Cy,
                     int K, int stride, cudaStream_t stream);
+// HBM-bound shapes (1x1x1 kernels, single-channel outputs, single-channel-input stride-2 dgrad), conv_small.cu
+int vg_small_k1_fwd(const bf16* x, const bf16* wp, const float* bias, bf16* y, long long nvox, int Cin, int Cout, cudaStream_t st);
+int vg_small_k1_wgrad(const bf16* x, const bf16* dy, float* dw, int N, int ID, int IH, int IW, int Cin, int OD, int OH, int OW, int Cout,
+                      int stride, cudaStream_t st);
+int vg_small_cout1_k1_fwd(const bf16* x, const bf16* wp, const float* bias, float* y, size_t nvox, int Cin, int act, cudaStream_t st);
+int vg_small_cout1_k1_dgrad(const float* dy, const float* w, bf16* dx, size_t nvox, int Cin, cudaStream_t st);
+int vg_small_cout1_k1_wgrad(const bf16* x, const float* dy, float* dw, size_t nvox, int Cin, cudaStream_t st);
+int vg_small_cout1_wgrad(const bf16* x, const float* dy, float* dw, int N, int ID, int IH, int IW, int OD, int OH, int OW, int Cin, int K,
+                         cudaStream_t st);
+int vg_small_cin1_dgrad_s2(const bf16* dy, const bf16* wd, float* dx, int N, int ID, int IH, int IW, int OD, int OH, int OW, int Cout, int K,
+                           cudaStream_t st);

@@ -659,9 +659,10 @@ __global__ void __launch_bounds__(256) cout1_dgrad_kernel(const float* __restric
                     int ow = pw - kw;
                     if ((unsigned)ow >= (unsigned)OW) continue;
                     float g = __ldg(dy + (((size_t)n * OD + od) * OH + oh) * OW + ow);
-                    const float* wr = w + (size_t)((kd * K + kh) * K + kw) * Cin + c8 * 8;
+                    float wv[8];
+                    load8<float>(w + (size_t)((kd * K + kh) * K + kw) * Cin + c8 * 8, wv);   // two 128-bit loads
 #pragma unroll
-                    for (int k = 0; k < 8; k++) a[k] = fmaf(g, __ldg(wr + k), a[k]);
+                    for (int k = 0; k < 8; k++) a[k] = fmaf(g, wv[k], a[k]);
                 }
             }
         }
@@ -778,6 +779,15 @@ inline bool tc_wgrad_enabled() {
     }
     return v == 1 && tc_enabled();
 }
+// VG_SMALL=0 disables the streaming kernels of conv_small.cu (A/B testing and cross-checks)
+inline bool small_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VG_SMALL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 inline size_t mma_fwd_elems(const vg_conv3d_desc* d) {
     return d->Cin == 1 ? 0 : (size_t)d->K * d->K * d->K * rup(d->Cout, NPAD) * d->Cin;
 }
@@ -887,6 +897,15 @@ int vg_conv3d_fwd(const vg_conv3d_desc* d, const void* x, const void* w_fwd, con
         VG_CHECK_LAUNCH();
         return VG_OK;
     }
+    if (small_enabled() && d->K == 1 && d->stride == 1) {
+        int rc = VG_ERR_UNSUPPORTED;
+        const long long nvox = (long long)d->N * OD * OH * OW;
+        if (d->Cout == 1) rc = vg_small_cout1_k1_fwd((const bf16*)x, (const bf16*)w_fwd, bias, (float*)y, (size_t)nvox, d->Cin, d->act, st);
+        else if (d->act == VG_ACT_NONE && d->y_dtype == VG_BF16)
+            rc = vg_small_k1_fwd((const bf16*)x, (const bf16*)w_fwd, bias, (bf16*)y, nvox, d->Cin, d->Cout, st);
+        if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
+        if (rc != VG_ERR_UNSUPPORTED) return rc;
+    }
     if (tc_enabled() && tc_fwd_ok(d) && d->y_dtype == VG_BF16) {
         const bf16* wt = (const bf16*)((const char*)w_fwd + rup256(mma_fwd_elems(d) * 2));
         const int kt = tc_fwd_s2(d) ? 2 : d->K;
@@ -916,6 +935,11 @@ int vg_conv3d_dgrad(const vg_conv3d_desc* d, const void* dy, const void* w_dgrad
     const int OD = odim(d->ID, d->K, d->stride), OH = odim(d->IH, d->K, d->stride), OW = odim(d->IW, d->K, d->stride);
     if (d->Cout == 1) {
         VG_REQUIRE(d->stride == 1 && d->Cin % 8 == 0);
+        if (small_enabled() && d->K == 1) {
+            int rc = vg_small_cout1_k1_dgrad((const float*)dy, (const float*)w_dgrad, (bf16*)dx, (size_t)d->N * OD * OH * OW, d->Cin, st);
+            if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
+            if (rc != VG_ERR_UNSUPPORTED) return rc;
+        }
         size_t total = (size_t)d->N * d->ID * d->IH * d->IW * (d->Cin / 8);
         cout1_dgrad_kernel<<<vg_grid_for(total, 256, 16), 256, 0, st>>>((const float*)dy, (const float*)w_dgrad, (bf16*)dx, d->N,
                                                                        d->ID, d->IH, d->IW, OD, OH, OW, d->Cin, d->K); VG_LAUNCHED(1);
@@ -923,6 +947,11 @@ int vg_conv3d_dgrad(const vg_conv3d_desc* d, const void* dy, const void* w_dgrad
         return VG_OK;
     }
     const int s = d->stride;
+    if (small_enabled() && d->Cin == 1 && s == 2 && d->x_dtype == VG_F32) {
+        int rc = vg_small_cin1_dgrad_s2((const bf16*)dy, (const bf16*)w_dgrad, (float*)dx, d->N, d->ID, d->IH, d->IW, OD, OH, OW, d->Cout, d->K, st);
+        if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
+        if (rc != VG_ERR_UNSUPPORTED) return rc;
+    }
     if (d->K < s) {  // k1 s2: odd-parity classes receive nothing
         size_t bytes = (size_t)d->N * d->ID * d->IH * d->IW * d->Cin * (d->x_dtype == VG_F32 ? 4 : 2);
         if (cudaMemsetAsync(dx, 0, bytes, st) != cudaSuccess) return VG_ERR_CUDA;
@@ -1007,6 +1036,12 @@ int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, floa
     }
     if (d->Cout == 1) {
         VG_REQUIRE(d->stride == 1 && d->Cin % 8 == 0 && d->Cin <= 2048);
+        if (small_enabled()) {
+            int rc = d->K == 1 ? vg_small_cout1_k1_wgrad((const bf16*)x, (const float*)dy, dw, rows, d->Cin, st)
+                               : vg_small_cout1_wgrad((const bf16*)x, (const float*)dy, dw, d->N, d->ID, d->IH, d->IW, OD, OH, OW, d->Cin, d->K, st);
+            if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
+            if (rc != VG_ERR_UNSUPPORTED) return rc;
+        }
         int T = d->K * d->K * d->K;
         int nbx = (148 * 4 + T - 1) / T;
         int per_block = (int)((rows + nbx - 1) / nbx);
@@ -1016,6 +1051,11 @@ int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, floa
                                                                                 d->IH, d->IW, OD, OH, OW, d->Cin, d->K, per_block); VG_LAUNCHED(1);
         VG_CHECK_LAUNCH();
         return VG_OK;
+    }
+    if (small_enabled() && d->K == 1) {
+        int rc = vg_small_k1_wgrad((const bf16*)x, (const bf16*)dy, dw, d->N, d->ID, d->IH, d->IW, d->Cin, OD, OH, OW, d->Cout, d->stride, st);
+        if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
+        if (rc != VG_ERR_UNSUPPORTED) return rc;
     }
     if (tc_wgrad_enabled()) {
         int rc = vg_wg_tc_launch((const bf16*)x, (const bf16*)dy, dw, d->N, d->ID, d->IH, d->IW, d->Cin, OD, OH, OW, d->Cout, d->K, d->stride, st);
