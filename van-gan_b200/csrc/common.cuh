@@ -160,3 +160,5 @@ int vg_small_cout1_wgrad(const bf16* x, const float* dy, float* dw, int N, int I
                          cudaStream_t st);
 int vg_small_cin1_dgrad_s2(const bf16* dy, const bf16* wd, float* dx, int N, int ID, int IH, int IW, int OD, int OH, int OW, int Cout, int K,
                            cudaStream_t st);
+int vg_small_cin1_wgrad(const float* x, const bf16* dy, float* dw, float* dbias, int N, int ID, int IH, int IW, int OD, int OH, int OW,
+                        int Cout, int K, int stride, int* bias_done, cudaStream_t st);

@@ -1001,6 +1001,20 @@ int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, floa
     const size_t rows = (size_t)d->N * OD * OH * OW;
     if (d->Cin == 1) {
         VG_REQUIRE(d->Cout % 16 == 0);
+        if (small_enabled()) {
+            int bias_done = 0;
+            int rc = vg_small_cin1_wgrad((const float*)x, (const bf16*)dy, dw, dbias, d->N, d->ID, d->IH, d->IW, OD, OH, OW, d->Cout, d->K,
+                                         d->stride, &bias_done, st);
+            if (rc == VG_OK) {
+                if (dbias && !bias_done) {
+                    channel_sum_kernel<bf16><<<vg_grid_for(rows, 32, 2), 256, (size_t)(256 / (d->Cout / 8)) * d->Cout * sizeof(float), st>>>(
+                        (const bf16*)dy, rows, d->Cout, dbias); VG_LAUNCHED(1);
+                }
+                VG_CHECK_LAUNCH();
+                return VG_OK;
+            }
+            if (rc != VG_ERR_UNSUPPORTED) return rc;
+        }
         const int ntask = d->K * d->K * (d->Cout / 16);
         int wpb = ntask;                       // warps per block: all tasks when they fit, else the largest divisor <= 16
         while (wpb > 16) wpb = (wpb % 2 == 0) ? wpb / 2 : 1;

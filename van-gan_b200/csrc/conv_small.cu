@@ -451,6 +451,185 @@ __global__ void __launch_bounds__(256) cin1_dgrad_s2_kernel(const bf16* __restri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ Cin == 1 weight gradient on tensor cores
+// dw[tap][co] += sum_o x[S*o + tap] * dy[o][co]   (stem 1->16 k3 s1, PatchGAN d0 1->64 k4 s2; resunet_model.py:89, discriminator.py:63).
+// GEMM view: M = taps (27 -> 32, 64), N = Cout, K = 16 consecutive output voxels of one row.  x is fp32 and dw must be fp32-exact
+// (the reference differentiates fp32 inputs), so x is split on the fly into THREE bf16 planes h + m + l = x (exact to 2^-25) and
+// every k-step issues three MMAs per tile; dy is already bf16.  The A fragment of tap (kd,kh,kw) is a pair of adjacent elements
+// of the x row (kd, S*oh+kh), de-interleaved by w-parity for stride 2: an aligned 32-bit shared load, or two loads and a funnel
+// shift for odd offsets.  The B fragment is dy^T through ldmatrix.trans (XOR-swizzled 16-byte chunks).  A spare M row of ones
+// yields the bias gradient for free when taps < 16*MT.
+__device__ __forceinline__ void split3(float v, uint32_t& h, uint32_t& m, uint32_t& l) {
+    const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hb);
+    const __nv_bfloat16 mb = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(mb);
+    const __nv_bfloat16 lb = __float2bfloat16_rn(r2);
+    h = __bfloat16_as_ushort(hb); m = __bfloat16_as_ushort(mb); l = __bfloat16_as_ushort(lb);
+}
+
+template <int K, int S, int COUT>
+__global__ void __launch_bounds__(256) cin1_wgrad_tc_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
+                                                            float* __restrict__ dbias, int N, int ID, int IH, int IW, int OD, int OH, int OW,
+                                                            int WP, int OWp) {
+    constexpr int T = K * K * K, MT = (T + 15) / 16, NG = COUT / 16, RW = 8 / NG, NCHK = COUT / 8;
+    constexpr int BH = S == 1 ? 8 : 4, HB = (BH - 1) * S + K;
+    constexpr bool ONES = T < MT * 16;
+    constexpr int SWZ_SH = NCHK == 8 ? 0 : (NCHK == 4 ? 1 : 2);
+    extern __shared__ __align__(16) uint8_t c1w_smem[];
+    const int plane_elems = S * K * HB * WP;                // one split
+    uint16_t* xs = reinterpret_cast<uint16_t*>(c1w_smem);  // [3][S][K][HB][WP]
+    const uint32_t xs_u32 = sm_u32(c1w_smem);
+    const uint32_t dy_u32 = xs_u32 + (uint32_t)(3 * plane_elems * 2 + 15) / 16 * 16;   // [BH][OWp][NCHK] 16-byte chunks, swizzled
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int ng = warp % NG, rw = warp / NG;
+    // per-lane tap constants: element offset of the tap inside a split plane (row oh_l = 0, voxel 0), -1 = zero row, -2 = ones row
+    int toff[MT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+            const int tap = mt * 16 + g + 8 * hf;
+            if (tap < T) {
+                const int kw = tap % K, kh = (tap / K) % K, kd = tap / (K * K);
+                toff[mt][hf] = (((kw % S) * K + kd) * HB + kh) * WP + kw / S;
+            } else toff[mt][hf] = (ONES && tap == T) ? -2 : -1;
+        }
+    float acc[MT][2][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[mt][nt][e] = 0.f;
+    const int nhb = (OH + BH - 1) / BH;
+    const int nbricks = N * OD * nhb;
+    const int ksteps = BH * (OWp / 16);
+    const int j = lane >> 3, r = lane & 7;
+    for (int brick = blockIdx.x; brick < nbricks; brick += gridDim.x) {
+        const int hb = brick % nhb, q = brick / nhb;
+        const int od = q % OD, n = q / OD;
+        const int oh0 = hb * BH;
+        __syncthreads();   // previous brick consumed
+        // dy tile: rows oh0..oh0+BH-1, voxels 0..OWp-1 (zero beyond OH / OW)
+        for (int i = threadIdx.x; i < BH * OWp * NCHK; i += 256) {
+            const int c = i % NCHK, v = (i / NCHK) % OWp, row = i / (NCHK * OWp);
+            const bool ok = oh0 + row < OH && v < OW;
+            const bf16* src = dy + ((((size_t)n * OD + od) * OH + oh0 + row) * OW + v) * COUT + c * 8;
+            cpa16(dy_u32 + (uint32_t)((row * OWp + v) * NCHK + (c ^ ((v >> SWZ_SH) & (NCHK - 1)))) * 16, ok ? src : dy, ok ? 16 : 0);
+        }
+        cpa_commit();
+        // x halo -> three bf16 planes per w-parity; a work item = (d, h, pair index): 2*S consecutive floats -> S pairs
+        const int npair = WP / 2;
+        for (int i = threadIdx.x; i < K * HB * npair; i += 256) {
+            const int pi = i % npair, h = (i / npair) % HB, d = i / (npair * HB);
+            const int xd = od * S + d, xh = oh0 * S + h;
+            const bool rok = xh < IH;   // xd < ID always (od < OD)
+            const float* xr = x + (((size_t)n * ID + xd) * IH + (rok ? xh : 0)) * IW;
+            float v[2 * S];
+#pragma unroll
+            for (int e = 0; e < 2 * S; e++) {
+                const int w = 2 * S * pi + e;
+                v[e] = (rok && w < IW) ? __ldg(xr + w) : 0.f;
+            }
+#pragma unroll
+            for (int par = 0; par < S; par++) {
+                uint32_t h0, m0, l0, h1, m1, l1;
+                split3(v[par], h0, m0, l0);
+                split3(v[par + S], h1, m1, l1);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(xs + ((par * K + d) * HB + h) * WP + 2 * pi);
+                dst[0] = h0 | (h1 << 16);
+                dst[plane_elems / 2] = m0 | (m1 << 16);
+                dst[plane_elems] = l0 | (l1 << 16);
+            }
+        }
+        cpa_wait<0>();
+        __syncthreads();
+        for (int ks = rw; ks < ksteps; ks += RW) {
+            const int row = ks / (OWp / 16), w0 = (ks % (OWp / 16)) * 16;
+            uint32_t bq[4];
+            {
+                const int v = w0 + (j & 1) * 8 + r, c = 2 * ng + (j >> 1);
+                ldsm4_t(dy_u32 + (uint32_t)((row * OWp + v) * NCHK + (c ^ ((v >> SWZ_SH) & (NCHK - 1)))) * 16, bq);
+            }
+            const int rbase = row * S * WP + w0 + 2 * t;
+#pragma unroll
+            for (int sp = 0; sp < 3; sp++) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    uint32_t a[4];
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        const int to = toff[mt][hf];
+                        if (to >= 0) {
+                            const uint16_t* pl = xs + sp * plane_elems + to + rbase;
+                            const int odd = (to + rbase) & 1;
+                            const uint32_t* wp0 = reinterpret_cast<const uint32_t*>(pl - odd);
+                            const uint32_t lo0 = wp0[0], hi0 = wp0[1], lo1 = wp0[4], hi1 = wp0[5];
+                            a[hf] = odd ? __funnelshift_r(lo0, hi0, 16) : lo0;
+                            a[hf + 2] = odd ? __funnelshift_r(lo1, hi1, 16) : lo1;
+                        } else {
+                            a[hf] = a[hf + 2] = (to == -2 && sp == 0) ? 0x3F803F80u : 0u;
+                        }
+                    }
+                    mma16816(acc[mt][0], a, bq[0], bq[1]);
+                    mma16816(acc[mt][1], a, bq[2], bq[3]);
+                }
+            }
+        }
+    }
+    // block reduction over the row-warps, then one atomic per output per block
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(c1w_smem);   // [8 warps][MT*16][16]
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            float* o = red + ((size_t)warp * MT * 16 + mt * 16 + g) * 16 + nt * 8 + 2 * t;
+            o[0] = acc[mt][nt][0]; o[1] = acc[mt][nt][1];
+            o[8 * 16] = acc[mt][nt][2]; o[8 * 16 + 1] = acc[mt][nt][3];
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NG * MT * 16 * 16; i += 256) {
+        const int col = i % 16, tap = (i / 16) % (MT * 16), gq = i / (16 * MT * 16);
+        float sacc = 0.f;
+#pragma unroll
+        for (int w = 0; w < RW; w++) sacc += red[((size_t)(w * NG + gq) * MT * 16 + tap) * 16 + col];
+        if (tap < T) atomicAdd(dw + (size_t)tap * COUT + gq * 16 + col, sacc);
+        else if (ONES && tap == T && dbias) atomicAdd(dbias + gq * 16 + col, sacc);
+    }
+}
+
+template <int K, int S, int COUT>
+int launch_cin1_wgrad_tc(const float* x, const bf16* dy, float* dw, float* dbias, int N, int ID, int IH, int IW, int OD, int OH, int OW,
+                         cudaStream_t st) {
+    constexpr int T = K * K * K, MT = (T + 15) / 16, BH = S == 1 ? 8 : 4, HB = (BH - 1) * S + K, NCHK = COUT / 8;
+    const int OWp = (OW + 15) / 16 * 16;
+    const int WP = (OWp + (K - 1) / S + 2 + 1) & ~1;
+    if ((IW + S - 1) / S + 1 > WP) return VG_ERR_UNSUPPORTED;
+    const size_t planes = ((size_t)3 * S * K * HB * WP * 2 + 15) / 16 * 16;
+    size_t smem = planes + (size_t)BH * OWp * NCHK * 16;
+    const size_t red = (size_t)8 * MT * 16 * 16 * 4;
+    if (smem < red) smem = red;
+    if (smem > 200 * 1024) return VG_ERR_UNSUPPORTED;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(cin1_wgrad_tc_kernel<K, S, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return VG_ERR_CUDA;
+        attr = true;
+    }
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm < 1) per_sm = 1;
+    const int nbricks = N * OD * ((OH + BH - 1) / BH);
+    int grid = 148 * per_sm;
+    if (grid > nbricks) grid = nbricks;
+    cin1_wgrad_tc_kernel<K, S, COUT><<<grid, 256, smem, st>>>(x, dy, dw, dbias, N, ID, IH, IW, OD, OH, OW, WP, OWp);
+    VG_LAUNCHED(1);
+    return VG_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------- dispatch (called from conv_mma.cu)
@@ -537,4 +716,17 @@ int vg_small_cin1_dgrad_s2(const bf16* dy, const bf16* wd, float* dx, int N, int
     cin1_dgrad_s2_kernel<NC><<<grid, 256, smem, st>>>(dy, wd, dx, N, ID, IH, IW, OD, OH, OW, nbd, nbh, nbw);
     VG_LAUNCHED(1);
     return VG_OK;
+}
+
+// Returns VG_OK with *bias_done = 1 when the bias gradient was produced by the same launch.
+int vg_small_cin1_wgrad(const float* x, const bf16* dy, float* dw, float* dbias, int N, int ID, int IH, int IW, int OD, int OH, int OW,
+                        int Cout, int K, int stride, int* bias_done, cudaStream_t st) {
+    *bias_done = 0;
+    if (K == 3 && stride == 1 && Cout == 16) {
+        int rc = launch_cin1_wgrad_tc<3, 1, 16>(x, dy, dw, dbias, N, ID, IH, IW, OD, OH, OW, st);
+        if (rc == VG_OK) *bias_done = 1;
+        return rc;
+    }
+    if (K == 4 && stride == 2 && Cout == 64) return launch_cin1_wgrad_tc<4, 2, 64>(x, dy, dw, nullptr, N, ID, IH, IW, OD, OH, OW, st);
+    return VG_ERR_UNSUPPORTED;
 }
