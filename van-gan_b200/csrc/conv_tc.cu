@@ -57,6 +57,8 @@ struct TcParams {
     int ED, EH, EW;
     int ss, cpc;   // source stride (1, or 2 = stride-2 forward as 8 parity classes of 2x2x2 taps) and 16-channel chunks per class
     int goff;   // origin of the output grid inside the output tensor (cropped dgrad); applied to source and output coordinates
+    int dm_order[12];   // d-march: issue order of the source slices (overlapping TMEM windows kept >= 3 instructions apart)
+    int dm;   // d-march: the TD taps along d are folded into the MMA N dimension (N = cnt * NCTA, sliding TMEM window)
     int stages, act, use_tma, dbg;   // dbg: bit0 = skip brick/weight loads, bit1 = skip MMA issue (timing experiments only)
     const bf16* x;        // source tensor (gather loader)
     int XD, XH, XW, Cx;
@@ -145,6 +147,13 @@ __device__ __forceinline__ void tc_ld_wait16(uint32_t* v) {
                  :
                  : "memory");
 }
+
+// zero 16 consecutive TMEM columns of this warp's 32 lanes
+__device__ __forceinline__ void tc_st16_zero(uint32_t taddr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr), "r"(0)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 template <int BD>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
@@ -312,7 +321,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         const int aoff0 = p.st > 0 ? 0 : ((p.TD - 1) * p.EH + (p.TH - 1)) * p.EW + (p.TW - 1);
         for (int wk = blockIdx.x; wk < p.nwork; wk += gridDim.x, it++) {
             const int buf = it & 1;
-            mbar_wait(tempty0 + 8 * buf, ((it >> 1) & 1) ^ 1);
+            // d-march: the epilogue hands every buffer over ZEROED (and pre-arrives once at start), so use n waits for completion n
+            mbar_wait(tempty0 + 8 * buf, ((it >> 1) & 1) ^ (p.dm ? 0u : 1u));
             tc_fence_after();
             const uint32_t d0 = tmem_base + (uint32_t)(buf * BD) * p.NCTA;
             for (int c = 0; c < p.nchunks; c++) {
@@ -320,6 +330,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 tc_fence_after();
                 const uint32_t a_base = (sbase + stage * p.stage_bytes) >> 4;
                 uint32_t b_addr = a_base + ((2 * p.plane_bytes) >> 4);
+                if (p.dm) {
+                    // d-march.  Source slice sl feeds the output tiles m = sl - td' (td' = 0..TD-1) with the SAME A operand, so the
+                    // TD weight blocks sit side by side along N (position pos <-> tile m_lo + pos, see tc_pack_kernel) and ONE MMA of
+                    // N = cnt * NCTA accumulates into the TMEM columns of tiles m_lo..m_hi (tile m lives at column m * NCTA):
+                    // TH*TW*(BD+TD-1) instructions per chunk instead of TD*TH*TW*BD, each ~(32 + N/4) cycles.
+                    // Measured: an MMA that accumulates into columns the previous MMA wrote waits ~95 cycles for it, so the slices
+                    // are issued in an order (dm_order) that keeps overlapping windows >= 3 instructions apart, and every
+                    // instruction accumulates (the epilogue returns the buffer zeroed) so that the order is free.
+                    const uint32_t ntot = (uint32_t)(p.TD * p.NCTA);
+                    const uint32_t b_lbo_dm = (ntot & 0x3fffu) << 16;   // K-half stride = Ntot rows x 16 bytes
+                    const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+                    const int ED = BD + p.TD - 1;
+                    int aoff_q = p.st > 0 ? 0 : (p.TH - 1) * p.EW + (p.TW - 1);
+                    uint32_t bq = b_addr;
+                    for (int th = 0; th < p.TH; th++) {
+                        for (int tw = 0; tw < p.TW; tw++) {
+                            if (leader && !(p.dbg & 2)) {
+                                for (int i = 0; i < ED; i++) {
+                                    const int sl = p.dm_order[i];
+                                    const int m_lo = sl - p.TD + 1 > 0 ? sl - p.TD + 1 : 0;
+                                    const int m_hi = sl < BD - 1 ? sl : BD - 1;
+                                    const uint32_t ncols = (uint32_t)((m_hi - m_lo + 1) * p.NCTA);
+                                    const uint64_t adesc = ((uint64_t)a_hi << 32) | (a_lo_lbo | (a_base + (uint32_t)(aoff_q + sl * tile_step)));
+                                    const uint64_t bdesc = ((uint64_t)b_hi << 32) | (b_lbo_dm | (bq + (uint32_t)((p.TD - 1 - sl + m_lo) * p.NCTA)));
+                                    tc_mma(d0 + (uint32_t)(m_lo * p.NCTA), adesc, bdesc, idesc0 | ((ncols >> 3) << 17), 1u);
+                                }
+                            }
+                            aoff_q += sgn;
+                            bq += 2 * ntot;
+                        }
+                        aoff_q += sgn * (p.EW - p.TW);
+                    }
+                    __syncwarp();
+                    if (leader) tc_commit(empty0 + 8 * stage);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 int aoff = aoff0;
                 uint32_t acc = c ? 1u : 0u;
                 for (int td = 0; td < p.TD; td++) {
@@ -358,6 +405,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         const int lh = r >> 3, lw = r & 7;
         const int nb16 = p.NCTA >> 4, units = BD * nb16;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (p.dm) {
+            // d-march start-up: zero both accumulator buffers (warpgroup 0 covers the four lane quarters) and release them
+            if (grp == 0)
+                for (uint32_t col = 0; col < (uint32_t)(2 * BD * p.NCTA); col += 16) tc_st16_zero(lane_base + col);
+            tc_st_wait();
+            tc_fence_before();
+            mbar_arrive(tempty0);
+            mbar_arrive(tempty0 + 8);
+        }
         int it = 0;
         for (int wk = blockIdx.x; wk < p.nwork; wk += gridDim.x, it++) {
             const int nb = wk % p.nblk;
@@ -407,17 +463,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             if (u < units) tc_ld16_issue(tbuf + (uint32_t)(u << 4), va);
             while (u < units) {
                 tc_ld_wait16(va);
+                if (p.dm) tc_st16_zero(tbuf + (uint32_t)(u << 4));
                 int un = u + 2;
                 if (un < units) tc_ld16_issue(tbuf + (uint32_t)(un << 4), vb);
                 finish(u, va);
                 u = un;
                 if (u >= units) break;
                 tc_ld_wait16(vb);
+                if (p.dm) tc_st16_zero(tbuf + (uint32_t)(u << 4));
                 un = u + 2;
                 if (un < units) tc_ld16_issue(tbuf + (uint32_t)(un << 4), va);
                 finish(u, vb);
                 u = un;
             }
+            if (p.dm) tc_st_wait();
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * buf);
         }
@@ -453,6 +512,17 @@ EncodeTiledFn get_encode() {
 
 unsigned long long g_vg_tc_launches = 0;
 extern "C" unsigned long long vg_tc_launch_count(void) { return g_vg_tc_launches; }
+
+// d-march (taps along d folded into the MMA N dimension) is used when the folded width stays within one MMA that the
+// shared-memory operand bandwidth can feed (measured: N <= 128 reaches the issue floor).  VG_TC_DM=0 disables it.
+static bool vg_tc_dmarch(int ncta, int TD) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("VG_TC_DM");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on && (TD == 2 || TD == 3) && TD * ncta <= 128;   // TD = 4: every window overlaps its 3 neighbours, nothing to interleave
+}
 
 // N-block width used by the tensor-core path for a GEMM with `ncols` output columns and T taps (0 = not eligible)
 int vg_tc_ncta(int ncols, int T) {
@@ -514,7 +584,14 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
     p.EH = MH + TH - 1; p.EW = MW + TW - 1;
     p.wstage_bytes = (uint32_t)T * 2 * ncta * 16;
     const size_t smem_cap = 220 * 1024;
-    int BD = 4;
+    p.dm = vg_tc_dmarch(ncta, TD) ? 1 : 0;
+    static int bd_max = -1;   // d-march amortises its TD-1 edge slices over BD tiles: deeper bricks pay (VG_TC_BD overrides)
+    if (bd_max < 0) {
+        const char* e = getenv("VG_TC_BD");
+        bd_max = e ? atoi(e) : 8;
+        if (bd_max != 1 && bd_max != 2 && bd_max != 4 && bd_max != 8) bd_max = 8;
+    }
+    int BD = p.dm ? bd_max : (bd_max < 4 ? bd_max : 4);
     while (BD > GD && BD > 1) BD >>= 1;
     for (;; BD >>= 1) {
         p.BD = BD;
@@ -524,8 +601,28 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
         p.stage_bytes = 2 * p.plane_bytes + p.wstage_bytes;
         p.stages = (int)((smem_cap - TC_TAIL) / p.stage_bytes);
         if (p.stages > 4) p.stages = 4;
-        if (p.stages >= 2 && 2 * BD * ncta <= 512) break;
+        if (p.stages >= ((BD > 4 && !p.dm) ? 3 : 2) && 2 * BD * ncta <= 512) break;
         if (BD == 1) return VG_ERR_UNSUPPORTED;
+    }
+    if (p.dm) {
+        // issue order of the BD+TD-1 source slices: s_i = (i * g) mod ED with the step g that maximises the smallest cyclic
+        // distance between two slices whose TMEM windows overlap (|s - s'| < TD)
+        const int ED = p.BD + TD - 1;
+        int best_g = 1, best_d = -1;
+        for (int g = 1; g < ED; g++) {
+            int a = g, b = ED;
+            while (b) { int t = a % b; a = b; b = t; }
+            if (a != 1) continue;
+            int dmin = ED;
+            for (int i = 0; i < ED; i++)
+                for (int k = 1; k < ED; k++) {
+                    const int si = (i * g) % ED, sj = ((i + k) * g) % ED;
+                    const int ds = si > sj ? si - sj : sj - si;
+                    if (ds < TD && k < dmin) dmin = k;
+                }
+            if (dmin > best_d) { best_d = dmin; best_g = g; }
+        }
+        for (int i = 0; i < ED && i < 12; i++) p.dm_order[i] = (i * best_g) % ED;
     }
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * p.BD * ncta)) cols <<= 1;
@@ -551,12 +648,14 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
     if (!attr_done) {
         if (cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(tc_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            cudaFuncSetAttribute(tc_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(tc_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return VG_ERR_CUDA;
         attr_done = true;
     }
     int grid = p.nwork < 148 ? p.nwork : 148;
-    if (p.BD == 4) tc_conv_kernel<4><<<grid, TC_THREADS, smem, stream>>>(tmap, p);
+    if (p.BD == 8) tc_conv_kernel<8><<<grid, TC_THREADS, smem, stream>>>(tmap, p);
+    else if (p.BD == 4) tc_conv_kernel<4><<<grid, TC_THREADS, smem, stream>>>(tmap, p);
     else if (p.BD == 2) tc_conv_kernel<2><<<grid, TC_THREADS, smem, stream>>>(tmap, p);
     else tc_conv_kernel<1><<<grid, TC_THREADS, smem, stream>>>(tmap, p);
     VG_LAUNCHED(1);
@@ -569,7 +668,7 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
 // dgrad: src(t',k,col) = w[tap(t')][col][k]      (K = Cout, cols = Cin), taps restricted to one stride-parity class
 // fwd stride 2 (dgrad == 2): chunk c = (parity class a,b,c ; 16-channel chunk), taps t' in 2x2x2, src = w[2t'+a][k][col] (0 if >= K)
 __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int K, int stride, int Cin, int Cout, int dgrad,
-                               int ad, int ah, int aw, int td, int th, int tw, int ncta, int nblk) {
+                               int ad, int ah, int aw, int td, int th, int tw, int ncta, int nblk, int dm) {
     const int T = td * th * tw;
     const int Kt = dgrad == 1 ? Cout : Cin, ncols = dgrad == 1 ? Cin : Cout;
     const int cpc = Kt / 16;
@@ -579,12 +678,23 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ o
         size_t r = i;
         int j = (int)(r % 8); r /= 8;
         int n = (int)(r % ncta); r /= ncta;
-        int kh = (int)(r % 2); r /= 2;
-        int t = (int)(r % T); r /= T;
+        int w_, h_, d_, kh;
+        if (dm) {
+            // d-march layout [q = (th, tw)][K half][pos][n][8]: position pos along N holds the tap that maps source slice s to output
+            // tile m_lo + pos, i.e. loop index td = TD-1-pos for a forward gather (slice = m + td) and td = pos for dgrad
+            int pos = (int)(r % td); r /= td;
+            kh = (int)(r % 2); r /= 2;
+            int q = (int)(r % (th * tw)); r /= (th * tw);
+            w_ = q % tw; h_ = q / tw;
+            d_ = dgrad == 1 ? pos : td - 1 - pos;
+        } else {
+            kh = (int)(r % 2); r /= 2;
+            int t = (int)(r % T); r /= T;
+            w_ = t % tw; h_ = (t / tw) % th; d_ = t / (tw * th);
+        }
         int c = (int)(r % nchunks);
         int nb = (int)(r / nchunks);
         int col = nb * ncta + n;
-        int w_ = t % tw, h_ = (t / tw) % th, d_ = t / (tw * th);
         int k, kd, kh2, kw;
         if (dgrad == 2) {
             const int cls = c / cpc, cc = c - cls * cpc;
@@ -611,7 +721,7 @@ int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, 
     const int nblk = (ncols + ncta - 1) / ncta;
     size_t total = vg_tc_pack_elems(ncols, dgrad == 1 ? Cout : (dgrad == 2 ? 8 * Cin : Cin), T);
     tc_pack_kernel<<<vg_grid_for((long long)total, 256, 4), 256, 0, st>>>(w, out, K, stride, Cin, Cout, dgrad, ad, ah, aw, td, th, tw, ncta,
-                                                                          nblk);
+                                                                          nblk, vg_tc_dmarch(ncta, td) ? 1 : 0);
     VG_LAUNCHED(1);
     return VG_OK;
 }
