@@ -173,6 +173,8 @@ CONV_CASES = [
     # streaming kernels of conv_small.cu: ragged voxel counts, every template instance, odd extents for the fused-parity dgrad
     (48, 16, 1, 1, (5, 7, 9), 1), (96, 32, 1, 1, (8, 8, 10), 1), (32, 64, 1, 2, (8, 9, 12), 1), (16, 16, 1, 1, (7, 5, 3), 2),
     (32, 32, 1, 1, (6, 6, 7), 1), (1, 64, 4, 2, (19, 21, 40), 2), (512, 1, 3, 1, (5, 6, 9), 1), (16, 1, 1, 1, (33, 5, 7), 1),
+    # more work items than SMs: persistent tcgen05 CTAs re-use their (zeroed) TMEM buffers and run several d-march bricks
+    (16, 16, 3, 1, (34, 34, 66), 3), (32, 32, 3, 1, (34, 34, 34), 5),
 ]
 
 

@@ -57,6 +57,7 @@ struct TcParams {
     int ED, EH, EW;
     int ss, cpc;   // source stride (1, or 2 = stride-2 forward as 8 parity classes of 2x2x2 taps) and 16-channel chunks per class
     int goff;   // origin of the output grid inside the output tensor (cropped dgrad); applied to source and output coordinates
+    int dsplit;   // d-split: the kd taps become extra K-chunks (chunk = (kd, 16 channels)), each staging a BD-slice brick shifted by kd
     int dm_order[12];   // d-march: issue order of the source slices (overlapping TMEM windows kept >= 3 instructions apart)
     int dm;   // d-march: the TD taps along d are folded into the MMA N dimension (N = cnt * NCTA, sliding TMEM window)
     int stages, act, use_tma, dbg;   // dbg: bit0 = skip brick/weight loads, bit1 = skip MMA issue (timing experiments only)
@@ -227,13 +228,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                     // cp.async gather: 16-byte copies straight into the two planes (zero fill outside the tensor), no register
                     // staging, so a whole stage (or two) is in flight per SM; published one stage late (see below)
                     // stride-2 forward: chunk c = (parity class, 16-channel chunk); the class reads the strided view x[2i + a]
-                    const int cls = p.ss == 2 ? c / p.cpc : 0, cc = p.ss == 2 ? c - cls * p.cpc : c;
+                    const int grp = (p.ss == 2 || p.dsplit) ? c / p.cpc : 0, cc = c - grp * p.cpc;
+                    const int cls = p.ss == 2 ? grp : 0;
                     const int oa = (cls >> 2) & 1, ob = (cls >> 1) & 1, oc = cls & 1;
+                    const int dshift = p.dsplit ? (p.st > 0 ? grp : -grp) : 0;
                     const bf16* xc = xn + cc * 16;
                     for (int v = tid; v < EV; v += NPROD) {
                         const int ld = (int)p.by_ehw.div((uint32_t)v), rem = v - ld * EHW;
                         const int lh = (int)p.by_ew.div((uint32_t)rem), lw = rem - lh * p.EW;
-                        const int sd = p.ss * (sd0 + ld) + oa, sh = p.ss * (sh0 + lh) + ob, sw = p.ss * (sw0 + lw) + oc;
+                        const int sd = p.ss * (sd0 + ld + dshift) + oa, sh = p.ss * (sh0 + lh) + ob, sw = p.ss * (sw0 + lw) + oc;
                         const bool ok = (unsigned)sd < (unsigned)p.XD && (unsigned)sh < (unsigned)p.XH && (unsigned)sw < (unsigned)p.XW;
                         const bf16* src = ok ? xc + (((size_t)sd * p.XH + sh) * p.XW + sw) * p.Cx : xc;
                         const uint32_t d0 = dst + (uint32_t)v * 16;
@@ -524,6 +527,17 @@ static bool vg_tc_dmarch(int ncta, int TD) {
     return on && (TD == 2 || TD == 3) && TD * ncta <= 128;   // TD = 4: every window overlaps its 3 neighbours, nothing to interleave
 }
 
+// d-split (k4 s1 layers, 64 taps): with all taps of a 16-channel chunk in one stage the weight block caps the N tile at 32
+// columns (40 cycles per MMA against a floor of 16).  Splitting the chunk by kd keeps 16 taps per stage, N = 64.
+bool vg_tc_dsplit(int ncols, int td, int th, int tw) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("VG_TC_DSPLIT");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on && td == 4 && th == 4 && tw == 4 && ncols % 64 == 0;   // same padded width as the unsplit pack (N tile 32)
+}
+
 // N-block width used by the tensor-core path for a GEMM with `ncols` output columns and T taps (0 = not eligible)
 int vg_tc_ncta(int ncols, int T) {
     if (ncols < 16 || ncols % 16) return 0;
@@ -552,8 +566,11 @@ size_t vg_tc_pack_elems(int ncols, int K_total, int T) {
 int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf16* wpack, void* y, const float* bias, int YD, int YH,
                  int YW, int Cy, int GD, int GH, int GW, int TD, int TH, int TW, int st, int oso, int ood, int ooh, int oow, int act,
                  cudaStream_t stream, int goff, int ss) {
+    const int TD_full = TD;
+    const bool dsplit = ss == 1 && vg_tc_dsplit(Cy, TD, TH, TW);
+    const int ncta = dsplit ? 64 : vg_tc_ncta(Cy, TD * TH * TW);
+    if (dsplit) TD = 1;   // the kernel sees a (1, TH, TW) filter and TD_full x as many K-chunks
     const int T = TD * TH * TW;
-    const int ncta = vg_tc_ncta(Cy, T);
     if (!ncta || Cx % 16) return VG_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
     if (!enc) return VG_ERR_UNSUPPORTED;
@@ -568,12 +585,13 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
         dbg = e ? atoi(e) : 0;
     }
     TcParams p{};
-    p.use_tma = ss == 2 ? 2 : loader;   // the strided view is only implemented by the cp.async gather
+    p.use_tma = (ss == 2 || dsplit) ? 2 : loader;   // strided views / shifted bricks are only implemented by the cp.async gather
+    p.dsplit = dsplit ? TD_full : 0;
     p.dbg = dbg;
     p.x = x; p.XD = XD; p.XH = XH; p.XW = XW; p.Cx = Cx;
     p.w = wpack; p.y = y; p.bias = bias;
     p.ss = ss; p.cpc = Cx / 16;
-    p.Nb = Nb; p.nchunks = (ss == 2 ? 8 : 1) * (Cx / 16);
+    p.Nb = Nb; p.nchunks = (ss == 2 ? 8 : (dsplit ? TD_full : 1)) * (Cx / 16);
     p.YD = YD; p.YH = YH; p.YW = YW; p.Cy = Cy;
     p.GD = GD; p.GH = GH; p.GW = GW;
     p.TD = TD; p.TH = TH; p.TW = TW; p.st = st;
@@ -668,11 +686,11 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
 // dgrad: src(t',k,col) = w[tap(t')][col][k]      (K = Cout, cols = Cin), taps restricted to one stride-parity class
 // fwd stride 2 (dgrad == 2): chunk c = (parity class a,b,c ; 16-channel chunk), taps t' in 2x2x2, src = w[2t'+a][k][col] (0 if >= K)
 __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int K, int stride, int Cin, int Cout, int dgrad,
-                               int ad, int ah, int aw, int td, int th, int tw, int ncta, int nblk, int dm) {
-    const int T = td * th * tw;
+                               int ad, int ah, int aw, int td, int th, int tw, int ncta, int nblk, int dm, int dsplit) {
+    const int T = dsplit ? th * tw : td * th * tw;
     const int Kt = dgrad == 1 ? Cout : Cin, ncols = dgrad == 1 ? Cin : Cout;
     const int cpc = Kt / 16;
-    const int nchunks = (dgrad == 2 ? 8 : 1) * cpc;
+    const int nchunks = (dgrad == 2 ? 8 : (dsplit ? td : 1)) * cpc;
     size_t total = (size_t)nblk * nchunks * T * 2 * ncta * 8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
@@ -690,7 +708,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ o
         } else {
             kh = (int)(r % 2); r /= 2;
             int t = (int)(r % T); r /= T;
-            w_ = t % tw; h_ = (t / tw) % th; d_ = t / (tw * th);
+            w_ = t % tw; h_ = (t / tw) % th; d_ = t / (tw * th);   // d-split: t < th*tw, d_ = 0 here, set from the chunk below
         }
         int c = (int)(r % nchunks);
         int nb = (int)(r / nchunks);
@@ -701,7 +719,9 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ o
             k = cc * 16 + kh * 8 + j;
             kd = 2 * d_ + ((cls >> 2) & 1); kh2 = 2 * h_ + ((cls >> 1) & 1); kw = 2 * w_ + (cls & 1);
         } else {
-            k = c * 16 + kh * 8 + j;
+            int cc = c;
+            if (dsplit) { d_ = c / cpc; cc = c - d_ * cpc; }
+            k = cc * 16 + kh * 8 + j;
             kd = dgrad ? ad + stride * d_ : d_; kh2 = dgrad ? ah + stride * h_ : h_; kw = dgrad ? aw + stride * w_ : w_;
         }
         int tap = (kd * K + kh2) * K + kw;
@@ -716,12 +736,13 @@ int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, 
                int tw, cudaStream_t st) {
     const int T = td * th * tw;
     const int ncols = dgrad == 1 ? Cin : Cout;
-    const int ncta = vg_tc_ncta(ncols, T);
+    const bool dsplit = dgrad != 2 && stride == 1 && vg_tc_dsplit(ncols, td, th, tw);
+    const int ncta = dsplit ? 64 : vg_tc_ncta(ncols, T);
     if (!ncta) return VG_ERR_UNSUPPORTED;
     const int nblk = (ncols + ncta - 1) / ncta;
     size_t total = vg_tc_pack_elems(ncols, dgrad == 1 ? Cout : (dgrad == 2 ? 8 * Cin : Cin), T);
     tc_pack_kernel<<<vg_grid_for((long long)total, 256, 4), 256, 0, st>>>(w, out, K, stride, Cin, Cout, dgrad, ad, ah, aw, td, th, tw, ncta,
-                                                                          nblk, vg_tc_dmarch(ncta, td) ? 1 : 0);
+                                                                          nblk, vg_tc_dmarch(ncta, td) ? 1 : 0, dsplit ? 1 : 0);
     VG_LAUNCHED(1);
     return VG_OK;
 }
