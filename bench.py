@@ -234,6 +234,16 @@ def run_gpu(args):
     fam = prof.summary()
     gan._graph, gan.use_graph = saved
 
+    # second half of BASELINE.json's metric: sliding-window inference (config 5) through the public GanMonitor call, host volume
+    # in / host result out, windows sharded over the ranks
+    sliding = None
+    if not args.no_sliding and S == 128:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("vg_bench_configs", os.path.join(ROOT, "scripts", "bench_configs.py"))
+        bc = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bc)
+        torch.cuda.empty_cache()
+        sliding = bc.run_sliding(gen=gan.gen_IS, strategy=strategy, cases=((False, "512x512x256, 128^3 windows, stride 64, complete=False"),))[0]
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -279,6 +289,9 @@ def run_gpu(args):
                                    "d2h_bytes_per_step": int(64 * 8 * world), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roofline,
             "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    if sliding is not None:
+        line["sliding_window"] = {"value": sliding["Mvoxel_per_s"], "unit": "Mvoxel/s", "windows": sliding["windows"],
+                                  "seconds": sliding["seconds"], "gen_fwd_TFLOPs": sliding["gen_fwd_TFLOPs"], "workload": sliding["case"]}
     if world == 1 and not args.no_cpu_baseline:
         v, sec, cores, _tot = cpu_oracle_sample(S=64, steps=1, warmup=0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -295,6 +308,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--global-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sliding", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -13,69 +13,81 @@ namespace {
 
 constexpr int NT = 256;
 
+// A block walks whole output rows (n, d, h): the row decode is one 32-bit division chain per row instead of five 64-bit
+// divisions per 16-byte packet (the first version was instruction-bound at 39 % of HBM bandwidth).
 __global__ void __launch_bounds__(NT) upsample_concat_kernel(const bf16* __restrict__ lo, const bf16* __restrict__ skip,
                                                              bf16* __restrict__ out, int N, int D, int H, int W, int C0, int C1) {
-    const int C = C0 + C1, cg = C / 8, cg0 = C0 / 8;
+    const int C = C0 + C1, cg = C / 8, cg0 = C0 / 8, cg1 = cg - cg0;
     const int D2 = 2 * D, H2 = 2 * H, W2 = 2 * W;
-    size_t total = (size_t)N * D2 * H2 * W2 * cg;
-    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
-        int c8 = (int)(i % cg);
-        size_t v = i / cg;
-        int w = (int)(v % W2), h = (int)((v / W2) % H2), d = (int)((v / ((size_t)W2 * H2)) % D2);
-        int n = (int)(v / ((size_t)W2 * H2 * D2));
-        bf16x8 val;
-        if (c8 < cg0)
-            val = *reinterpret_cast<const bf16x8*>(lo + ((((size_t)n * D + (d >> 1)) * H + (h >> 1)) * W + (w >> 1)) * C0 + c8 * 8);
-        else
-            val = *reinterpret_cast<const bf16x8*>(skip + v * C1 + (c8 - cg0) * 8);
-        *reinterpret_cast<bf16x8*>(out + i * 8) = val;
+    const int rows = N * D2 * H2, per_row = W2 * cg;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int h = row % H2, r = row / H2;
+        const int d = r % D2, n = r / D2;
+        const uint4* lrow = reinterpret_cast<const uint4*>(lo + (((size_t)n * D + (d >> 1)) * H + (h >> 1)) * W * C0);
+        const uint4* srow = reinterpret_cast<const uint4*>(skip + (size_t)row * W2 * C1);
+        uint4* orow = reinterpret_cast<uint4*>(out + (size_t)row * W2 * C);
+        for (int i = threadIdx.x; i < per_row; i += NT) {
+            const int w = i / cg, c8 = i - w * cg;
+            orow[i] = c8 < cg0 ? __ldg(lrow + (w >> 1) * cg0 + c8) : __ldg(srow + w * cg1 + (c8 - cg0));
+        }
     }
 }
 
+// dlo[n,d,h,w] = sum of the 8 fine voxels' first C0 channels.  A block owns coarse rows (n, d, h).
 __global__ void __launch_bounds__(NT) upsample_concat_bwd_lo_kernel(const bf16* __restrict__ dcat, bf16* __restrict__ dlo, int N,
                                                                     int D, int H, int W, int C0, int C1) {
     const int C = C0 + C1, cg0 = C0 / 8;
     const int H2 = 2 * H, W2 = 2 * W, D2 = 2 * D;
-    size_t total = (size_t)N * D * H * W * cg0;
-    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
-        int c8 = (int)(i % cg0);
-        size_t v = i / cg0;
-        int w = (int)(v % W), h = (int)((v / W) % H), d = (int)((v / ((size_t)W * H)) % D);
-        int n = (int)(v / ((size_t)W * H * D));
-        float a[8];
+    const int rows = N * D * H, per_row = W * cg0;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int h = row % H, r = row / H;
+        const int d = r % D, n = r / D;
+        const bf16* src = dcat + (((size_t)n * D2 + 2 * d) * H2 + 2 * h) * W2 * C;
+        bf16* dst = dlo + (size_t)row * W * C0;
+        for (int i = threadIdx.x; i < per_row; i += NT) {
+            const int w = i / cg0, c8 = i - w * cg0;
+            uint4 pk[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) a[k] = 0.f;
+            for (int dz = 0; dz < 2; dz++)
 #pragma unroll
-        for (int dz = 0; dz < 2; dz++)
+                for (int dy = 0; dy < 2; dy++)
 #pragma unroll
-            for (int dy = 0; dy < 2; dy++)
+                    for (int dx = 0; dx < 2; dx++)
+                        pk[dz * 4 + dy * 2 + dx] =
+                            __ldg(reinterpret_cast<const uint4*>(src + (((size_t)dz * H2 + dy) * W2 + 2 * w + dx) * C + c8 * 8));
+            float a[8];
 #pragma unroll
-                for (int dx = 0; dx < 2; dx++) {
-                    float f[8];
-                    load8<bf16>(dcat + ((((size_t)n * D2 + 2 * d + dz) * H2 + 2 * h + dy) * W2 + 2 * w + dx) * C + c8 * 8, f);
+            for (int k = 0; k < 8; k++) a[k] = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) a[k] += f[k];
-                }
-        store8<bf16>(dlo + i * 8, a);
+            for (int q = 0; q < 8; q++) {
+                float f[8];
+                unpack8(pk[q], f);
+#pragma unroll
+                for (int k = 0; k < 8; k++) a[k] += f[k];
+            }
+            store8<bf16>(dst + (size_t)i * 8, a);
+        }
     }
 }
 
 __global__ void __launch_bounds__(NT) upsample_concat_bwd_skip_kernel(const bf16* __restrict__ dcat, bf16* __restrict__ dskip,
                                                                       size_t V2, int C0, int C1, int accumulate) {
     const int C = C0 + C1, cg1 = C1 / 8;
-    size_t total = V2 * cg1;
+    // voxel-major walk with 32-bit arithmetic inside chunks of 2^20 voxels
+    const size_t total = V2 * cg1;
     for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
-        int c8 = (int)(i % cg1);
-        size_t v = i / cg1;
-        float f[8];
-        load8<bf16>(dcat + v * C + C0 + c8 * 8, f);
+        const size_t v = i / (unsigned)cg1;
+        const int c8 = (int)(i - v * cg1);
+        uint4 p = __ldg(reinterpret_cast<const uint4*>(dcat + v * C + C0 + c8 * 8));
         if (accumulate) {
-            float o[8];
+            float f[8], o[8];
+            unpack8(p, f);
             load8<bf16>(dskip + i * 8, o);
 #pragma unroll
             for (int k = 0; k < 8; k++) f[k] += o[k];
+            p = pack8(f);
         }
-        store8<bf16>(dskip + i * 8, f);
+        reinterpret_cast<uint4*>(dskip)[i] = p;
     }
 }
 
@@ -284,8 +296,8 @@ unsigned long long vg_launch_count(void) { return g_vg_launches; }
 
 int vg_upsample_concat(const void* lo, const void* skip, void* out, int N, int D, int H, int W, int C0, int C1, void* stream) {
     VG_REQUIRE(lo && skip && out && C0 % 8 == 0 && C1 % 8 == 0 && N > 0);
-    size_t total = (size_t)N * 8 * D * H * W * ((C0 + C1) / 8);
-    upsample_concat_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>((const bf16*)lo, (const bf16*)skip, (bf16*)out,
+    VG_REQUIRE((long long)N * 4 * D * H < 0x7fffffffLL && (long long)2 * W * (C0 + C1) / 8 < 0x7fffffffLL);
+    upsample_concat_kernel<<<vg_grid_for((long long)N * 4 * D * H, 1, 16), NT, 0, (cudaStream_t)stream>>>((const bf16*)lo, (const bf16*)skip, (bf16*)out,
                                                                                        N, D, H, W, C0, C1); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
@@ -296,7 +308,8 @@ int vg_upsample_concat_bwd(const void* dcat, void* dlo, void* dskip, int accumul
     VG_REQUIRE(dcat && dlo && dskip && C0 % 8 == 0 && C1 % 8 == 0);
     cudaStream_t st = (cudaStream_t)stream;
     size_t t0 = (size_t)N * D * H * W * (C0 / 8), V2 = (size_t)N * 8 * D * H * W;
-    upsample_concat_bwd_lo_kernel<<<vg_grid_for(t0, NT, 16), NT, 0, st>>>((const bf16*)dcat, (bf16*)dlo, N, D, H, W, C0, C1); VG_LAUNCHED(1);
+    VG_REQUIRE((long long)N * D * H < 0x7fffffffLL);
+    upsample_concat_bwd_lo_kernel<<<vg_grid_for((long long)N * D * H, 1, 16), NT, 0, st>>>((const bf16*)dcat, (bf16*)dlo, N, D, H, W, C0, C1); VG_LAUNCHED(1);
     upsample_concat_bwd_skip_kernel<<<vg_grid_for(V2 * (C1 / 8), NT, 16), NT, 0, st>>>((const bf16*)dcat, (bf16*)dskip, V2, C0, C1,
                                                                                       accumulate_skip); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
