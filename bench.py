@@ -263,16 +263,19 @@ def run_gpu(args):
         if name.startswith("vg_conv3d"):
             conv_ms += v["ms"]
         if m:
-            kind, ci, co, st = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(5))
-            if ci % 16 == 0 and co % 16 == 0 and (kind == "dgrad" or st == 1):
+            kind, ci, co, kk, st = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4)), int(m.group(5))
+            k1_small = (ci, co) in ((48, 16), (96, 32), (16, 16), (32, 32))     # 1x1x1 forward shapes served by conv_small.cu
+            on_tc = kind == "dgrad" or kk >= 3 or (kk == 1 and st == 1 and not k1_small)
+            if ci % 16 == 0 and co % 16 == 0 and on_tc:
                 tc_ms += v["ms"]; tc_flop += v["work"]; tc_calls += v["calls"]
     achieved = tc_flop / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None
     ms_ref = ms_prof / psteps      # step time of the profiled (eager) pass: shares are taken against it
-    roofline = {"kernel": "tc_conv_kernel (tcgen05/TMEM implicit-GEMM Conv3D: stride-1 forward + all dgrads)", "bound": "tensor",
+    roofline = {"kernel": "tc_conv_kernel (tcgen05/TMEM implicit-GEMM Conv3D: stride-1/2 forward + all dgrads)", "bound": "tensor",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": (achieved / tf_peak) if achieved else None,
-                # one `ncu --set full` capture of this kernel on the 48->16 k3 layer at 8x128^3 (profiles/): dram read+write bytes
-                # of that launch; its algorithmic bytes (bf16 in + out) are 2.22e9
-                "traffic": 2.205e9, "traffic_launch": "fwd 48->16 k3 s1, 8x130^3 -> 8x128^3",
+                # one `ncu --set full` capture of this kernel (d-march, BD=8) on the 48->16 k3 layer at 8x128^3
+                # (profiles/r01_ncu_full_fwd_48-16_dmarch_call37.txt): dram read 1.6875 GB + write 0.5193 GB for that launch; its
+                # algorithmic bytes (bf16 in + out) are 2.22e9
+                "traffic": 2.2068e9, "traffic_launch": "fwd 48->16 k3 s1, 8x130^3 -> 8x128^3",
                 "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peak_src,
                 "calls_per_step": tc_calls / psteps, "share_of_step": tc_ms / psteps / ms_ref if ms_ref > 0 else None,
                 "conv_family_share_of_step": conv_ms / psteps / ms_ref if ms_ref > 0 else None,

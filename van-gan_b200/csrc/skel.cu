@@ -12,6 +12,8 @@
 // The backward pass walks the levels in reverse in gather form (no atomics): a per-window
 // winner index (first extreme in scan order) is recomputed in shared memory and every voxel
 // sums the upstream gradients of the windows it wins.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -215,6 +217,106 @@ skel_bwd_route_kernel(const float* __restrict__ ej, const float* __restrict__ a_
     }
 }
 
+// ------------------------------------------------------------------------------------------ z-marching level kernels
+// The tile kernels above spend their time on shared-memory window scans (19 + 27 loads per voxel plus the halo re-computation:
+// 58 LDS per output voxel, 20 % of the HBM model).  min / max are exact and associative, so the same bits come out of a
+// SEPARABLE evaluation:  erode = min(Pxy, Pxz, Pyz) with  rx = min3_x(e), ry = min3_y(e):
+//     Pxy = min3_y(rx),  Pxz = min3_z(rx),  Pyz = min3_z(ry);      dilate = max3_z(max3_y(max3_x(e1))).
+// A thread owns one (x, y) column and marches along z with the 3-deep z windows in registers; x neighbours come from warp
+// shuffles (a warp = 32 consecutive x, 28 outputs + halo 2), y neighbours from one shared-memory row exchange per plane
+// (three arrays, double-buffered, ONE barrier per plane).  Per plane and thread: 1 global load, 3 STS, 6 LDS, 4 SHFL.
+constexpr int MW_OUT = 28, MH_OUT = 16, M_ROWS = MH_OUT + 4, M_THREADS = 32 * M_ROWS;
+
+__global__ void __launch_bounds__(M_THREADS, 2)
+skel_level_fwd_march_kernel(const float* __restrict__ e_in, float* __restrict__ e_out, const float* __restrict__ skel_in,
+                            float* __restrict__ skel_out, Vol v, int tiles_x, int tiles_y, int zchunks, int ZL, int first) {
+    __shared__ float sV[2][M_ROWS + 2][32], sRX[2][M_ROWS + 2][32], sMX[2][M_ROWS + 2][32];
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    int t = blockIdx.x;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y; t /= tiles_y;
+    const int zc = t % zchunks;
+    const int n = t / zchunks;
+    const int gx = tx * MW_OUT - 2 + lane, gy = ty * MH_OUT - 2 + wy;
+    const int z0 = zc * ZL, zend = min(z0 + ZL, v.D);
+    const bool col_in = (unsigned)gx < (unsigned)v.W && (unsigned)gy < (unsigned)v.H;
+    const bool out_thread = col_in && lane >= 2 && lane < 30 && wy >= 2 && wy < M_ROWS - 2;
+    const size_t HW = (size_t)v.H * v.W;
+    const size_t col = (size_t)n * v.D * HW + (size_t)(col_in ? gy : 0) * v.W + (col_in ? gx : 0);
+    if (wy == 0) {
+        for (int b = 0; b < 2; b++) {
+            sV[b][0][lane] = INFINITY; sV[b][M_ROWS + 1][lane] = INFINITY;
+            sRX[b][0][lane] = INFINITY; sRX[b][M_ROWS + 1][lane] = INFINITY;
+            sMX[b][0][lane] = -INFINITY; sMX[b][M_ROWS + 1][lane] = -INFINITY;
+        }
+    }
+    auto loadv = [&](int pz) -> float {
+        return (col_in && pz >= 0 && pz < v.D && pz < zend + 2) ? __ldg(e_in + col + (size_t)pz * HW) : INFINITY;
+    };
+    float vnext = loadv(z0 - 2);
+    float v1 = INFINITY, v2 = INFINITY, v3 = INFINITY;          // e at planes pz-1, pz-2, pz-3
+    float rx1 = INFINITY, rx2 = INFINITY, ry1 = INFINITY, ry2 = INFINITY, rxy1 = INFINITY;
+    float e1_1 = -INFINITY, e1_2 = -INFINITY;                   // eroded image at planes pz-2, pz-3
+    float mxy3 = -INFINITY, mxy4 = -INFINITY, mx_prev = -INFINITY;
+    const unsigned FULL = 0xffffffffu;
+    for (int i = 0; i < ZL + 5; i++) {
+        const int pz = z0 - 2 + i, buf = i & 1, zo = pz - 3;
+        const float vA = vnext;
+        vnext = loadv(pz + 1);
+        const bool out_ok = out_thread && zo >= z0 && zo < zend;
+        float sp = 0.f;
+        if (out_ok && !first) sp = skel_in[col + (size_t)zo * HW];
+        const float rxA = fminf(vA, fminf(__shfl_up_sync(FULL, vA, 1), __shfl_down_sync(FULL, vA, 1)));
+        sV[buf][wy + 1][lane] = vA;
+        sRX[buf][wy + 1][lane] = rxA;
+        sMX[buf][wy + 1][lane] = mx_prev;
+        __syncthreads();
+        const float ryA = fminf(vA, fminf(sV[buf][wy][lane], sV[buf][wy + 2][lane]));
+        const float rxyA = fminf(rxA, fminf(sRX[buf][wy][lane], sRX[buf][wy + 2][lane]));
+        const float mxyC = fmaxf(mx_prev, fmaxf(sMX[buf][wy][lane], sMX[buf][wy + 2][lane]));   // plane pz-2
+        // eroded image at plane b = pz-1 (out-of-volume voxels must not take part in the dilation)
+        float e1b = fminf(rxy1, fminf(fminf(rx2, fminf(rx1, rxA)), fminf(ry2, fminf(ry1, ryA))));
+        if (!(col_in && pz - 1 >= 0 && pz - 1 < v.D)) e1b = -INFINITY;
+        const float mxb = fmaxf(e1b, fmaxf(__shfl_up_sync(FULL, e1b, 1), __shfl_down_sync(FULL, e1b, 1)));
+        if (out_ok) {
+            const float o = fmaxf(mxy4, fmaxf(mxy3, mxyC));
+            const float delta = fmaxf(__fsub_rn(v3, o), 0.f);
+            const float sk = first ? delta : __fadd_rn(sp, fmaxf(__fsub_rn(delta, __fmul_rn(sp, delta)), 0.f));
+            const size_t g = col + (size_t)zo * HW;
+            skel_out[g] = sk;
+            e_out[g] = e1_2;
+        }
+        v3 = v2; v2 = v1; v1 = vA;
+        rx2 = rx1; rx1 = rxA; ry2 = ry1; ry1 = ryA; rxy1 = rxyA;
+        e1_2 = e1_1; e1_1 = e1b;
+        mxy4 = mxy3; mxy3 = mxyC;
+        mx_prev = mxb;
+    }
+}
+
+// chunk length along z for the marching kernels: fill the resident-block slots evenly (2 blocks per SM) at a small halo cost
+inline int pick_zl(int D, long long columns, int halo_iters) {
+    int best = D;
+    double best_eff = 0.0;
+    for (int zl = 8; zl <= D; zl += 4) {
+        const long long blocks = columns * ((D + zl - 1) / zl);
+        const long long waves = (blocks + 295) / 296;
+        const double eff = ((double)blocks / (double)(waves * 296)) * ((double)zl / (double)(zl + halo_iters));
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = zl; }
+    }
+    if (D < 8) best = D;
+    return best;
+}
+// VG_SKEL=tile selects the shared-memory tile kernels (A/B testing and cross-checks)
+inline bool skel_march() {
+    static int m = -1;
+    if (m < 0) {
+        const char* e = getenv("VG_SKEL");
+        m = (e && e[0] == 't') ? 0 : 1;
+    }
+    return m == 1;
+}
+
 constexpr size_t ROUTE_SMEM = (size_t)(H2Z * H2Y * H2X + 2 * H1Z * H1Y * H1X) * sizeof(float) + 2 * H1Z * H1Y * H1X;
 
 inline void tiles_of(const Vol& v, int& tx, int& ty, int& tz) {
@@ -238,10 +340,19 @@ int vg_soft_skel_fwd(const float* x, float* E, float* S, int N, int D, int H, in
     int tx, ty, tz;
     tiles_of(v, tx, ty, tz);
     int blocks = tx * ty * tz * N;
+    const int mtx = vg_cdiv(W, MW_OUT), mty = vg_cdiv(H, MH_OUT);
+    const int ZL = pick_zl(D, (long long)N * mtx * mty, 5), zch = vg_cdiv(D, ZL);
     for (int j = 0; j <= iters; j++) {
-        skel_level_fwd_kernel<<<blocks, NTHREADS, 0, st>>>(E + (size_t)j * nv, E + (size_t)(j + 1) * nv,
-                                                          j ? S + (size_t)(j - 1) * nv : nullptr, S + (size_t)j * nv, v,
-                                                          tx, ty, tz, j == 0); VG_LAUNCHED(1);
+        if (skel_march()) {
+            skel_level_fwd_march_kernel<<<N * mtx * mty * zch, M_THREADS, 0, st>>>(E + (size_t)j * nv, E + (size_t)(j + 1) * nv,
+                                                                                  j ? S + (size_t)(j - 1) * nv : nullptr,
+                                                                                  S + (size_t)j * nv, v, mtx, mty, zch, ZL, j == 0);
+        } else {
+            skel_level_fwd_kernel<<<blocks, NTHREADS, 0, st>>>(E + (size_t)j * nv, E + (size_t)(j + 1) * nv,
+                                                              j ? S + (size_t)(j - 1) * nv : nullptr, S + (size_t)j * nv, v,
+                                                              tx, ty, tz, j == 0);
+        }
+        VG_LAUNCHED(1);
     }
     VG_CHECK_LAUNCH();
     return VG_OK;
@@ -270,17 +381,20 @@ int vg_soft_skel_bwd(const float* E, const float* S, const float* gskel, float* 
     auto Ej = [&](int j) { return E + (size_t)j * nv; };
     // a_j lives in Ab[j&1]; G_{j} (for j<k) in Gb[j&1]; D_j in Db[j&1]
     const float* Gcur = gskel;
-    skel_bwd_coeff_kernel<<<blocks, NTHREADS, 0, st>>>(Gcur, k ? S + (size_t)(k - 1) * nv : nullptr, Ej(k), Ej(k + 1),
-                                                       Ab[k & 1], Gb[(k + 1) & 1], v, tx, ty, tz, k == 0); VG_LAUNCHED(1);
+    // (a z-marching version of the coefficient kernel was measured slower than the tile kernel: 5 global accesses and one
+    // barrier per plane leave nothing to amortise -- 10.8 -> 13.3 ms at 256^3, iters 15 -- and was dropped)
+    auto coeff = [&](const float* Gin, const float* sprev, const float* e0, const float* e1, float* aout, float* gout, int first) {
+        skel_bwd_coeff_kernel<<<blocks, NTHREADS, 0, st>>>(Gin, sprev, e0, e1, aout, gout, v, tx, ty, tz, first);
+        VG_LAUNCHED(1);
+    };
+    coeff(Gcur, k ? S + (size_t)(k - 1) * nv : nullptr, Ej(k), Ej(k + 1), Ab[k & 1], Gb[(k + 1) & 1], k == 0);
     Gcur = Gb[(k + 1) & 1];  // now holds G_{k-1}
     skel_bwd_route_kernel<<<blocks, NTHREADS, ROUTE_SMEM, st>>>(Ej(k + 1), nullptr, nullptr, Ab[k & 1], Db[(k + 1) & 1], v, tx, ty,
                                                        tz); VG_LAUNCHED(1);
     for (int j = k; j >= 0; j--) {
         if (j >= 1) {
             int jj = j - 1;
-            skel_bwd_coeff_kernel<<<blocks, NTHREADS, 0, st>>>(Gcur, jj ? S + (size_t)(jj - 1) * nv : nullptr, Ej(jj),
-                                                               Ej(jj + 1), Ab[jj & 1], Gb[(jj + 1) & 1], v, tx, ty, tz,
-                                                               jj == 0); VG_LAUNCHED(1);
+            coeff(Gcur, jj ? S + (size_t)(jj - 1) * nv : nullptr, Ej(jj), Ej(jj + 1), Ab[jj & 1], Gb[(jj + 1) & 1], jj == 0);
             Gcur = Gb[(jj + 1) & 1];
         }
         float* out = j == 0 ? dx : Db[j & 1];

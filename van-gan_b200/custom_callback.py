@@ -99,9 +99,9 @@ class GanMonitor:
         call("vg_stitch_finalize", pred, cnt, H, W, D, xs, ys, zs, oH, oW, oD, out, mm, enc)
         call("vg_stitch_scale", out, out.numel(), mm)
         self.last_stats = dict(windows=len(starts), unique=len(set(starts)), local_windows=len(mine))
-        res = out.cpu().numpy()[..., None]
         if not complete:
-            res = res.astype("uint8")
+            out = out.to(torch.uint8)        # custom_callback.py:204-205 (astype('uint8')): cast on the device, 4x less D2H
+        res = out.cpu().numpy()[..., None]
         if output_path is not None and name is not None and rank == 0:
             np.save(os.path.join(output_path, "{name}.npy".format(name=name)), res)
         return res
