@@ -478,10 +478,12 @@ __global__ void __launch_bounds__(256) cin1_wgrad_tc_kernel(const float* __restr
     constexpr bool ONES = T < MT * 16;
     constexpr int SWZ_SH = NCHK == 8 ? 0 : (NCHK == 4 ? 1 : 2);
     extern __shared__ __align__(16) uint8_t c1w_smem[];
-    const int plane_elems = S * K * HB * WP;                // one split
-    uint16_t* xs = reinterpret_cast<uint16_t*>(c1w_smem);  // [3][S][K][HB][WP]
+    const int plane_elems = S * K * HB * WP;                // one split of one copy
+    // [2 copies][3 splits][S][K][HB][WP]: copy 0 holds P[i], copy 1 holds P[i+1], so that the element pair of ANY tap offset
+    // starts on an even index = one aligned 32-bit shared load (no funnel shift, no select)
+    uint16_t* xs = reinterpret_cast<uint16_t*>(c1w_smem);
     const uint32_t xs_u32 = sm_u32(c1w_smem);
-    const uint32_t dy_u32 = xs_u32 + (uint32_t)(3 * plane_elems * 2 + 15) / 16 * 16;   // [BH][OWp][NCHK] 16-byte chunks, swizzled
+    const uint32_t dy_u32 = xs_u32 + (uint32_t)(6 * plane_elems * 2 + 15) / 16 * 16;   // [BH][OWp][NCHK] 16-byte chunks, swizzled
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int ng = warp % NG, rw = warp / NG;
     // per-lane tap constants: element offset of the tap inside a split plane (row oh_l = 0, voxel 0), -1 = zero row, -2 = ones row
@@ -493,7 +495,8 @@ __global__ void __launch_bounds__(256) cin1_wgrad_tc_kernel(const float* __restr
             const int tap = mt * 16 + g + 8 * hf;
             if (tap < T) {
                 const int kw = tap % K, kh = (tap / K) % K, kd = tap / (K * K);
-                toff[mt][hf] = (((kw % S) * K + kd) * HB + kh) * WP + kw / S;
+                const int shf = kw / S;
+                toff[mt][hf] = (shf & 1) * 3 * plane_elems + (((kw % S) * K + kd) * HB + kh) * WP + (shf & ~1);
             } else toff[mt][hf] = (ONES && tap == T) ? -2 : -1;
         }
     float acc[MT][2][4];
@@ -527,21 +530,26 @@ __global__ void __launch_bounds__(256) cin1_wgrad_tc_kernel(const float* __restr
             const int xd = od * S + d, xh = oh0 * S + h;
             const bool rok = xh < IH;   // xd < ID always (od < OD)
             const float* xr = x + (((size_t)n * ID + xd) * IH + (rok ? xh : 0)) * IW;
-            float v[2 * S];
+            float v[3 * S];
 #pragma unroll
-            for (int e = 0; e < 2 * S; e++) {
+            for (int e = 0; e < 3 * S; e++) {
                 const int w = 2 * S * pi + e;
                 v[e] = (rok && w < IW) ? __ldg(xr + w) : 0.f;
             }
 #pragma unroll
             for (int par = 0; par < S; par++) {
-                uint32_t h0, m0, l0, h1, m1, l1;
+                uint32_t h0, m0, l0, h1, m1, l1, h2, m2, l2;
                 split3(v[par], h0, m0, l0);
                 split3(v[par + S], h1, m1, l1);
+                split3(v[par + 2 * S], h2, m2, l2);
                 uint32_t* dst = reinterpret_cast<uint32_t*>(xs + ((par * K + d) * HB + h) * WP + 2 * pi);
-                dst[0] = h0 | (h1 << 16);
+                dst[0] = h0 | (h1 << 16);                       // copy 0: (P[2pi], P[2pi+1])
                 dst[plane_elems / 2] = m0 | (m1 << 16);
                 dst[plane_elems] = l0 | (l1 << 16);
+                uint32_t* dso = dst + 3 * plane_elems / 2;      // copy 1: (P[2pi+1], P[2pi+2])
+                dso[0] = h1 | (h2 << 16);
+                dso[plane_elems / 2] = m1 | (m2 << 16);
+                dso[plane_elems] = l1 | (l2 << 16);
             }
         }
         cpa_wait<0>();
@@ -563,12 +571,9 @@ __global__ void __launch_bounds__(256) cin1_wgrad_tc_kernel(const float* __restr
                     for (int hf = 0; hf < 2; hf++) {
                         const int to = toff[mt][hf];
                         if (to >= 0) {
-                            const uint16_t* pl = xs + sp * plane_elems + to + rbase;
-                            const int odd = (to + rbase) & 1;
-                            const uint32_t* wp0 = reinterpret_cast<const uint32_t*>(pl - odd);
-                            const uint32_t lo0 = wp0[0], hi0 = wp0[1], lo1 = wp0[4], hi1 = wp0[5];
-                            a[hf] = odd ? __funnelshift_r(lo0, hi0, 16) : lo0;
-                            a[hf + 2] = odd ? __funnelshift_r(lo1, hi1, 16) : lo1;
+                            const uint32_t* wp0 = reinterpret_cast<const uint32_t*>(xs + sp * plane_elems + to + rbase);   // even index
+                            a[hf] = wp0[0];
+                            a[hf + 2] = wp0[4];
                         } else {
                             a[hf] = a[hf + 2] = (to == -2 && sp == 0) ? 0x3F803F80u : 0u;
                         }
@@ -608,7 +613,7 @@ int launch_cin1_wgrad_tc(const float* x, const bf16* dy, float* dw, float* dbias
     const int OWp = (OW + 15) / 16 * 16;
     const int WP = (OWp + (K - 1) / S + 2 + 1) & ~1;
     if ((IW + S - 1) / S + 1 > WP) return VG_ERR_UNSUPPORTED;
-    const size_t planes = ((size_t)3 * S * K * HB * WP * 2 + 15) / 16 * 16;
+    const size_t planes = ((size_t)6 * S * K * HB * WP * 2 + 15) / 16 * 16;
     size_t smem = planes + (size_t)BH * OWp * NCHK * 16;
     const size_t red = (size_t)8 * MT * 16 * 16 * 4;
     if (smem < red) smem = red;
