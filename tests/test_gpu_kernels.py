@@ -175,6 +175,8 @@ CONV_CASES = [
     (32, 32, 1, 1, (6, 6, 7), 1), (1, 64, 4, 2, (19, 21, 40), 2), (512, 1, 3, 1, (5, 6, 9), 1), (16, 1, 1, 1, (33, 5, 7), 1),
     # more work items than SMs: persistent tcgen05 CTAs re-use their (zeroed) TMEM buffers and run several d-march bricks
     (16, 16, 3, 1, (34, 34, 66), 3), (32, 32, 3, 1, (34, 34, 34), 5),
+    # fused parity-class stride-2 dgrad (Cin 16 / 32): two N blocks, k4 taps, odd extents
+    (32, 64, 3, 2, (11, 9, 13), 1), (16, 32, 4, 2, (10, 12, 14), 1), (16, 32, 3, 2, (34, 18, 35), 2),
 ]
 
 

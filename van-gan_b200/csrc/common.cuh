@@ -143,7 +143,9 @@ int vg_tc_ncta(int ncols, int T);
 size_t vg_tc_pack_elems(int ncols, int K_total, int T);
 int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf16* wpack, void* y, const float* bias, int YD, int YH,
                  int YW, int Cy, int GD, int GH, int GW, int TD, int TH, int TW, int st, int oso, int ood, int ooh, int oow, int act,
-                 cudaStream_t stream, int goff = 0, int ss = 1);
+                 cudaStream_t stream, int goff = 0, int ss = 1, int cls_cin = 0);
+bool vg_tc_s2dgrad_ok(int K, int stride, int Cin, int Cout);
+size_t vg_tc_s2dgrad_elems(int Cin, int Cout);
 int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, int dgrad, int ad, int ah, int aw, int td, int th,
                int tw, cudaStream_t st);
 // tensor-core (tcgen05) weight-gradient path, wgrad_tc.cu

@@ -833,6 +833,7 @@ size_t vg_conv3d_packed_bytes(const vg_conv3d_desc* d, int for_dgrad) {
         for (int a = 0; a < d->stride; a++)
             for (int b = 0; b < d->stride; b++)
                 for (int c = 0; c < d->stride; c++) bytes += rup256(tc_dgrad_class_elems(d, a, b, c) * 2);
+    if (tc_dgrad_ok(d) && vg_tc_s2dgrad_ok(d->K, d->stride, d->Cin, d->Cout)) bytes += rup256(vg_tc_s2dgrad_elems(d->Cin, d->Cout) * 2);
     return bytes;
 }
 
@@ -868,6 +869,9 @@ int vg_conv3d_pack_weights(const vg_conv3d_desc* d, const float* w, void* w_fwd,
                         return VG_ERR_CUDA;
                     dst += rup256(el * 2);
                 }
+        if (vg_tc_s2dgrad_ok(d->K, s_, d->Cin, d->Cout) &&
+            vg_tc_pack(w, (bf16*)dst, d->K, s_, d->Cin, d->Cout, 3, 0, 0, 0, 2, 2, 2, st) != VG_OK)   // fused classes, after the class packs
+            return VG_ERR_CUDA;
     }
     VG_CHECK_LAUNCH();
     return VG_OK;
@@ -960,6 +964,17 @@ int vg_conv3d_dgrad(const vg_conv3d_desc* d, const void* dy, const void* w_dgrad
     size_t woff = 0;
     const bool use_tc = tc_enabled() && tc_dgrad_ok(d) && d->x_dtype == VG_BF16;
     const char* wtc = (const char*)w_dgrad + rup256(mma_dgrad_elems(d) * 2);
+    if (use_tc && vg_tc_s2dgrad_ok(d->K, s, d->Cin, d->Cout)) {
+        const char* wf = wtc;
+        for (int a = 0; a < s; a++)
+            for (int b = 0; b < s; b++)
+                for (int c = 0; c < s; c++) wf += rup256(tc_dgrad_class_elems(d, a, b, c) * 2);
+        // one launch over the class grid p' (p = 2p' + a): 2x2x2 taps (zero weights where a + 2t' >= K), columns = (class, ci)
+        int rc = vg_tc_launch((const bf16*)dy, d->N, OD, OH, OW, d->Cout, (const bf16*)wf, dx, nullptr, d->ID, d->IH, d->IW, d->Cin,
+                              (d->ID + 1) / 2, (d->IH + 1) / 2, (d->IW + 1) / 2, 2, 2, 2, -1, 2, 0, 0, 0, VG_ACT_NONE, st, 0, 1, d->Cin);
+        if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
+        if (rc != VG_ERR_UNSUPPORTED) return rc;
+    }
     for (int ad = 0; ad < s; ad++)
         for (int ah = 0; ah < s; ah++)
             for (int aw = 0; aw < s; aw++) {

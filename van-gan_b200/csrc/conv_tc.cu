@@ -57,6 +57,7 @@ struct TcParams {
     int ED, EH, EW;
     int ss, cpc;   // source stride (1, or 2 = stride-2 forward as 8 parity classes of 2x2x2 taps) and 16-channel chunks per class
     int goff;   // origin of the output grid inside the output tensor (cropped dgrad); applied to source and output coordinates
+    int cls_cin;  // fused stride-2 dgrad: the GEMM columns are (parity class, input channel); cls_cin = Cin, 0 = off
     int dsplit;   // d-split: the kd taps become extra K-chunks (chunk = (kd, 16 channels)), each staging a BD-slice brick shifted by kd
     int dm_order[12];   // d-march: issue order of the source slices (overlapping TMEM windows kept >= 3 instructions apart)
     int dm;   // d-march: the TD taps along d are folded into the MMA N dimension (N = cnt * NCTA, sliding TMEM window)
@@ -438,6 +439,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 const int m = u / nb16, n0 = (u - m * nb16) << 4;
                 const int gd = bd * BD + m, yd = gd * p.oso + p.ood;
                 const int col0 = nb * p.NCTA + n0;
+                if (p.cls_cin) {
+                    // fused parity classes (stride-2 dgrad): column block -> (class, first channel); the class is the output offset
+                    const int cls = col0 / p.cls_cin, ci0 = col0 - cls * p.cls_cin;
+                    const int zd = 2 * gd + ((cls >> 2) & 1), zh = 2 * gh + ((cls >> 1) & 1), zw = 2 * gw + (cls & 1);
+                    if (cls >= 8 || gd >= p.GD || gh >= p.GH || gw >= p.GW || zd >= p.YD || zh >= p.YH || zw >= p.YW) return;
+                    uint32_t o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) o[j] = pack2_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    bf16* dst = (bf16*)p.y + ((((size_t)n * p.YD + zd) * p.YH + zh) * p.YW + zw) * p.Cy + ci0;
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                                 "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                    return;
+                }
                 if (!(row_ok && gd < p.GD && yd < p.YD && col0 < p.Cy)) return;
                 float f[16];
                 const float4* sb = reinterpret_cast<const float4*>(sbias + col0);
@@ -554,6 +568,22 @@ int vg_tc_ncta(int ncols, int T) {
     return best;
 }
 
+// Fused stride-2 dgrad (all 8 parity classes of a k3/k4 s2 layer as the N dimension of one launch): used for narrow layers, where a
+// class alone gives N = Cin = 16 or 32 columns per MMA (39-40 cycles for 8-16 cycles of math) and 8 launches re-stage the same dy brick.
+bool vg_tc_s2dgrad_ok(int K, int stride, int Cin, int Cout) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("VG_TC_S2FUSED");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    // k4 layers with >= 64 channels keep the per-class d-march launches (N = 128 there already)
+    return on && stride == 2 && Cin % 16 == 0 && Cout % 16 == 0 && ((K == 3 && Cin <= 128) || (K == 4 && Cin <= 32));
+}
+size_t vg_tc_s2dgrad_elems(int Cin, int Cout) {
+    const int ncols = 8 * Cin, nblk = (ncols + 127) / 128;
+    return (size_t)nblk * (Cout / 16) * 8 * 2 * 128 * 8;
+}
+
 size_t vg_tc_pack_elems(int ncols, int K_total, int T) {
     int ncta = vg_tc_ncta(ncols, T);
     if (!ncta || K_total % 16) return 0;
@@ -565,10 +595,11 @@ size_t vg_tc_pack_elems(int ncols, int K_total, int T) {
 // Returns VG_ERR_UNSUPPORTED when the shape does not fit (caller falls back to the mma.sync path).
 int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf16* wpack, void* y, const float* bias, int YD, int YH,
                  int YW, int Cy, int GD, int GH, int GW, int TD, int TH, int TW, int st, int oso, int ood, int ooh, int oow, int act,
-                 cudaStream_t stream, int goff, int ss) {
+                 cudaStream_t stream, int goff, int ss, int cls_cin) {
     const int TD_full = TD;
     const bool dsplit = ss == 1 && vg_tc_dsplit(Cy, TD, TH, TW);
-    const int ncta = dsplit ? 64 : vg_tc_ncta(Cy, TD * TH * TW);
+    const int ncols = cls_cin ? 8 * cls_cin : Cy;   // GEMM columns
+    const int ncta = cls_cin ? 128 : (dsplit ? 64 : vg_tc_ncta(Cy, TD * TH * TW));
     if (dsplit) TD = 1;   // the kernel sees a (1, TH, TW) filter and TD_full x as many K-chunks
     const int T = TD * TH * TW;
     if (!ncta || Cx % 16) return VG_ERR_UNSUPPORTED;
@@ -597,12 +628,13 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
     p.TD = TD; p.TH = TH; p.TW = TW; p.st = st;
     p.goff = goff;
     p.oso = oso; p.ood = ood + goff * oso; p.ooh = ooh + goff * oso; p.oow = oow + goff * oso;
-    p.NCTA = ncta; p.nblk = (Cy + ncta - 1) / ncta;
+    p.NCTA = ncta; p.nblk = (ncols + ncta - 1) / ncta;
+    p.cls_cin = cls_cin;
     p.act = act;
     p.EH = MH + TH - 1; p.EW = MW + TW - 1;
     p.wstage_bytes = (uint32_t)T * 2 * ncta * 16;
     const size_t smem_cap = 220 * 1024;
-    p.dm = vg_tc_dmarch(ncta, TD) ? 1 : 0;
+    p.dm = (!cls_cin && vg_tc_dmarch(ncta, TD)) ? 1 : 0;
     static int bd_max = -1;   // d-march amortises its TD-1 edge slices over BD tiles: deeper bricks pay (VG_TC_BD overrides)
     if (bd_max < 0) {
         const char* e = getenv("VG_TC_BD");
@@ -688,7 +720,8 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
 __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int K, int stride, int Cin, int Cout, int dgrad,
                                int ad, int ah, int aw, int td, int th, int tw, int ncta, int nblk, int dm, int dsplit) {
     const int T = dsplit ? th * tw : td * th * tw;
-    const int Kt = dgrad == 1 ? Cout : Cin, ncols = dgrad == 1 ? Cin : Cout;
+    // dgrad == 3: fused stride-2 parity classes -- columns are (class, ci), every class padded to 2x2x2 taps
+    const int Kt = (dgrad == 1 || dgrad == 3) ? Cout : Cin, ncols = dgrad == 1 ? Cin : (dgrad == 3 ? 8 * Cin : Cout);
     const int cpc = Kt / 16;
     const int nchunks = (dgrad == 2 ? 8 : (dsplit ? td : 1)) * cpc;
     size_t total = (size_t)nblk * nchunks * T * 2 * ncta * 8;
@@ -724,10 +757,16 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ o
             k = cc * 16 + kh * 8 + j;
             kd = dgrad ? ad + stride * d_ : d_; kh2 = dgrad ? ah + stride * h_ : h_; kw = dgrad ? aw + stride * w_ : w_;
         }
+        int ci = col;
+        if (dgrad == 3) {
+            const int cls = col / Cin;
+            ci = col - cls * Cin;
+            kd = ((cls >> 2) & 1) + 2 * d_; kh2 = ((cls >> 1) & 1) + 2 * h_; kw = (cls & 1) + 2 * w_;
+        }
         int tap = (kd * K + kh2) * K + kw;
         float v = 0.f;
         if (col < ncols && kd < K && kh2 < K && kw < K)
-            v = dgrad == 1 ? w[((size_t)tap * Cin + col) * Cout + k] : w[((size_t)tap * Cin + k) * Cout + col];
+            v = (dgrad == 1 || dgrad == 3) ? w[((size_t)tap * Cin + ci) * Cout + k] : w[((size_t)tap * Cin + k) * Cout + col];
         out[i] = __float2bfloat16(v);
     }
 }
@@ -735,14 +774,14 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ o
 int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, int dgrad, int ad, int ah, int aw, int td, int th,
                int tw, cudaStream_t st) {
     const int T = td * th * tw;
-    const int ncols = dgrad == 1 ? Cin : Cout;
-    const bool dsplit = dgrad != 2 && stride == 1 && vg_tc_dsplit(ncols, td, th, tw);
-    const int ncta = dsplit ? 64 : vg_tc_ncta(ncols, T);
+    const int ncols = dgrad == 1 ? Cin : (dgrad == 3 ? 8 * Cin : Cout);
+    const bool dsplit = dgrad != 2 && dgrad != 3 && stride == 1 && vg_tc_dsplit(ncols, td, th, tw);
+    const int ncta = dgrad == 3 ? 128 : (dsplit ? 64 : vg_tc_ncta(ncols, T));
     if (!ncta) return VG_ERR_UNSUPPORTED;
     const int nblk = (ncols + ncta - 1) / ncta;
-    size_t total = vg_tc_pack_elems(ncols, dgrad == 1 ? Cout : (dgrad == 2 ? 8 * Cin : Cin), T);
+    size_t total = dgrad == 3 ? vg_tc_s2dgrad_elems(Cin, Cout) : vg_tc_pack_elems(ncols, dgrad == 1 ? Cout : (dgrad == 2 ? 8 * Cin : Cin), T);
     tc_pack_kernel<<<vg_grid_for((long long)total, 256, 4), 256, 0, st>>>(w, out, K, stride, Cin, Cout, dgrad, ad, ah, aw, td, th, tw, ncta,
-                                                                          nblk, vg_tc_dmarch(ncta, td) ? 1 : 0, dsplit ? 1 : 0);
+                                                                          nblk, (dgrad != 3 && vg_tc_dmarch(ncta, td)) ? 1 : 0, dsplit ? 1 : 0);
     VG_LAUNCHED(1);
     return VG_OK;
 }
