@@ -176,7 +176,7 @@ CONV_CASES = [
     # more work items than SMs: persistent tcgen05 CTAs re-use their (zeroed) TMEM buffers and run several d-march bricks
     (16, 16, 3, 1, (34, 34, 66), 3), (32, 32, 3, 1, (34, 34, 34), 5),
     # fused parity-class stride-2 dgrad (Cin 16 / 32): two N blocks, k4 taps, odd extents
-    (32, 64, 3, 2, (11, 9, 13), 1), (16, 32, 4, 2, (10, 12, 14), 1), (16, 32, 3, 2, (34, 18, 35), 2),
+    (32, 64, 3, 2, (11, 9, 13), 1), (16, 32, 4, 2, (10, 12, 14), 1), (16, 32, 3, 2, (34, 18, 35), 2), (128, 256, 3, 2, (9, 7, 11), 2),
 ]
 
 

@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_base + 16 * p.stages + 32);
     const uint32_t sbase = s_addr(smem);
     float* sbias = reinterpret_cast<float*>(bar_base + 128);   // bias of all nblk * NCTA (padded) output columns
-    for (int i = threadIdx.x; i < p.nblk * p.NCTA; i += TC_THREADS) sbias[i] = (p.bias && i < p.Cy) ? p.bias[i] : 0.f;
+    if (!p.cls_cin)   // the fused-class epilogue has no bias (and up to 1024 columns: they would not fit the tail)
+        for (int i = threadIdx.x; i < p.nblk * p.NCTA; i += TC_THREADS) sbias[i] = (p.bias && i < p.Cy) ? p.bias[i] : 0.f;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; s++) {
@@ -630,6 +631,7 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
     p.oso = oso; p.ood = ood + goff * oso; p.ooh = ooh + goff * oso; p.oow = oow + goff * oso;
     p.NCTA = ncta; p.nblk = (ncols + ncta - 1) / ncta;
     p.cls_cin = cls_cin;
+    if (!cls_cin && (size_t)p.nblk * ncta * sizeof(float) + 128 > (size_t)TC_TAIL) return VG_ERR_UNSUPPORTED;   // bias copy lives in the tail
     p.act = act;
     p.EH = MH + TH - 1; p.EW = MW + TW - 1;
     p.wstage_bytes = (uint32_t)T * 2 * ncta * 16;
