@@ -347,8 +347,16 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
     p.M = p.CC == 16 ? 64 : 128;
     p.R = p.M / p.CC;
     p.PLC = p.CC / 8;
+    // co block: 128 at most.  A 256-wide block is never td-folded (K*CO > 256), so it only halves the taps a CTA can keep in TMEM
+    // (512 columns) and every CTA then streams all of X and dY for two taps: L2 traffic per tile ~ (CB + CO), i.e. 1.5x more at
+    // CO = 256 than at CO = 128, where the MMA already runs at the N >= 128 issue floor (VG_WG_CO256=1 restores the old choice).
+    static int co256 = -1;
+    if (co256 < 0) {
+        const char* e = getenv("VG_WG_CO256");
+        co256 = (e && e[0] == '1') ? 1 : 0;
+    }
     const int cos[5] = {256, 128, 64, 32, 16};
-    p.CO = largest_div(Cy, cos, 5);
+    p.CO = (co256 || stride == 2) ? largest_div(Cy, cos, 5) : largest_div(Cy, cos + 1, 4);   // measured: 256->512 k4 s1 0.96 -> 0.69 ms, 128->256 k4 s2 0.51 -> 0.55 ms (kept at 256)
     p.NPLy = p.CO / 8;
     p.NF = (stride == 1 && K > 1 && K * p.CO <= 256) ? K : 1;
     p.Nmma = p.NF * p.CO;
