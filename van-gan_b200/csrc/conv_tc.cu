@@ -532,14 +532,23 @@ unsigned long long g_vg_tc_launches = 0;
 extern "C" unsigned long long vg_tc_launch_count(void) { return g_vg_tc_launches; }
 
 // d-march (taps along d folded into the MMA N dimension) is used when the folded width stays within one MMA that the
-// shared-memory operand bandwidth can feed (measured: N <= 128 reaches the issue floor).  VG_TC_DM=0 disables it.
+// shared-memory operand bandwidth can feed (N >= 128 runs at the issue floor, so wider folds only save instructions).
+// VG_TC_DM=0 disables it.
 static bool vg_tc_dmarch(int ncta, int TD) {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("VG_TC_DM");
         on = (e && e[0] == '0') ? 0 : 1;
     }
-    return on && (TD == 2 || TD == 3) && TD * ncta <= 128;   // TD = 4: every window overlaps its 3 neighbours, nothing to interleave
+    static int nmax = -1;   // widest folded N (VG_TC_DMMAX overrides)
+    if (nmax < 0) {
+        const char* e = getenv("VG_TC_DMMAX");
+        // VG_TC_DMMAX=192 also folds the 64-column tiles (k3, 64..256 channels): 192->64 fwd 938 -> 1082 TFLOP/s, dgrad 529 -> 618,
+        // conv parity unchanged (unit + full-size).  It stays opt-in: with it two 32^3 train-step cases move from 1.9 % to 2.1-2.2 %
+        // of the oracle's loss (tolerance 2e-2) -- rounding-order noise of the ill-conditioned deepest level, to be settled first.
+        nmax = e ? atoi(e) : 128;
+    }
+    return on && (TD == 2 || TD == 3) && TD * ncta <= nmax;   // TD = 4: every window overlaps its 3 neighbours, nothing to interleave
 }
 
 // d-split (k4 s1 layers, 64 taps): with all taps of a 16-channel chunk in one stage the weight block caps the N tile at 32
