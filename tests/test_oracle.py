@@ -193,3 +193,74 @@ def test_vnet_oracle_matches_reference_parameter_count_and_shapes():
     ym = ON.vnet_forward(P, x, 3, masks=ON.make_vnet_masks(np.random.default_rng(1), 1, 16, 3))
     assert y0.shape == x.shape and torch.equal(y0, y1) and float(y0.abs().max()) <= 1.0
     assert not torch.allclose(y0, ym)
+
+
+def test_conv_and_norm_against_independent_numpy_restatement():
+    """The oracle's Conv3D / InstanceNormalization / UpSampling3D against a second restatement written with numpy only
+    (sliding_window_view + einsum; explicit moments): Keras kernel layout (kd,kh,kw,Cin,Cout), VALID and strided, NDHWC."""
+    from numpy.lib.stride_tricks import sliding_window_view
+    rng = np.random.default_rng(21)
+    for (cin, cout, k, s, sp) in [(3, 5, 3, 1, (6, 7, 8)), (4, 2, 4, 2, (10, 8, 12)), (2, 3, 1, 2, (5, 6, 7))]:
+        x = rng.standard_normal((2,) + sp + (cin,))
+        w = rng.standard_normal((k, k, k, cin, cout))
+        b = rng.standard_normal(cout)
+        win = sliding_window_view(x, (k, k, k), axis=(1, 2, 3))[:, ::s, ::s, ::s]     # (N, OD, OH, OW, Cin, kd, kh, kw)
+        ref = np.einsum("ndhwcijk,ijkco->ndhwo", win, w) + b
+        got = ON.conv3d(torch.tensor(x), torch.tensor(w), torch.tensor(b), stride=s).numpy()
+        assert got.shape == ref.shape
+        assert np.allclose(got, ref, rtol=1e-10, atol=1e-10), (cin, cout, k, s)
+    x = rng.standard_normal((2, 4, 5, 6, 3)) * 2 + 1
+    g, bt = rng.standard_normal(3), rng.standard_normal(3)
+    mu = x.mean(axis=(1, 2, 3), keepdims=True)
+    var = ((x - mu) ** 2).mean(axis=(1, 2, 3), keepdims=True)                          # biased, eps = 1e-3 (tfa default)
+    ref = g * (x - mu) / np.sqrt(var + 1e-3) + bt
+    got = ON.instance_norm(torch.tensor(x), torch.tensor(g), torch.tensor(bt)).numpy()
+    assert np.allclose(got, ref, rtol=1e-10, atol=1e-10)
+    up = ON.upsample2(torch.tensor(x)).numpy()
+    assert np.array_equal(up, x.repeat(2, 1).repeat(2, 2).repeat(2, 3))
+
+
+def test_instance_norm_gradient_properties_fp64():
+    """Two analytic identities of y = gamma * xhat + beta, xhat = (x - mu) * rsqrt(var + eps), for ANY upstream gradient u:
+    sum dx = 0 per (sample, channel), and  sum dx * xhat = gamma * rstd * (sum u * xhat) * eps / (var + eps)  -- the second one
+    vanishes only for eps = 0, so it pins where the 1e-3 of tfa's InstanceNormalization enters."""
+    rng = np.random.default_rng(22)
+    x = torch.tensor(rng.standard_normal((2, 5, 4, 6, 3)), dtype=torch.float64, requires_grad=True)
+    g = torch.tensor(1 + 0.3 * rng.standard_normal(3), dtype=torch.float64)
+    b = torch.tensor(rng.standard_normal(3), dtype=torch.float64)
+    up = torch.tensor(rng.standard_normal((2, 5, 4, 6, 3)), dtype=torch.float64)
+    ON.instance_norm(x, g, b).backward(up)
+    dx = x.grad
+    assert float(dx.sum(dim=(1, 2, 3)).abs().max()) < 1e-12
+    xd = x.detach()
+    mu = xd.mean(dim=(1, 2, 3), keepdim=True)
+    var = ((xd - mu) ** 2).mean(dim=(1, 2, 3), keepdim=True)
+    rstd = 1.0 / torch.sqrt(var + 1e-3)
+    xhat = (xd - mu) * rstd
+    lhs = (dx * xhat).sum(dim=(1, 2, 3))
+    rhs = (g * rstd * (up * xhat).sum(dim=(1, 2, 3), keepdim=True) * 1e-3 / (var + 1e-3)).reshape(lhs.shape)
+    assert float((lhs - rhs).abs().max()) < 1e-12 * max(1.0, float(rhs.abs().max()))
+    assert float(rhs.abs().max()) > 1e-6          # the identity is not vacuous
+
+
+def test_keras_bce_and_lsgan_known_values():
+    """Closed-form values of the Keras BCE branch (clip to [1e-7, 1-1e-7], log(p + 1e-7)) and of the LSGAN terms."""
+    cfg = OL.make_cfg(1, 1)
+    ones = torch.ones((1, 2, 2, 2, 1))
+    zeros = torch.zeros((1, 2, 2, 2, 1))
+    # generator: MSE(1, D(fake)) with D(fake) = 0 -> 1;  discriminator: 0.5 * (MSE(1, real=1) + MSE(0, fake=1)) = 0.5
+    assert abs(float(OL.generator_loss_fn(cfg, zeros)) - 1.0) < 1e-7
+    assert abs(float(OL.discriminator_loss_fn(cfg, ones, ones)) - 0.5) < 1e-7
+    # bce cycle loss on a two-level volume: after per-sample min-max both tensors are {0,1}; identical -> -log(1 + 1e-7 - 1e-7)
+    v = torch.tensor([0.0, 1.0] * 4).reshape(1, 2, 2, 2, 1) * 2 - 1
+    same = float(OL.cycle_loss(cfg, v, v.clone(), typ="bce"))
+    expect_same = -np.log(1 - 1e-7 + 1e-7) * 10.0
+    assert abs(same - expect_same) < 1e-5
+    flipped = float(OL.cycle_loss(cfg, v, -v, typ="bce"))                              # every voxel maximally wrong
+    # fp32 like TF: y=1 voxels give -log(clip(0) + eps) = -log(2e-7); y=0 voxels -log(1 - clip(1) + eps), where 1 - 1e-7 rounds
+    # to 1 - 2^-23 in fp32, i.e. -log(1.19e-7 + 1e-7): half the voxels each
+    f = np.float32
+    t1 = -np.log(f(1e-7) + f(1e-7))
+    t0 = -np.log((f(1) - f(f(1) - f(1e-7))) + f(1e-7))
+    expect_flip = 10.0 * 0.5 * (float(t1) + float(t0))
+    assert abs(flipped - expect_flip) < 1e-4 * expect_flip
