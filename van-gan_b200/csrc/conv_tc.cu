@@ -60,6 +60,7 @@ struct TcParams {
     int cls_cin;  // fused stride-2 dgrad: the GEMM columns are (parity class, input channel); cls_cin = Cin, 0 = off
     int dsplit;   // d-split: the kd taps become extra K-chunks (chunk = (kd, 16 channels)), each staging a BD-slice brick shifted by kd
     int dm_order[12];   // d-march: issue order of the source slices (overlapping TMEM windows kept >= 3 instructions apart)
+    int dm_lean;  // d-march issue loop driven by a per-slice table in shared memory (VG_TC_DMLEAN=1; not yet validated on a GPU)
     int dm;   // d-march: the TD taps along d are folded into the MMA N dimension (N = cnt * NCTA, sliding TMEM window)
     int stages, act, use_tma, dbg;   // dbg: bit0 = skip brick/weight loads, bit1 = skip MMA issue (timing experiments only)
     const bf16* x;        // source tensor (gather loader)
@@ -324,6 +325,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         const uint32_t b_step = (2 * lbo_b) >> 4;
         const int sgn = p.st > 0 ? 1 : -1;
         const int aoff0 = p.st > 0 ? 0 : ((p.TD - 1) * p.EH + (p.TH - 1)) * p.EW + (p.TW - 1);
+        // lean d-march: everything that depends only on the slice (A offset, B offset, first TMEM column, instruction descriptor)
+        // is computed once, one table entry per issue position; the issue loop then costs one LDS.128 and two adds per MMA
+        uint4* s_dm = reinterpret_cast<uint4*>(bar_base + TC_TAIL - 192);
+        if (p.dm && p.dm_lean) {
+            const int EDl = BD + p.TD - 1;
+            if (lane < EDl) {
+                const int sl = p.dm_order[lane];
+                const int m_lo = sl - p.TD + 1 > 0 ? sl - p.TD + 1 : 0;
+                const int m_hi = sl < BD - 1 ? sl : BD - 1;
+                const uint32_t ncols = (uint32_t)((m_hi - m_lo + 1) * p.NCTA);
+                s_dm[lane] = make_uint4((uint32_t)(sl * tile_step), (uint32_t)((p.TD - 1 - sl + m_lo) * p.NCTA), (uint32_t)(m_lo * p.NCTA),
+                                        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24) | ((ncols >> 3) << 17));
+            }
+            __syncwarp();
+        }
         for (int wk = blockIdx.x; wk < p.nwork; wk += gridDim.x, it++) {
             const int buf = it & 1;
             // d-march: the epilogue hands every buffer over ZEROED (and pre-arrives once at start), so use n waits for completion n
@@ -349,6 +365,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                     const int ED = BD + p.TD - 1;
                     int aoff_q = p.st > 0 ? 0 : (p.TH - 1) * p.EW + (p.TW - 1);
                     uint32_t bq = b_addr;
+                    if (p.dm_lean) {
+                        for (int th = 0; th < p.TH; th++) {
+                            for (int tw = 0; tw < p.TW; tw++) {
+                                if (leader && !(p.dbg & 2)) {
+                                    const uint32_t a_lo = a_lo_lbo | (a_base + (uint32_t)aoff_q);   // 14-bit address field: no carry below 256 KB
+                                    const uint32_t b_lo = b_lbo_dm | bq;
+#pragma unroll 2
+                                    for (int i = 0; i < ED; i++) {
+                                        const uint4 e = s_dm[i];
+                                        tc_mma(d0 + e.z, ((uint64_t)a_hi << 32) | (a_lo + e.x), ((uint64_t)b_hi << 32) | (b_lo + e.y), e.w, 1u);
+                                    }
+                                }
+                                aoff_q += sgn;
+                                bq += 2 * ntot;
+                            }
+                            aoff_q += sgn * (p.EW - p.TW);
+                        }
+                        __syncwarp();
+                        if (leader) tc_commit(empty0 + 8 * stage);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     for (int th = 0; th < p.TH; th++) {
                         for (int tw = 0; tw < p.TW; tw++) {
                             if (leader && !(p.dbg & 2)) {
@@ -646,6 +684,12 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
     p.wstage_bytes = (uint32_t)T * 2 * ncta * 16;
     const size_t smem_cap = 220 * 1024;
     p.dm = (!cls_cin && vg_tc_dmarch(ncta, TD)) ? 1 : 0;
+    static int dm_lean = -1;
+    if (dm_lean < 0) {
+        const char* e = getenv("VG_TC_DMLEAN");
+        dm_lean = (e && e[0] == '1') ? 1 : 0;
+    }
+    p.dm_lean = (p.dm && dm_lean && (size_t)p.nblk * ncta * sizeof(float) + 128 + 192 <= (size_t)TC_TAIL) ? 1 : 0;   // table = last 192 B of the tail
     static int bd_max = -1;   // d-march amortises its TD-1 edge slices over BD tiles: deeper bricks pay (VG_TC_BD overrides)
     if (bd_max < 0) {
         const char* e = getenv("VG_TC_BD");
