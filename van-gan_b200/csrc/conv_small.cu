@@ -282,8 +282,7 @@ __global__ void __launch_bounds__(256) cout1_k1_dgrad_kernel(const float* __rest
 __global__ void __launch_bounds__(256) cout1_k1_wgrad_kernel(const bf16* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
                                                              size_t nvox, int Cin) {
     __shared__ float sred[256 * 8];
-    const int cg = Cin / 8;
-    const int c8 = threadIdx.x % cg;
+    const int cg = Cin / 8;   // host guarantees 256 % cg == 0: a thread's channel group (threadIdx.x % cg) is loop-invariant
     float a[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) a[k] = 0.f;

@@ -307,7 +307,7 @@ int vg_upsample_concat_bwd(const void* dcat, void* dlo, void* dskip, int accumul
                            int C1, void* stream) {
     VG_REQUIRE(dcat && dlo && dskip && C0 % 8 == 0 && C1 % 8 == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    size_t t0 = (size_t)N * D * H * W * (C0 / 8), V2 = (size_t)N * 8 * D * H * W;
+    const size_t V2 = (size_t)N * 8 * D * H * W;
     VG_REQUIRE((long long)N * D * H < 0x7fffffffLL);
     upsample_concat_bwd_lo_kernel<<<vg_grid_for((long long)N * D * H, 1, 16), NT, 0, st>>>((const bf16*)dcat, (bf16*)dlo, N, D, H, W, C0, C1); VG_LAUNCHED(1);
     upsample_concat_bwd_skip_kernel<<<vg_grid_for(V2 * (C1 / 8), NT, 16), NT, 0, st>>>((const bf16*)dcat, (bf16*)dskip, V2, C0, C1,
