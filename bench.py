@@ -102,6 +102,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bench_config(S, G, world):
+    """The `config` object both arms print (the reference arm runs on OUR arm's config)."""
+    return {"workload": "VanGan.train_step 2xResUNet(f16,L4)+2xPatchGAN(f64), %d^3x1 volumes, global batch %d "
+                        "(b=%d per GPU), clDice iters 15, LSGAN, Adam+clipnorm" % (S, G, G // world),
+            "parallelism": "dp%d" % world, "l2": "256 MiB flush write between timed steps"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -112,21 +119,38 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
-def cpu_oracle_sample(S=64, steps=1, warmup=0):
-    """Times the oracle port of the reference's train_step (torch CPU fp32, all host cores) on a bounded
-    sample: one 1 x S^3 step; converted to 128^3-volumes/s by the voxel ratio.  Returns (value, seconds/step, cores)."""
+def _host_threads():
+    """All host threads, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def _oracle_state(seed0=1234):
+    from oracle import nets as ON, step as OS
+    P = {"gen_IS": ON.to_torch(ON.init_params(ON.resunet_param_shapes(), seed0)),
+         "gen_SI": ON.to_torch(ON.init_params(ON.resunet_param_shapes(), seed0 + 1)),
+         "disc_I": ON.to_torch(ON.init_params(ON.disc_param_shapes(), seed0 + 2)),
+         "disc_S": ON.to_torch(ON.init_params(ON.disc_param_shapes(), seed0 + 3))}
+    return P, {k: OS.Adam(list(v.keys())) for k, v in P.items()}
+
+
+def cpu_oracle_steps(S, steps, warmup=0):
+    """Times `steps` train steps of the oracle port of the reference (torch CPU fp32, all host threads) on one 1 x S^3 sample.
+    Returns (mean seconds per step, threads)."""
     import numpy as np
     import torch
     from oracle import losses as OL, nets as ON, step as OS
-    cores = torch.get_num_threads()
+    cores = _host_threads()
     rng = np.random.default_rng(0)
     I, Sg = synth_batch(1, S, 11)
     real_I, real_S = torch.tensor(I), torch.tensor(Sg)
-    P = {"gen_IS": ON.to_torch(ON.init_params(ON.resunet_param_shapes(), 1234)),
-         "gen_SI": ON.to_torch(ON.init_params(ON.resunet_param_shapes(), 1235)),
-         "disc_I": ON.to_torch(ON.init_params(ON.disc_param_shapes(), 1236)),
-         "disc_S": ON.to_torch(ON.init_params(ON.disc_param_shapes(), 1237))}
-    opts = {k: OS.Adam(list(v.keys())) for k, v in P.items()}
+    P, opts = _oracle_state()
     cfg = OL.make_cfg(1, 1)
     times = []
     for it in range(warmup + steps):
@@ -135,26 +159,55 @@ def cpu_oracle_sample(S=64, steps=1, warmup=0):
         OS.train_step_dp(cfg, P, opts, real_I, real_S, [rand])
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    vol_ratio = (128.0 / S) ** 3
-    return 1.0 / (sec * vol_ratio), sec, cores, sum(times)
+    return sum(times) / len(times), cores
+
+
+def cpu_full_size_ok():
+    """One oracle step at 1 x 128^3 keeps ~45 GB of autograd state: only run it where the host has the memory."""
+    try:
+        import psutil
+        return psutil.virtual_memory().available > 70 * 2 ** 30
+    except Exception:
+        return False
+
+
+def cpu_baseline_128(allow_full=True):
+    """CPU baseline on the bench's own volume size.  Preferred: ONE full oracle train_step on 1 x 128^3 (the workload processes 8
+    such volumes per step; CPU time is linear in the batch).  Fallback when the host lacks the memory: a 1 x 64^3 step scaled
+    by the voxel ratio 8.  Returns (volumes/s, threads, description, seconds of the sample)."""
+    if allow_full and cpu_full_size_ok():
+        sec, cores = cpu_oracle_steps(128, 1)
+        return 1.0 / sec, cores, "one full oracle (torch CPU fp32) train_step on 1x128^3: %.1f s" % sec, sec
+    sec, cores = cpu_oracle_steps(64, 1)
+    return 1.0 / (8.0 * sec), cores, ("one oracle (torch CPU fp32) train_step on 1x64^3 (%.1f s) scaled by the voxel ratio 8 "
+                                      "(host memory < 70 GB free: the 1x128^3 step does not fit)" % sec), sec
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU path for this workload.  TensorFlow cannot be installed in this image, so it is
+    the oracle port (kind "port").  Timed steps are bounded samples (one 1 x 64^3 train step each) so that --steps 20 --warmup 5
+    ends within minutes; the VALUE comes from one full 1 x 128^3 step measured in the same run whenever the host has the memory
+    for it, so the line is on our arm's configuration (128^3 volumes), not an extrapolation."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    S = 64
-    value, sec, cores, total = cpu_oracle_sample(S=S, steps=args.steps, warmup=args.warmup)
-    sample = "one oracle train_step on 1x%d^3 per step (%.2fs/step), scaled by (128/%d)^3 to 128^3 volumes" % (S, sec, S)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = _host_threads()
+    v128, _, desc128, sec128 = cpu_baseline_128()
+    sec64, _ = cpu_oracle_steps(64, args.steps, max(args.warmup - 1, 0))
+    v64 = 1.0 / (8.0 * sec64)
+    full = "1x128^3" in desc128 and "scaled" not in desc128
+    sample = "%s -> %.4f volumes/s (the line's value); the %d timed steps are bounded samples: one oracle train_step on 1x64^3 each " \
+             "(%.2f s/step; x8 voxels -> %.4f volumes/s)" % (desc128, v128, args.steps, sec64, v64)
+    line = {"impl": "reference", "metric": METRIC, "value": v128, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec64 * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "VanGan.train_step 2xResUNet+2xPatchGAN, 128^3x1, global batch 8 (CPU arm: bounded sample)",
-                       "note": "TensorFlow is not installable here; the reference arm is the oracle port (torch CPU fp32) "
-                               "of the reference's train_step on the host cores"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "config": bench_config(args.size, args.global_batch, max(world, args.gpus)),
+            "note": "TensorFlow is not installable here; the reference arm is the oracle port (torch CPU fp32) of the reference's "
+                    "train_step on the host cores; ms_per_step = mean duration of a timed step (= one bounded 1x64^3 sample, 1/8 volume)",
+            "full_128_step_s": sec128 if full else None, "value_from_64cubed_samples": v64,
+            "cpu_baseline": {"value": v128, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v128, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -269,6 +322,20 @@ def run_gpu(args):
             if ci % 16 == 0 and co % 16 == 0 and on_tc:
                 tc_ms += v["ms"]; tc_flop += v["work"]; tc_calls += v["calls"]
     achieved = tc_flop / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None
+
+    def fam_rate(prefix, scale):
+        t = sum(v["ms"] for k, v in fam.items() if k.startswith(prefix))
+        w = sum(v["work"] for k, v in fam.items() if k.startswith(prefix))
+        return (w / (t / 1e3) / scale, t / psteps) if t > 0 and w > 0 else (None, t / psteps)
+
+    extra = {}
+    for label, prefix, bound in (("instnorm_bwd", "vg_instnorm_bwd", "hbm"), ("instnorm_apply", "vg_instnorm_apply", "hbm"),
+                                 ("instnorm_stats", "vg_instnorm_stats", "hbm"), ("soft_skel_fwd", "vg_soft_skel_fwd", "hbm"),
+                                 ("soft_skel_bwd", "vg_soft_skel_bwd", "hbm"), ("conv3d_wgrad", "vg_conv3d_wgrad", "tensor")):
+        rate, t = fam_rate(prefix, 1e9 if bound == "hbm" else 1e12)
+        pk = hbm_peak if bound == "hbm" else tf_peak
+        extra[label] = {"bound": bound, "achieved": rate, "peak": pk, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                        "frac": (rate / pk) if rate else None, "ms_per_step": round(t, 3)}
     ms_ref = ms_prof / psteps      # step time of the profiled (eager) pass: shares are taken against it
     roofline = {"kernel": "tc_conv_kernel (tcgen05/TMEM implicit-GEMM Conv3D: stride-1/2 forward + all dgrads)", "bound": "tensor",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": (achieved / tf_peak) if achieved else None,
@@ -276,6 +343,7 @@ def run_gpu(args):
                 # (profiles/r01_ncu_full_fwd_48-16_dmarch_call37.txt): dram read 1.6875 GB + write 0.5193 GB for that launch; its
                 # algorithmic bytes (bf16 in + out) are 2.22e9
                 "traffic": 2.2068e9, "traffic_launch": "fwd 48->16 k3 s1, 8x130^3 -> 8x128^3",
+                "traffic_source": "ncu --set full capture of that one launch, profiles/r01_ncu_full_fwd_48-16_dmarch_call37.txt (not re-measured by this run)",
                 "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peak_src,
                 "calls_per_step": tc_calls / psteps, "share_of_step": tc_ms / psteps / ms_ref if ms_ref > 0 else None,
                 "conv_family_share_of_step": conv_ms / psteps / ms_ref if ms_ref > 0 else None,
@@ -284,21 +352,19 @@ def run_gpu(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "VanGan.train_step 2xResUNet(f16,L4)+2xPatchGAN(f64), %d^3x1 volumes, global batch %d "
-                                   "(b=%d per GPU), clDice iters 15, LSGAN, Adam+clipnorm" % (S, G, b),
-                       "parallelism": "dp%d" % world, "l2": "256 MiB flush write between timed steps",
-                       "launch": "one CUDA graph replay per step" if graph_on else "eager launches"},
+            "config": bench_config(S, G, world),
+            "launch_mode": "CUDA graph replay (one graph per backward sweep, NCCL all-reduce between them)" if graph_on else "eager launches",
             "clocks": clk, "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * b * S ** 3 * 4 * world),
                                    "d2h_bytes_per_step": int(64 * 8 * world), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "roofline": roofline,
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_other_kernels": extra,
             "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
     if sliding is not None:
         line["sliding_window"] = {"value": sliding["Mvoxel_per_s"], "unit": "Mvoxel/s", "windows": sliding["windows"],
                                   "seconds": sliding["seconds"], "gen_fwd_TFLOPs": sliding["gen_fwd_TFLOPs"], "workload": sliding["case"]}
     if world == 1 and not args.no_cpu_baseline:
-        v, sec, cores, _tot = cpu_oracle_sample(S=64, steps=1, warmup=0)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "one oracle (torch CPU fp32) train_step on 1x64^3 (%.1fs), scaled by 8 to 128^3 volumes" % sec}
+        torch.cuda.empty_cache()
+        v, cores, desc, _sec = cpu_baseline_128(allow_full=S == 128)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
     print(json.dumps(line), flush=True)
 
 

@@ -1,0 +1,446 @@
+"""Round-2 parity tests: the evidence that the GRADIENTS are right, in regimes where a bound means something.
+
+Why not "full-step gradients within 2e-2 of the fp32 oracle": measured with the fp64 oracle as arbiter
+(scripts/grad_conditioning.py), the gradient of two chained conv blocks moves by 3-4.5 % when
+ONLY the weight operands are rounded to bf16 -- every ReLU whose pre-activation changes sign switches its gradient
+on or off, so the gradient error is ~sqrt(fraction of flipped units), not ~(forward error).  Over the 58 stages of a
+ResUNet application that is 28-50 % at 64^3, for any bf16 (or TF32) implementation, including the reference's own
+arithmetic with bf16 storage.  So the bound is applied where it is meaningful:
+
+* per LAYER, teacher-forced (oracle input, same upstream gradient): dx and parameter gradients within 2e-2 of the fp32
+  oracle (measured floor of bf16 storage: 0.2-0.3 %);
+* per BLOCK (1 residual block = 3 convolutions): 8e-2 on dx, 5e-2 on parameters (floor 3.7 % / 2.6 %);
+* whole step: against the oracle run with bf16 rounding at the CUDA path's storage points (oracle.nets.Emu), i.e. the
+  same arithmetic, plus the cosine against the fp32 oracle; every measured error is printed;
+* a zeroed / sign-flipped / permuted gradient must FAIL every one of these criteria (test_criteria_reject_wrong_gradients).
+
+Also here: CUDA-graph replay == eager launches (the path bench.py times), the in-kernel Philox noise / dropout
+distributions, and clip+Adam with the device-resident step size.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _blocks import (agg_rel, bf, cosine, disc_stage, disc_stage_inputs, disc_stage_params, gen_blocks, oracle_block_grads,
+                     smooth_grad)
+
+pytestmark = pytest.mark.gpu
+
+LAYER_TOL = 2e-2           # north_star's relative-L2 bound, per teacher-forced layer
+BLOCK_TOL_DX, BLOCK_TOL_P = 8e-2, 5e-2
+STEP_TOL_EMU = 0.25        # whole-network gradient vs the bf16-emulating oracle (measured values are printed)
+STEP_MIN_COS = 0.80        # whole-network gradient cosine vs the fp32 oracle
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a).double().flatten().cpu()
+    b = torch.as_tensor(b).double().flatten().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _dev(t):
+    return (t if t.shape[-1] == 1 else t.to(torch.bfloat16)).cuda()
+
+
+# ----------------------------------------------------------------------------- CUDA-side block runners
+def cuda_gen_block(net, name, tape, xs):
+    from van_gan_b200 import engine as E
+    from van_gan_b200._lib import ACT_NONE
+    if name == "stem":
+        conv = net.stem_cb(tape, net.stem_conv0(tape, E.pad_noise(tape, xs[0])))
+        return net.stem_short_norm(tape, net.stem_short(tape, xs[0]), act=ACT_NONE, residual=conv)
+    if name.startswith("enc"):
+        return net.enc[int(name[3:]) - 1](tape, xs[0])
+    if name == "bridge":
+        h = xs[0]
+        for blk in net.bridge:
+            h = blk(tape, h)
+        return h
+    if name.startswith("dec"):
+        return net.dec[int(name[3:])](tape, E.upsample_concat(tape, xs[0], xs[1]))
+    assert name == "head"
+    return net.head(tape, xs[0])
+
+
+def _gen_setup(S, seed):
+    from oracle import nets as ON
+    from test_gpu_train_step import synth
+    from van_gan_b200.resunet_model import ResUNet
+    rng = np.random.default_rng(seed)
+    real_I, _ = synth(rng, 1, S)
+    init = ON.init_params(ON.resunet_param_shapes(), 1, 0.05)
+    P = ON.to_torch(init)
+    taps = {}
+    with torch.no_grad():
+        ON.resunet_forward(P, real_I, taps=taps)
+    taps["input"] = real_I
+    net = ResUNet((S, S, S, 1), upsample_mode='simple')
+    net.load(init)
+    return rng, P, taps, net
+
+
+def test_generator_blocks_teacher_forced(cuda):
+    """Every block of the ResUNet, fed the oracle's input activation (bf16-exact) and a given upstream gradient:
+    output, input gradients and parameter gradients against the fp32 oracle."""
+    from van_gan_b200 import engine as E
+    rng, P, taps, net = _gen_setup(64, 21)
+    report = []
+    for name, (fn, ins, prefixes) in gen_blocks().items():
+        xs = [bf(taps[i]) if taps[i].shape[-1] > 1 else taps[i] for i in ins]
+        pn = [n for n in P if any(n.startswith(pr) for pr in prefixes)]
+        with torch.no_grad():
+            yshape = tuple(fn(P, *xs).shape)
+        g = smooth_grad(rng, yshape)
+        y, gx, gp = oracle_block_grads(fn, P, xs, g, pn)
+        tape = E.Tape()
+        xv = [E.Var(_dev(x)) for x in xs]
+        out = cuda_gen_block(net, name, tape, xv)
+        net.zero_grad()
+        tape.backward([(out, _dev(g))], net.trainable_variables, wrt_vars=xv)
+        gk = net.export_grads()
+        e_f = rel_l2(out.data.float(), y)
+        e_x = [rel_l2(v.grad.float(), gxi) for v, gxi in zip(xv, gx)]
+        e_p = agg_rel(gk, gp, pn)
+        report.append((name, e_f, e_x, e_p))
+        tape.clear()
+    for r in report:
+        print("gen block %-7s fwd %.2e  dx %s  params %.2e" % (r[0], r[1], ["%.2e" % e for e in r[2]], r[3]))
+    for name, e_f, e_x, e_p in report:
+        single = name in ("head",)
+        assert e_f < 2e-2, (name, e_f)
+        assert max(e_x) < (LAYER_TOL if single else BLOCK_TOL_DX), (name, e_x)
+        assert e_p < (LAYER_TOL if single else BLOCK_TOL_P), (name, e_p)
+
+
+def test_generator_layers_teacher_forced(cuda):
+    """Single layers (one convolution each): conv_block = InstanceNorm -> ReLU -> ReflectionPadding3D -> Conv3D
+    (resunet_model.py:42-66) and shortcut = Conv3D k1 -> InstanceNorm -> Add (resunet_model.py:133-143), every instance of
+    the network, at north_star's 2e-2 against the fp32 oracle."""
+    from oracle import nets as ON
+    from van_gan_b200 import engine as E
+    from van_gan_b200._lib import ACT_NONE
+    rng, P, taps, net = _gen_setup(64, 22)
+    layers = []   # (label, oracle fn, cuda fn, inputs, param names)
+
+    def add_cb(label, cb, x, stride):
+        layers.append((label, lambda p, h: ON._conv_block(p, label, h, stride), lambda tape, xs: cb(tape, xs[0]), [x],
+                       [n for n in P if n.startswith(label + ".")]))
+
+    def add_short(label, conv, norm, x, res, stride):
+        def ofn(p, h, r):
+            sc = ON.conv3d(h, p[label + ".conv.w"], p[label + ".conv.b"], stride=stride, padding="same")
+            return ON._norm_act(p, label + ".in", sc, act=False) + r
+        layers.append((label, ofn, lambda tape, xs: norm(tape, conv(tape, xs[0]), act=ACT_NONE, residual=xs[1]), [x, res],
+                       [n for n in P if n.startswith(label + ".")]))
+
+    def rnd(shape):
+        return bf(torch.tensor(rng.standard_normal(shape) * 1.3 + 0.2, dtype=torch.float32))
+
+    f = [16, 32, 64, 128, 256]
+    S = 64
+    add_cb("stem.cb", net.stem_cb, rnd((1, S, S, S, 16)), 1)
+    add_short("stem.short", net.stem_short, net.stem_short_norm, taps["input"], rnd((1, S, S, S, 16)), 1)
+    prev = "stem"
+    for e in range(1, 5):
+        s_in, s_out = S >> (e - 1), S >> e
+        blk = net.enc[e - 1]
+        add_cb("enc%d.cb1" % e, blk.cb1, bf(taps[prev]), 2)
+        add_cb("enc%d.cb2" % e, blk.cb2, rnd((1, s_out, s_out, s_out, f[e])), 1)
+        add_short("enc%d.short" % e, blk.short, blk.short_norm, bf(taps[prev]), rnd((1, s_out, s_out, s_out, f[e])), 2)
+        prev = "enc%d" % e
+    add_cb("bridge1", net.bridge[0], bf(taps["enc4"]), 1)
+    add_cb("bridge2", net.bridge[1], rnd((1, 4, 4, 4, 256)), 1)
+    for d in reversed(range(4)):
+        s_d = S >> d
+        blk = net.dec[d]
+        xin = rnd((1, s_d, s_d, s_d, f[d + 1] + f[d]))
+        add_cb("dec%d.cb1" % d, blk.cb1, xin, 1)
+        add_cb("dec%d.cb2" % d, blk.cb2, rnd((1, s_d, s_d, s_d, f[d])), 1)
+        add_short("dec%d.short" % d, blk.short, blk.short_norm, xin, rnd((1, s_d, s_d, s_d, f[d])), 1)
+    worst = 0.0
+    for label, ofn, kfn, xs, pn in layers:
+        with torch.no_grad():
+            yshape = tuple(ofn(P, *xs).shape)
+        g = smooth_grad(rng, yshape)
+        y, gx, gp = oracle_block_grads(ofn, P, xs, g, pn)
+        tape = E.Tape()
+        xv = [E.Var(_dev(x)) for x in xs]
+        out = kfn(tape, xv)
+        net.zero_grad()
+        tape.backward([(out, _dev(g))], net.trainable_variables, wrt_vars=xv)
+        gk = net.export_grads()
+        e_f = rel_l2(out.data.float(), y)
+        e_x = [rel_l2(v.grad.float(), gxi) for v, gxi in zip(xv, gx) if float(gxi.norm()) > 0]
+        e_p = agg_rel(gk, gp, pn)
+        print("gen layer %-11s fwd %.2e  dx %s  params %.2e" % (label, e_f, ["%.2e" % e for e in e_x], e_p))
+        worst = max([worst, e_f, e_p] + e_x)
+        assert e_f < LAYER_TOL and e_p < LAYER_TOL and all(e < LAYER_TOL for e in e_x), (label, e_f, e_x, e_p)
+        tape.clear()
+    print("worst single-layer error %.2e (bound %.0e)" % (worst, LAYER_TOL))
+
+
+def test_discriminator_stages_teacher_forced(cuda):
+    """The five PatchGAN stages (InstanceNorm + LeakyReLU + SpatialDropout3D + pad + GaussianNoise + Conv3D each), explicit
+    noise and masks, each fed the oracle's raw convolution output: 2e-2 against the fp32 oracle."""
+    from oracle import nets as ON
+    from test_gpu_train_step import synth
+    from van_gan_b200 import engine as E
+    from van_gan_b200.discriminator import get_discriminator
+    S = 64
+    rng = np.random.default_rng(23)
+    _, real_S = synth(rng, 1, S)
+    initd = ON.init_params(ON.disc_param_shapes(), 3, 0.05)
+    P = ON.to_torch(initd)
+    nz, mk = ON.make_disc_rand(rng, 1, S)
+    with torch.no_grad():
+        ins = disc_stage_inputs(P, real_S, nz, mk)
+    d = get_discriminator((S, S, S, 1), filters=64, use_dropout=True, use_input_noise=True, use_layer_noise=True, name='d')
+    d.load(initd)
+    nzc, mkc = [t.cuda() for t in nz], [m.cuda() for m in mk]
+    for k in range(5):
+        x = ins[k] if k == 0 else bf(ins[k])
+        fn = (lambda kk: (lambda p, h: disc_stage(kk)(p, h, nz, mk)))(k)
+        pn = disc_stage_params(k)
+        with torch.no_grad():
+            yshape = tuple(fn(P, x).shape)
+        g = smooth_grad(rng, yshape)
+        y, gx, gp = oracle_block_grads(fn, P, [x], g, pn)
+        tape = E.Tape()
+        xv = E.Var(_dev(x))
+        out = d.stage(k, tape, xv, training=True, noise=nzc, masks=mkc)
+        d.zero_grad()
+        tape.backward([(out, _dev(g))], d.trainable_variables, wrt_vars=[xv])
+        gk = d.export_grads()
+        e_f, e_x, e_p = rel_l2(out.data.float(), y), rel_l2(xv.grad.float(), gx[0]), agg_rel(gk, gp, pn)
+        print("disc stage %d fwd %.2e dx %.2e params %.2e" % (k, e_f, e_x, e_p))
+        assert e_f < LAYER_TOL and e_x < LAYER_TOL and e_p < LAYER_TOL, (k, e_f, e_x, e_p)
+        tape.clear()
+
+
+# ----------------------------------------------------------------------------- whole step
+def _step_errors(S, b, nd, seed):
+    from oracle import losses as OL, nets as ON, step as OS
+    from test_gpu_train_step import _cuda_step, _setup
+    G = b * nd
+    real_I, real_S, init, rand = _setup(S, b, nd, seed)
+    cfg = OL.make_cfg(G, nd)
+    res_o, grads_o, _ = OS.replica_grads(cfg, {k: ON.to_torch(v) for k, v in init.items()}, real_I, real_S, rand)
+    ON.Emu.on = True
+    try:
+        res_e, grads_e, _ = OS.replica_grads(cfg, {k: ON.to_torch(v) for k, v in init.items()}, real_I, real_S, rand)
+    finally:
+        ON.Emu.on = False
+    gan, res_k = _cuda_step(S, G, nd, init, real_I, real_S, rand)
+    out = {}
+    for name, net in gan.networks.items():
+        g = net.export_grads()
+        out[name] = dict(vs_emu=agg_rel(g, grads_e[name]), vs_fp32=agg_rel(g, grads_o[name]), emu_vs_fp32=agg_rel(grads_e[name], grads_o[name]),
+                         cos_fp32=cosine(g, grads_o[name]), cos_emu=cosine(g, grads_e[name]))
+    return out, res_k, res_o, grads_o, gan
+
+
+@pytest.mark.parametrize("S,b", [(64, 1)])
+def test_train_step_gradients_vs_emulated_oracle(cuda, S, b):
+    """Whole step (four sweeps): CUDA gradients against the oracle with bf16 rounding at the CUDA path's storage points, and
+    the cosine against the fp32 oracle.  Bounds are < 0.5 everywhere, so a missing term, a wrong sign or a zero gradient fails."""
+    errs, res_k, res_o, _, _ = _step_errors(S, b, 2, 100 + b)
+    for name, e in errs.items():
+        print("step %d^3 %-7s: CUDA vs Emu %.3f | CUDA vs fp32 %.3f | Emu vs fp32 %.3f | cos(CUDA, fp32) %.3f | cos(CUDA, Emu) %.3f"
+              % (S, name, e["vs_emu"], e["vs_fp32"], e["emu_vs_fp32"], e["cos_fp32"], e["cos_emu"]))
+    for name, e in errs.items():
+        assert e["vs_emu"] < STEP_TOL_EMU, (name, e)
+        assert e["cos_fp32"] > STEP_MIN_COS, (name, e)
+        assert e["vs_fp32"] < 1.25 * e["emu_vs_fp32"] + 2e-2 and e["vs_fp32"] < 0.7, (name, e)   # and never a bound >= 1
+
+
+def test_criteria_reject_wrong_gradients(cuda):
+    """Mutation check of the criteria themselves: a zeroed gradient, a sign flip and a rolled gradient buffer must each violate the
+    whole-step criteria (the round-1 bound `1.5*floor + 2e-2` accepted g = 0)."""
+    from oracle import nets as ON
+    rng = np.random.default_rng(5)
+    shapes = ON.disc_param_shapes()
+    go = {n: torch.tensor(rng.standard_normal(s), dtype=torch.float32) for n, s in shapes.items()}
+    ge = {n: v + 0.05 * torch.tensor(rng.standard_normal(v.shape), dtype=torch.float32) for n, v in go.items()}   # a 5 % "bf16 floor"
+
+    def passes(g):
+        vs_emu, vs32, floor, cs = agg_rel(g, ge), agg_rel(g, go), agg_rel(ge, go), cosine(g, go)
+        return vs_emu < STEP_TOL_EMU and cs > STEP_MIN_COS and vs32 < 1.25 * floor + 2e-2 and vs32 < 0.7
+
+    assert passes({n: v + 0.02 * torch.tensor(rng.standard_normal(v.shape), dtype=torch.float32) for n, v in go.items()})
+    assert not passes({n: torch.zeros_like(v) for n, v in go.items()})
+    assert not passes({n: -v for n, v in go.items()})
+    assert not passes({n: torch.roll(v.flatten(), 1).view_as(v) for n, v in go.items()})
+    assert not passes({n: 0.5 * v for n, v in go.items()})
+
+
+# ----------------------------------------------------------------------------- graph replay == eager
+def _fresh_gan(S, b, use_graph, seed=77):
+    from test_gpu_train_step import Args
+    from van_gan_b200.vangan import VanGan
+    gan = VanGan(Args(S, b, 1), gen_i2s='resUnet', gen_s2i='resUnet', seed=seed)
+    gan.use_graph = use_graph
+    return gan
+
+
+def test_graph_replay_equals_eager(cuda):
+    """bench.py times CUDA-graph replay with in-kernel Philox noise / dropout and the device-resident Adam step size;
+    the parity tests above run eager launches.  From identical state and seed, 5 steps each way (steps 3-5 are replays)
+    must give the same ten losses per step and the same weights (differences: fp32 atomics order in wgrad only)."""
+    from test_gpu_train_step import synth
+    S, b, steps = 32, 2, 5
+    rng = np.random.default_rng(31)
+    batches = [synth(rng, b, S) for _ in range(steps)]
+    runs = {}
+    for mode in ("eager", "graph", "eager2"):
+        gan = _fresh_gan(S, b, mode == "graph")
+        w0 = {k: net.w.clone() for k, net in gan.networks.items()}
+        losses = [gan.train_step(I.cuda(), Sg.cuda()) for I, Sg in batches]
+        if mode == "graph":
+            assert gan._graph is not None and gan.launches_per_replay > 100, "the graph path did not engage"
+        else:
+            assert gan._graph is None
+        runs[mode] = (losses, {k: (net.w - w0[k]).double().cpu() for k, net in gan.networks.items()},
+                      {k: net.step_count for k, net in gan.networks.items()})
+    for it in range(steps):
+        for k in runs["eager"][0][it]:
+            a, g, a2 = runs["eager"][0][it][k], runs["graph"][0][it][k], runs["eager2"][0][it][k]
+            noise = abs(a - a2)
+            assert abs(a - g) <= 1e-5 * abs(a) + 10 * noise + 1e-7, (it, k, a, g, a2)
+    for k in runs["eager"][1]:
+        de, dg, de2 = runs["eager"][1][k], runs["graph"][1][k], runs["eager2"][1][k]
+        nondet = float((de - de2).norm() / de.norm())
+        diff = float((de - dg).norm() / de.norm())
+        print("replay vs eager %-7s: weight-displacement rel diff %.2e (eager vs eager run-to-run %.2e), max abs %.2e"
+              % (k, diff, nondet, float((de - dg).abs().max())))
+        assert float(de.norm()) > 0
+        assert diff <= max(1e-3, 10 * nondet), (k, diff, nondet)
+        assert runs["eager"][2][k] == runs["graph"][2][k] == steps
+
+
+def test_clip_adam_device_step_size_variant(cuda):
+    """vg_clip_adam_step_dev (lr_t read from device memory: the variant the captured step uses) == vg_clip_adam_step, bit for bit."""
+    from collections import OrderedDict
+    from van_gan_b200 import engine as E
+    rng = np.random.default_rng(6)
+    shapes = OrderedDict([("a.w", (3, 3, 3, 4, 8)), ("a.b", (8,)), ("b.gamma", (16,)), ("c.w", (1, 1, 1, 64, 64))])
+    init = {k: rng.standard_normal(s).astype(np.float32) for k, s in shapes.items()}
+    nets = [E.Network("h", shapes), E.Network("d", shapes)]
+    for n in nets:
+        n.load(init)
+    lr_dev = torch.zeros(1, dtype=torch.float32, device="cuda")
+    for it in range(3):
+        g = {k: (rng.standard_normal(s) * (40.0 if k == "c.w" else 1.0)).astype(np.float32) for k, s in shapes.items()}
+        for n in nets:
+            for k in shapes:
+                n.params[k].grad.copy_(torch.tensor(g[k]).cuda())
+        nets[0].adam_step()
+        lr_dev.fill_(E.Network.lr_t(it + 1))
+        nets[1].adam_step(lr_t_dev=lr_dev)
+        assert torch.equal(nets[0].w, nets[1].w) and torch.equal(nets[0].m, nets[1].m) and torch.equal(nets[0].v, nets[1].v), it
+
+
+# ----------------------------------------------------------------------------- in-kernel Philox
+def test_philox_noise_and_dropout_distributions(cuda):
+    """GaussianNoise(0.1) / SpatialDropout3D(0.2) drawn in-kernel (discriminator.py:52,106; building_blocks.py:170,195):
+    mean 0 +- 1 % of sigma, sigma within 1 %, keep rate 0.8 +- 0.01, values in {0, 1/0.8}; a different draw per seed offset
+    (= per step / per replay), the same draw for the same (seed, offset)."""
+    from collections import OrderedDict
+    from van_gan_b200 import engine as E
+    from van_gan_b200._lib import ACT_NONE, PAD_REFLECT
+    seed_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+    x = torch.zeros((2, 62, 62, 62, 1), dtype=torch.float32, device="cuda")
+
+    def draw_pad(seed, off):
+        seed_dev.fill_(off)
+        return E.pad_noise(E.Tape(enabled=False), E.Var(x), noise=None, noise_std=0.1, seed=seed, seed_dev=seed_dev).data.clone()
+
+    a = draw_pad(3, 64)
+    assert abs(float(a.mean())) < 1e-3 and abs(float(a.std()) - 0.1) < 1e-3, (float(a.mean()), float(a.std()))
+    kurt = float(((a / a.std()) ** 4).mean())
+    assert abs(kurt - 3.0) < 0.1, kurt                                    # Gaussian, not uniform (1.8) or clipped
+    assert torch.equal(a, draw_pad(3, 64))
+    assert not torch.equal(a, draw_pad(3, 128)) and not torch.equal(a, draw_pad(4, 64))
+    assert abs(float((a * draw_pad(3, 128)).mean())) < 1e-4               # independent draws
+
+    # InstanceNorm-apply noise (bf16 feature maps): output = beta-less normalised zeros + noise
+    C = 64
+    net = E.Network("t", OrderedDict([("n.gamma", (C,)), ("n.beta", (C,))]))
+    net.load({"n.gamma": np.ones(C, np.float32), "n.beta": np.zeros(C, np.float32)})
+    layer = E.InstanceNorm(net, "n", C)
+    xin = torch.zeros((2, 30, 30, 30, C), dtype=torch.bfloat16, device="cuda")
+
+    def draw_in(off):
+        seed_dev.fill_(off)
+        return layer(E.Tape(enabled=False), E.Var(xin), act=ACT_NONE, pad=(1, 1, PAD_REFLECT), noise=None, noise_std=0.1, seed=5,
+                     seed_dev=seed_dev).data.float()
+
+    n1 = draw_in(0)
+    assert abs(float(n1.mean())) < 1e-3 and abs(float(n1.std()) - 0.1) < 1.5e-3, (float(n1.mean()), float(n1.std()))
+    assert not torch.equal(n1, draw_in(64))
+
+    n = 200000
+    def draw_mask(seed, off):
+        seed_dev.fill_(off)
+        return E.dropout_mask(n, 0.2, seed, seed_dev)
+    m = draw_mask(9, 0)
+    keep = float((m > 0).float().mean())
+    assert abs(keep - 0.8) < 0.01, keep
+    vals = torch.unique(m)
+    assert vals.numel() == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - 1.25) < 1e-6
+    assert torch.equal(m, draw_mask(9, 0)) and not torch.equal(m, draw_mask(9, 64)) and not torch.equal(m, draw_mask(10, 0))
+
+
+def test_replays_draw_fresh_noise(cuda):
+    """Two consecutive replays of the captured step on the SAME batch give different discriminator losses (new noise and
+    dropout draws per step through the device-resident seed offset), while the generator-only losses that do not depend on
+    the discriminators' noise stay a deterministic function of the weights."""
+    from test_gpu_train_step import synth
+    S, b = 32, 1
+    rng = np.random.default_rng(41)
+    I, Sg = synth(rng, b, S)
+    gan = _fresh_gan(S, b, True)
+    seeds = []
+    outs = []
+    for _ in range(5):
+        outs.append(gan.train_step(I.cuda(), Sg.cuda()))
+        seeds.append(int(gan._seed_dev.item()))
+    assert gan._graph is not None
+    assert len(set(seeds)) == 5, seeds
+    assert outs[3]["D_S_loss"] != outs[4]["D_S_loss"]
+
+
+# ----------------------------------------------------------------------------- BASELINE's size
+def test_train_step_128_b1_vs_golden_oracle(cuda):
+    """One full train step at BASELINE's volume size (1 x 128^3, N_DEVICES = 1) against the fp32 CPU oracle.  The oracle step
+    takes ~2 min and ~45 GB on the host, so its result is a committed fixture (tests/golden/step128_b1.npz, made by
+    scripts/make_golden_128.py): the ten losses, each network's gradient norm and 64 seeded random-sign projections of each
+    network's flat gradient, from which ||g - g_oracle|| / ||g_oracle|| and the cosine are estimated (+-18 %)."""
+    import os
+    from _blocks import projections
+    from test_gpu_train_step import _cuda_step, _setup
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step128_b1.npz"))
+    S, seed = int(z["S"]), int(z["seed"])
+    assert S == 128
+    real_I, real_S, init, rand = _setup(S, 1, 1, seed)
+    gan, res_k = _cuda_step(S, 1, 1, init, real_I, real_S, rand)
+    for k, v in res_k.items():
+        o = float(z["loss/" + k])
+        print("128^3 loss %-22s CUDA %.6f oracle %.6f rel %.2e" % (k, v, o, abs(v - o) / abs(o)))
+    for k, v in res_k.items():
+        o = float(z["loss/" + k])
+        assert abs(v - o) <= 2e-2 * abs(o) + 1e-4, (k, v, o)
+    for i, (name, net) in enumerate(gan.networks.items()):
+        g = net.export_grads()
+        flat = torch.cat([torch.as_tensor(g[n]).double().flatten() for n in g])
+        pk, po = projections(flat, 1000 + i, int(z["k_proj"])), z["proj/" + name]
+        no = float(z["norm/" + name])
+        rel = float(np.sqrt(np.mean((pk - po) ** 2))) / no
+        cs = float(np.mean(pk * po)) / (float(flat.norm()) * no)
+        tn = np.array([float(torch.as_tensor(g[n]).double().norm()) for n in g])
+        big = z["tnorm/" + name] > 1e-3 * no
+        ratio = tn[big] / z["tnorm/" + name][big]
+        print("128^3 %-7s: ||g|| CUDA %.4e oracle %.4e | est. rel-L2 vs fp32 oracle %.3f | est. cosine %.3f | per-variable norm ratio %.2f..%.2f"
+              % (name, float(flat.norm()), no, rel, cs, ratio.min(), ratio.max()))
+        assert abs(float(flat.norm()) / no - 1.0) < 0.25, name
+        assert cs > 0.75 and rel < 0.7, (name, rel, cs)
+        assert ratio.min() > 0.33 and ratio.max() < 3.0, (name, ratio.min(), ratio.max())   # no variable lost or blown up

@@ -12,7 +12,7 @@ def _skel_buffers(x, iters):
     nv = x.numel()
     Eb = torch.empty((iters + 2, nv), dtype=torch.float32, device=E.DEV)
     Sb = torch.empty((iters + 1, nv), dtype=torch.float32, device=E.DEV)
-    call("vg_soft_skel_fwd", x, Eb, Sb, n, d, h, w, iters)
+    call("vg_soft_skel_fwd", x, Eb, Sb, n, d, h, w, iters, work=16.0 * nv * (iters + 1))   # HBM model 16 B * V * (k+1)
     return Eb, Sb
 
 
@@ -41,7 +41,7 @@ def soft_skel_with_grad(img, iters):
         nb = lib().vg_soft_skel_bwd_workspace_bytes(n, d, h, w)
         ws = torch.empty(nb // 4, dtype=torch.float32, device=E.DEV)
         dx = torch.empty_like(img)
-        call("vg_soft_skel_bwd", Eb, Sb, gskel.contiguous(), dx, ws, nb, n, d, h, w, iters)
+        call("vg_soft_skel_bwd", Eb, Sb, gskel.contiguous(), dx, ws, nb, n, d, h, w, iters, work=16.0 * img.numel() * (iters + 1))
         return dx
 
     return Sb[iters].view(img.shape), backward

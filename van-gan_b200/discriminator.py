@@ -44,14 +44,14 @@ class DiscriminatorModel(E.Network):
         if seed is not None:
             self.load(E.default_init({n: p.shape for n, p in self.params.items()}, seed))
 
-    def forward(self, tape, x, training=True, noise=None, masks=None, seed=0, seed_dev=None):
-        """x: Var (N,D,H,W,1) fp32.  noise / masks: explicit tensors (parity mode; oracle layout) or None
-        -> in-kernel Philox noise and channel masks keyed on `seed` (+ the per-step offset *seed_dev, a device scalar)."""
-        n = x.shape[0]
+    def stage(self, k, tape, h, training=True, noise=None, masks=None, seed=0, seed_dev=None):
+        """Stage k = 0..4: everything between the raw output of convolution k-1 (the network input for k = 0) and the raw
+        output of convolution k, i.e. InstanceNorm + LeakyReLU + SpatialDropout3D of block k-1, then padding + GaussianNoise and
+        the convolution of block k (discriminator.py:50-114).  `forward` chains the five stages; the teacher-forced parity
+        tests run them one at a time."""
+        n = h.shape[0]
         std = self.noise_std if training else 0.0
-
-        def nz(i):
-            return None if noise is None else noise[i]
+        nz = None if noise is None else noise[k]
 
         def mask(i, c):
             if not training:
@@ -60,20 +60,25 @@ class DiscriminatorModel(E.Network):
                 return masks[i].reshape(n * c).contiguous()
             return E.dropout_mask(n * c, self.rate, seed * 16 + 8 + i, seed_dev)
 
-        h = E.pad_noise(tape, x, noise=nz(0), noise_std=std, seed=seed * 16 + 0, seed_dev=seed_dev)
-        h = self.conv0(tape, h)
-        h = self.norm0(tape, h, act=ACT_LEAKY, pad=(1, 1, PAD_REFLECT), noise=nz(1), noise_std=std, seed=seed * 16 + 1, seed_dev=seed_dev)
-        h = self.conv1(tape, h)
-        h = self.norm1(tape, h, act=ACT_LEAKY, pad=(1, 1, PAD_REFLECT), drop=mask(0, self.norm1.c), noise=nz(2),
-                       noise_std=std, seed=seed * 16 + 2, seed_dev=seed_dev)
-        h = self.conv2(tape, h)
-        # next conv is k4 s1 'same': TF pads 1 before / 2 after with zeros, AFTER the noise layer
-        h = self.norm2(tape, h, act=ACT_LEAKY, pad=(1, 2, PAD_ZERO), drop=mask(1, self.norm2.c), noise=nz(3),
-                       noise_std=std, seed=seed * 16 + 3, seed_dev=seed_dev)
-        h = self.conv3(tape, h)
-        h = self.norm3(tape, h, act=ACT_LEAKY, pad=(1, 1, PAD_ZERO), drop=mask(2, self.norm3.c), noise=nz(4),
-                       noise_std=std, seed=seed * 16 + 4, seed_dev=seed_dev)
-        return self.convo(tape, h)
+        kw = dict(noise=nz, noise_std=std, seed=seed * 16 + k, seed_dev=seed_dev)
+        if k == 0:
+            return self.conv0(tape, E.pad_noise(tape, h, **kw))
+        if k == 1:
+            return self.conv1(tape, self.norm0(tape, h, act=ACT_LEAKY, pad=(1, 1, PAD_REFLECT), **kw))
+        if k == 2:
+            return self.conv2(tape, self.norm1(tape, h, act=ACT_LEAKY, pad=(1, 1, PAD_REFLECT), drop=mask(0, self.norm1.c), **kw))
+        if k == 3:
+            # next conv is k4 s1 'same': TF pads 1 before / 2 after with zeros, AFTER the noise layer
+            return self.conv3(tape, self.norm2(tape, h, act=ACT_LEAKY, pad=(1, 2, PAD_ZERO), drop=mask(1, self.norm2.c), **kw))
+        return self.convo(tape, self.norm3(tape, h, act=ACT_LEAKY, pad=(1, 1, PAD_ZERO), drop=mask(2, self.norm3.c), **kw))
+
+    def forward(self, tape, x, training=True, noise=None, masks=None, seed=0, seed_dev=None):
+        """x: Var (N,D,H,W,1) fp32.  noise / masks: explicit tensors (parity mode; oracle layout) or None
+        -> in-kernel Philox noise and channel masks keyed on `seed` (+ the per-step offset *seed_dev, a device scalar)."""
+        h = x
+        for k in range(5):
+            h = self.stage(k, tape, h, training=training, noise=noise, masks=masks, seed=seed, seed_dev=seed_dev)
+        return h
 
     def __call__(self, x, training=False):
         xt = torch.as_tensor(x, dtype=torch.float32, device=E.DEV).contiguous()

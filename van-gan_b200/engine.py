@@ -287,13 +287,15 @@ class InstanceNorm:
         ws = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
         mean = torch.empty(n * c, dtype=torch.float32, device=DEV)
         rstd = torch.empty(n * c, dtype=torch.float32, device=DEV)
-        call("vg_instnorm_stats", x.data, dt, n, d, h, w, c, mean, rstd, ws, ws_bytes)
+        # algorithmic HBM bytes: forward = read x twice (statistics, apply) + write y; backward = read x and dy twice + write dx
+        es, nin = x.data.element_size(), x.data.numel()
+        call("vg_instnorm_stats", x.data, dt, n, d, h, w, c, mean, rstd, ws, ws_bytes, work=float(es * nin))
         desc = InDesc(n, d, h, w, c, dt, act, slope, pad[0], pad[1], pad[2], noise_std if noise is None else 0.0, seed,
                       seed_dev.data_ptr() if seed_dev is not None else None)
         pp = pad[0] + pad[1]
         y = torch.empty((n, d + pp, h + pp, w + pp, c), dtype=x.data.dtype, device=DEV)
         call("vg_instnorm_apply", desc, x.data, residual.data if residual is not None else None, y, mean, rstd,
-             self.gamma.w, self.beta.w, drop, noise)
+             self.gamma.w, self.beta.w, drop, noise, work=float(es * (nin * (2 if residual is not None else 1) + y.numel())))
         out = Var(y)
         ins = [x] + ([residual] if residual is not None else [])
 
@@ -306,7 +308,8 @@ class InstanceNorm:
             dres = torch.empty_like(x.data) if need_res else None
             ws2 = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
             call("vg_instnorm_bwd", desc, dy, x.data, mean, rstd, self.gamma.w, self.beta.w, drop, dx, 1 if fuse else 0, dres,
-                 self.gamma.grad if p_needs else None, self.beta.grad if p_needs else None, ws2, ws_bytes)
+                 self.gamma.grad if p_needs else None, self.beta.grad if p_needs else None, ws2, ws_bytes,
+                 work=float(es * (2 * (nin + y.numel()) + nin * (2 if need_res else 1))))
             if in_needs[0] and not fuse:
                 accumulate(x, dx)
             if need_res:

@@ -164,9 +164,17 @@ class VanGan:
     def _plan(self, total_I, total_S, dI, dS):
         return ((self.gen_IS, total_I), (self.gen_SI, total_S), (self.disc_I, dI), (self.disc_S, dS))
 
+    @staticmethod
+    def seed_offset(seed, step, world=1, rank=0):
+        """Offset added to every in-kernel Philox key of one step.  A (step, replica) pair owns a block of 64 keys (the four
+        discriminator applications use key = application * 16 + layer), so draws differ per step AND per replica --
+        MirroredStrategy draws GaussianNoise / SpatialDropout3D independently on every replica -- while `seed` itself, which
+        also initialises the weights, stays shared across ranks."""
+        return ((seed * 1000003 + step) * world + rank) * 64
+
     def _upload_step_state(self):
         """Seed offset and the four Adam step sizes of THIS step -> device (async copies on the current stream)."""
-        self._h_seed[0] = (self.seed * 1000003 + self.step) * 64
+        self._h_seed[0] = self.seed_offset(self.seed, self.step, self.strategy.num_replicas_in_sync, self.strategy.rank)
         for i, net in enumerate((self.gen_IS, self.gen_SI, self.disc_I, self.disc_S)):
             self._h_lr[i] = E.Network.lr_t(net.step_count + 1, self.opt["lr"], self.opt["beta_1"], self.opt["beta_2"])
         self._seed_dev.copy_(self._h_seed, non_blocking=True)
