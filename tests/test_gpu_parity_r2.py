@@ -28,8 +28,24 @@ pytestmark = pytest.mark.gpu
 
 LAYER_TOL = 2e-2           # north_star's relative-L2 bound, per teacher-forced layer
 BLOCK_TOL_DX, BLOCK_TOL_P = 8e-2, 5e-2
-STEP_TOL_EMU = 0.25        # whole-network gradient vs the bf16-emulating oracle (measured values are printed)
-STEP_MIN_COS = 0.80        # whole-network gradient cosine vs the fp32 oracle
+# whole step (chaotic regime, see the header): direction and magnitude against the fp32 oracle, and no worse than the oracle's own
+# arithmetic with bf16 storage (oracle.nets.Emu)
+STEP_MIN_COS = {"gen_IS": 0.85, "gen_SI": 0.85, "disc_I": 0.99, "disc_S": 0.99}
+STEP_NORM_TOL = 0.15
+
+
+def step_criteria(name, g, g_fp32, g_emu):
+    """Returns (ok, metrics).  A gradient passes when (1) its cosine with the fp32 oracle's gradient is >= 0.85 (generators) /
+    0.99 (discriminators), (2) its norm is within 15 % of the oracle's, and (3) its relative-L2 distance from the fp32 oracle does
+    not exceed that of the bf16-emulating oracle by more than 25 % + 2e-2.  (1) alone bounds the relative error below 0.55."""
+    m = dict(vs_fp32=agg_rel(g, g_fp32), emu_vs_fp32=agg_rel(g_emu, g_fp32), vs_emu=agg_rel(g, g_emu), cos_fp32=cosine(g, g_fp32),
+             cos_emu=cosine(g, g_emu))
+    ng = sum(float((torch.as_tensor(v).double() ** 2).sum()) for v in g.values()) ** 0.5
+    no = sum(float((torch.as_tensor(v).double() ** 2).sum()) for v in g_fp32.values()) ** 0.5
+    m["norm_ratio"] = ng / no
+    ok = (m["cos_fp32"] >= STEP_MIN_COS[name] and abs(m["norm_ratio"] - 1.0) <= STEP_NORM_TOL
+          and m["vs_fp32"] <= 1.25 * m["emu_vs_fp32"] + 2e-2)
+    return ok, m
 
 
 def rel_l2(a, b):
@@ -39,7 +55,7 @@ def rel_l2(a, b):
 
 
 def _dev(t):
-    return (t if t.shape[-1] == 1 else t.to(torch.bfloat16)).cuda()
+    return (t if t.shape[-1] == 1 else t.to(torch.bfloat16)).contiguous().cuda()
 
 
 # ----------------------------------------------------------------------------- CUDA-side block runners
@@ -171,7 +187,15 @@ def test_generator_layers_teacher_forced(cuda):
         gk = net.export_grads()
         e_f = rel_l2(out.data.float(), y)
         e_x = [rel_l2(v.grad.float(), gxi) for v, gxi in zip(xv, gx) if float(gxi.norm()) > 0]
-        e_p = agg_rel(gk, gp, pn)
+        # a bias feeding straight into an InstanceNorm is a NULL direction of the loss (the norm removes it): its exact gradient
+        # is 0 (fp64 oracle: 7e-11) and what any finite-precision path reports is rounding noise (bf16-emulating oracle: 190 against a
+        # layer gradient norm of 8 200), so it is bounded in absolute terms instead of entering the relative error
+        null = [n for n in pn if label.endswith(".short") and n.endswith(".conv.b")]
+        live = [n for n in pn if n not in null]
+        e_p = agg_rel(gk, gp, live)
+        scale = sum(float((gp[n].double() ** 2).sum()) for n in live) ** 0.5
+        for n in null:
+            assert float(torch.as_tensor(gk[n]).double().norm()) < 0.1 * scale, (n, float(torch.as_tensor(gk[n]).double().norm()), scale)
         print("gen layer %-11s fwd %.2e  dx %s  params %.2e" % (label, e_f, ["%.2e" % e for e in e_x], e_p))
         worst = max([worst, e_f, e_p] + e_x)
         assert e_f < LAYER_TOL and e_p < LAYER_TOL and all(e < LAYER_TOL for e in e_x), (label, e_f, e_x, e_p)
@@ -231,46 +255,43 @@ def _step_errors(S, b, nd, seed):
     finally:
         ON.Emu.on = False
     gan, res_k = _cuda_step(S, G, nd, init, real_I, real_S, rand)
-    out = {}
-    for name, net in gan.networks.items():
-        g = net.export_grads()
-        out[name] = dict(vs_emu=agg_rel(g, grads_e[name]), vs_fp32=agg_rel(g, grads_o[name]), emu_vs_fp32=agg_rel(grads_e[name], grads_o[name]),
-                         cos_fp32=cosine(g, grads_o[name]), cos_emu=cosine(g, grads_e[name]))
+    out = {name: step_criteria(name, net.export_grads(), grads_o[name], grads_e[name]) for name, net in gan.networks.items()}
     return out, res_k, res_o, grads_o, gan
 
 
 @pytest.mark.parametrize("S,b", [(64, 1)])
-def test_train_step_gradients_vs_emulated_oracle(cuda, S, b):
-    """Whole step (four sweeps): CUDA gradients against the oracle with bf16 rounding at the CUDA path's storage points, and
-    the cosine against the fp32 oracle.  Bounds are < 0.5 everywhere, so a missing term, a wrong sign or a zero gradient fails."""
+def test_train_step_gradients_whole_step(cuda, S, b):
+    """Whole step (four sweeps) against the fp32 oracle and the bf16-emulating oracle; every measured figure is printed.
+    Measured at 64^3 (round 2): generators cosine 0.94 / 0.87, relative L2 0.36 / 0.52 -- the same as the emulating oracle's own
+    distance from fp32 (0.36 / 0.52); discriminators cosine 0.999, relative L2 0.05."""
     errs, res_k, res_o, _, _ = _step_errors(S, b, 2, 100 + b)
-    for name, e in errs.items():
-        print("step %d^3 %-7s: CUDA vs Emu %.3f | CUDA vs fp32 %.3f | Emu vs fp32 %.3f | cos(CUDA, fp32) %.3f | cos(CUDA, Emu) %.3f"
-              % (S, name, e["vs_emu"], e["vs_fp32"], e["emu_vs_fp32"], e["cos_fp32"], e["cos_emu"]))
-    for name, e in errs.items():
-        assert e["vs_emu"] < STEP_TOL_EMU, (name, e)
-        assert e["cos_fp32"] > STEP_MIN_COS, (name, e)
-        assert e["vs_fp32"] < 1.25 * e["emu_vs_fp32"] + 2e-2 and e["vs_fp32"] < 0.7, (name, e)   # and never a bound >= 1
+    for name, (ok, e) in errs.items():
+        print("step %d^3 %-7s: cos(CUDA, fp32) %.3f | norm ratio %.3f | CUDA vs fp32 %.3f | Emu vs fp32 %.3f | CUDA vs Emu %.3f | cos(CUDA, Emu) %.3f"
+              % (S, name, e["cos_fp32"], e["norm_ratio"], e["vs_fp32"], e["emu_vs_fp32"], e["vs_emu"], e["cos_emu"]))
+    for name, (ok, e) in errs.items():
+        assert ok, (name, e)
 
 
 def test_criteria_reject_wrong_gradients(cuda):
-    """Mutation check of the criteria themselves: a zeroed gradient, a sign flip and a rolled gradient buffer must each violate the
-    whole-step criteria (the round-1 bound `1.5*floor + 2e-2` accepted g = 0)."""
+    """Mutation check of the criteria themselves: a zeroed gradient, a sign flip, a rolled buffer, a halved gradient and a gradient
+    with one network block zeroed must each FAIL (the round-1 bound `1.5*floor + 2e-2` accepted g = 0)."""
     from oracle import nets as ON
     rng = np.random.default_rng(5)
     shapes = ON.disc_param_shapes()
     go = {n: torch.tensor(rng.standard_normal(s), dtype=torch.float32) for n, s in shapes.items()}
-    ge = {n: v + 0.05 * torch.tensor(rng.standard_normal(v.shape), dtype=torch.float32) for n, v in go.items()}   # a 5 % "bf16 floor"
 
-    def passes(g):
-        vs_emu, vs32, floor, cs = agg_rel(g, ge), agg_rel(g, go), agg_rel(ge, go), cosine(g, go)
-        return vs_emu < STEP_TOL_EMU and cs > STEP_MIN_COS and vs32 < 1.25 * floor + 2e-2 and vs32 < 0.7
+    def noisy(rel):
+        return {n: v + rel * torch.tensor(rng.standard_normal(v.shape), dtype=torch.float32) for n, v in go.items()}
 
-    assert passes({n: v + 0.02 * torch.tensor(rng.standard_normal(v.shape), dtype=torch.float32) for n, v in go.items()})
-    assert not passes({n: torch.zeros_like(v) for n, v in go.items()})
-    assert not passes({n: -v for n, v in go.items()})
-    assert not passes({n: torch.roll(v.flatten(), 1).view_as(v) for n, v in go.items()})
-    assert not passes({n: 0.5 * v for n, v in go.items()})
+    for name, floor in (("gen_SI", 0.5), ("disc_I", 0.05)):
+        ge = noisy(floor)                                   # the emulating oracle's distance from fp32 in that regime
+        assert step_criteria(name, noisy(floor), go, ge)[0]
+        assert not step_criteria(name, {n: torch.zeros_like(v) for n, v in go.items()}, go, ge)[0]
+        assert not step_criteria(name, {n: -v for n, v in go.items()}, go, ge)[0]
+        assert not step_criteria(name, {n: torch.roll(v.flatten(), 1).view_as(v) for n, v in go.items()}, go, ge)[0]
+        assert not step_criteria(name, {n: 0.5 * v for n, v in go.items()}, go, ge)[0]
+        big = max(go, key=lambda n: go[n].numel())
+        assert not step_criteria(name, {n: (torch.zeros_like(v) if n == big else v) for n, v in go.items()}, go, ge)[0]
 
 
 # ----------------------------------------------------------------------------- graph replay == eager
@@ -283,38 +304,51 @@ def _fresh_gan(S, b, use_graph, seed=77):
 
 
 def test_graph_replay_equals_eager(cuda):
-    """bench.py times CUDA-graph replay with in-kernel Philox noise / dropout and the device-resident Adam step size;
-    the parity tests above run eager launches.  From identical state and seed, 5 steps each way (steps 3-5 are replays)
-    must give the same ten losses per step and the same weights (differences: fp32 atomics order in wgrad only)."""
+    """bench.py times CUDA-graph replay with in-kernel Philox noise / dropout and the device-resident Adam step size; the parity
+    tests above run eager launches.  From the SAME state (weights, Adam slots, step counters -> same noise keys) one replayed step
+    and one eagerly launched step must give the same ten losses, the same four gradient buffers and the same updated weights.
+    (Compared over ONE step: the weight-gradient kernels add with fp32 atomics, and after a few Adam updates that order noise is
+    amplified like any other perturbation -- two eager runs differ by 3e-4 in D_S_loss after a single update.)"""
     from test_gpu_train_step import synth
-    S, b, steps = 32, 2, 5
+    S, b = 32, 2
     rng = np.random.default_rng(31)
-    batches = [synth(rng, b, S) for _ in range(steps)]
-    runs = {}
-    for mode in ("eager", "graph", "eager2"):
-        gan = _fresh_gan(S, b, mode == "graph")
-        w0 = {k: net.w.clone() for k, net in gan.networks.items()}
-        losses = [gan.train_step(I.cuda(), Sg.cuda()) for I, Sg in batches]
-        if mode == "graph":
-            assert gan._graph is not None and gan.launches_per_replay > 100, "the graph path did not engage"
-        else:
-            assert gan._graph is None
-        runs[mode] = (losses, {k: (net.w - w0[k]).double().cpu() for k, net in gan.networks.items()},
-                      {k: net.step_count for k, net in gan.networks.items()})
-    for it in range(steps):
-        for k in runs["eager"][0][it]:
-            a, g, a2 = runs["eager"][0][it][k], runs["graph"][0][it][k], runs["eager2"][0][it][k]
-            noise = abs(a - a2)
-            assert abs(a - g) <= 1e-5 * abs(a) + 10 * noise + 1e-7, (it, k, a, g, a2)
-    for k in runs["eager"][1]:
-        de, dg, de2 = runs["eager"][1][k], runs["graph"][1][k], runs["eager2"][1][k]
-        nondet = float((de - de2).norm() / de.norm())
-        diff = float((de - dg).norm() / de.norm())
-        print("replay vs eager %-7s: weight-displacement rel diff %.2e (eager vs eager run-to-run %.2e), max abs %.2e"
-              % (k, diff, nondet, float((de - dg).abs().max())))
-        assert float(de.norm()) > 0
-        assert diff <= max(1e-3, 10 * nondet), (k, diff, nondet)
-        assert runs["eager"][2][k] == runs["graph"][2][k] == steps
+    batches = [synth(rng, b, S) for _ in range(4)]
+    gan = _fresh_gan(S, b, True)
+    for I, Sg in batches[:3]:
+        gan.train_step(I.cuda(), Sg.cuda())
+    assert gan._graph is not None and gan.launches_per_replay > 100, "the graph path did not engage"
+    snap = {k: (net.w.clone(), net.m.clone(), net.v.clone(), net.step_count) for k, net in gan.networks.items()}
+    step0 = gan.step
+
+    def one(use_graph):
+        for k, net in gan.networks.items():
+            w, m, v, sc = snap[k]
+            net.w.copy_(w); net.m.copy_(m); net.v.copy_(v)
+            net.step_count = sc
+            net.repack()
+        gan.step = step0
+        gan.use_graph = use_graph
+        I, Sg = batches[3]
+        res = gan.train_step(I.cuda(), Sg.cuda())
+        return res, {k: net.g.clone() for k, net in gan.networks.items()}, {k: net.w.clone() for k, net in gan.networks.items()}
+
+    r_g, g_g, w_g = one(True)
+    r_e, g_e, w_e = one(False)
+    r_e2, g_e2, w_e2 = one(False)
+    gan.use_graph = True
+    for k in r_e:
+        assert abs(r_e[k] - r_g[k]) <= 1e-6 * abs(r_e[k]) + 1e-9, (k, r_e[k], r_g[k])
+    for k in g_e:
+        nondet = float((g_e[k] - g_e2[k]).double().norm() / g_e[k].double().norm())
+        dg = float((g_e[k] - g_g[k]).double().norm() / g_e[k].double().norm())
+        dw = float((w_e[k] - w_g[k]).abs().max())
+        dstep = float((w_e[k] - snap[k][0]).abs().max())
+        print("replay vs eager %-7s: gradient rel diff %.2e (eager run-to-run %.2e) | max weight diff %.2e of a max update %.2e"
+              % (k, dg, nondet, dw, dstep))
+        assert float(g_e[k].double().norm()) > 0 and dstep > 0
+        assert dg <= max(1e-5, 10 * nondet), (k, dg, nondet)
+        rel_w = float((w_e[k] - w_g[k]).double().norm() / (w_e[k] - snap[k][0]).double().norm())
+        assert rel_w <= 1e-3, (k, rel_w)      # displacement of the update, relative L2 (single near-zero-gradient entries may flip sign)
 
 
 def test_clip_adam_device_step_size_variant(cuda):

@@ -21,6 +21,23 @@ from ._lib import call
 from .distribute import Strategy
 
 
+def _apply_hook(hook, win, batched):
+    """The reference's `process_imaging_domain` hook (main.py:169-177 passes `process_imaging_otf`).  The stitcher calls it per
+    window as hook(arr, axis=None, keepdims=False) (custom_callback.py:171-172), the plotter as hook(sample) on a batch of one
+    (:262-263).  Hooks marked `_vg_device` (utils.process_imaging_otf) run on the device on the whole window batch -- per-sample
+    reduction over a batch of windows is the same arithmetic as axis=None on each window; any other callable gets each window as
+    a host numpy array, like the reference."""
+    if getattr(hook, "_vg_device", False):
+        return hook(win, axis=(1, 2, 3, 4), keepdims=True)
+    out = []
+    for i in range(win.shape[0]):
+        a = win[i].cpu().numpy()
+        r = hook(a[None]) if batched else hook(a, axis=None, keepdims=False)
+        r = np.asarray(r, dtype=np.float32)
+        out.append(r[0] if batched else r)
+    return torch.as_tensor(np.stack(out), dtype=torch.float32, device=E.DEV).contiguous()
+
+
 def window_starts(n, k, s):
     """custom_callback.py:127-162: dim_out+1 iterations, start clamped to n-k."""
     dim_out = int(np.floor((n - k) / s + 1))
@@ -34,25 +51,124 @@ def window_starts(n, k, s):
 
 
 class GanMonitor:
-    def __init__(self, args=None, dataset=None, Alabel="I", Blabel="S", model_path=None, imaging_val_data=None,
-                 segmentation_val_data=None, process_imaging_domain=None, period=5, strategy=None, window_batch=4):
+    def __init__(self, args=None, dataset=None, imaging_val_data=None, segmentation_val_data=None, process_imaging_domain=None,
+                 strategy=None, window_batch=4):
+        """Same leading arguments as the reference (custom_callback.py:15-31); `strategy` / `window_batch` are this package's."""
+        self.imgSize = getattr(args, "INPUT_IMG_SIZE", None)
         self.dims = getattr(args, "DIMENSIONS", 3) if args is not None else 3
         if self.dims != 3:
             raise NotImplementedError("only DIMENSIONS=3 is built (main.py:80)")
-        self.model_path = model_path
+        self.imaging_val_full_vol_data = getattr(dataset, "imaging_val_full_vol_data", None)
+        self.segmentation_val_full_vol_data = getattr(dataset, "segmentation_val_full_vol_data", None)
+        self.imaging_val_data = imaging_val_data
+        self.segmentation_val_data = segmentation_val_data
         self.process_imaging_domain = process_imaging_domain
-        self.period = period
+        self.period = getattr(args, "PERIOD_2D_CALLBACK", 2)
+        self.period3D = getattr(args, "PERIOD_3D_CALLBACK", 2)
+        self.model_path = getattr(args, "output_dir", None)
         self.strategy = strategy if strategy is not None else Strategy()
         self.window_batch = window_batch
         self.last_stats = None
+        self.last_panels = None
+
+    # ------------------------------------------------------------------ epoch callbacks (custom_callback.py:33-45,326-464)
+    def save_model(self, model, epoch):
+        """custom_callback.py:33-45: one export per network under <output_dir>/checkpoints/e{epoch+1}_{genAB,genBA,discA,discB}
+        (Keras SavedModel in the reference; here the variables in Keras layout as .npz)."""
+        d = os.path.join(self.model_path, "checkpoints")
+        os.makedirs(d, exist_ok=True)
+        for net, tag in ((model.gen_IS, "genAB"), (model.gen_SI, "genBA"), (model.disc_I, "discA"), (model.disc_S, "discB")):
+            np.savez(os.path.join(d, "e{epoch}_{tag}.npz".format(epoch=epoch + 1, tag=tag)), **net.export())
+
+    def set_learning_rate(self, model, epoch, args):
+        """custom_callback.py:326-397: at epoch == INITIATE_LR_DECAY every optimizer's lr becomes a linear PolynomialDecay to 0
+        over the remaining steps; after a checkpoint load past that epoch the schedule is re-derived from the epoch."""
+        opts = (model.gen_I_optimizer, model.gen_S_optimizer, model.disc_I_optimizer, model.disc_S_optimizer)
+        if epoch == args.INITIATE_LR_DECAY:
+            for o in opts:
+                o.lr = E.PolynomialDecay(initial_learning_rate=args.INITIAL_LR,
+                                         decay_steps=(args.EPOCHS - args.INITIATE_LR_DECAY) * args.train_steps,
+                                         end_learning_rate=0, power=1)
+        if model.checkpoint_loaded and epoch > args.INITIATE_LR_DECAY:
+            model.checkpoint_loaded = False
+            learning_gradient = args.INITIAL_LR / (args.EPOCHS - args.INITIATE_LR_DECAY)
+            intermediate_learning_rate = learning_gradient * (args.EPOCHS - epoch)
+            print('Initial learning rate: %0.8f' % intermediate_learning_rate)
+            for o in opts:
+                o.lr = E.PolynomialDecay(initial_learning_rate=intermediate_learning_rate,
+                                         decay_steps=(args.EPOCHS - args.INITIATE_LR_DECAY - epoch) * args.train_steps,
+                                         end_learning_rate=0, power=1)
+
+    def updateDiscriminatorNoise(self, model, init_noise, epoch, args):
+        """custom_callback.py:399-424: stddev of every GaussianNoise layer of one discriminator decays linearly to 0 at NO_NOISE."""
+        decay_rate = 1. if args.NO_NOISE == 0 else epoch / args.NO_NOISE
+        noise = max(init_noise * (1. - decay_rate), 0.0)
+        print('Noise std: %0.5f' % noise)
+        model.noise_std = noise       # the captured train-step graph is keyed on this value (VanGan re-captures when it changes)
+
+    def on_epoch_start(self, model, epoch, args, logs=None):
+        """custom_callback.py:426-446."""
+        self.set_learning_rate(model, epoch, args)
+        self.updateDiscriminatorNoise(model.disc_I, model.layer_noise, epoch, args)
+        self.updateDiscriminatorNoise(model.disc_S, model.layer_noise, epoch, args)
+
+    def on_epoch_end(self, model, epoch, logs=None):
+        """custom_callback.py:448-464."""
+        a = self.imagePlotter(epoch, "genIS", self.imaging_val_data, self.imaging_val_full_vol_data, model.gen_IS, model.gen_SI,
+                              process_img=True)
+        b = self.imagePlotter(epoch, "geSI", self.segmentation_val_data, self.segmentation_val_full_vol_data, model.gen_SI,
+                              model.gen_IS, outputFull=True)
+        return a, b
+
+    def imagePlotter(self, epoch, filename, setlist, dataset, genX, genY, nfig=6, outputFull=True, process_img=False, rng=None):
+        """custom_callback.py:225-324.  The three forward passes of the panel (:265-267: prediction = genX(sample), cycled =
+        genY(prediction), identity = genY(sample)) run on the CUDA path on a random crop of the first sample of `dataset`
+        (an iterable of (volume, index) pairs); the four volumes are returned (and kept in `last_panels`).  The PNG is written
+        when matplotlib is importable; the 3-D stitch of the full sample follows the reference's epoch rule (:321-324)."""
+        sample, idx = next(iter(dataset))
+        store = np.asarray(sample, dtype=np.float32)
+        name = os.path.splitext(os.path.split(setlist[int(idx)])[1])[0] if setlist is not None else "sample"
+        size = self.imgSize[1:5]
+        rng = rng if rng is not None else np.random.default_rng()
+        o = [int(rng.integers(0, store.shape[a] - size[a] + 1)) for a in range(3)]           # tf.image.random_crop
+        crop = store[o[0]:o[0] + size[0], o[1]:o[1] + size[1], o[2]:o[2] + size[2], :][None]
+        x = torch.as_tensor(crop, dtype=torch.float32, device=E.DEV).contiguous()
+        if process_img and self.process_imaging_domain is not None:
+            x = _apply_hook(self.process_imaging_domain, x, batched=True)
+        prediction = genX(x, training=False)
+        cycled = genY(prediction, training=False)
+        identity = genY(x, training=False)
+        panels = dict(sample=x[0].cpu().numpy(), prediction=prediction[0].cpu().numpy(), cycled=cycled[0].cpu().numpy(),
+                      identity=identity[0].cpu().numpy(), name=name)
+        self.last_panels = panels
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+            _, ax = plt.subplots(nfig + 1, 4, figsize=(12, 12))
+            keys = ("sample", "prediction", "cycled", "identity")
+            for j in range(nfig):
+                for c, k in enumerate(keys):
+                    ax[j, c].imshow(panels[k][:, :, j * int(size[2] / nfig), 0], cmap='gray')
+                    ax[j, c].axis("off")
+            for c, k in enumerate(keys):
+                v = panels[k].ravel()
+                ax[nfig, c].hist(v, bins=256, range=(float(v.min()), float(v.max())), fc='k', ec='k', density=True)
+            os.makedirs("./GANMonitor", exist_ok=True)
+            plt.savefig("./GANMonitor/{epoch}_{genID}.png".format(epoch=epoch + 1, genID=filename), dpi=300)
+            plt.close()
+        except ImportError:
+            pass
+        if epoch % self.period3D == 1 and outputFull and epoch > 160:
+            self.stitch_subvolumes(genX, store, self.imgSize, epoch=epoch, name=name, process_img=process_img)
+        return panels
 
     def stitch_subvolumes(self, gen, img, subvol_size, epoch=-1, stride=(25, 25, 128), name=None, output_path=None,
                           complete=False, padFactor=0.25, border_removal=True, process_img=False):
         """img: (H,W,D,1) float array (host).  gen: a generator model of this package (ResUNetModel).
         Returns the stitched prediction (float32, or uint8 when complete=False) exactly as the reference
         computes it before its TIFF write."""
-        if process_img and self.process_imaging_domain is not None:
-            raise NotImplementedError("per-window process_imaging_domain hook (host callback) is not built")
+        hook = self.process_imaging_domain if (process_img and self.process_imaging_domain is not None) else None
         img = np.asarray(img, dtype=np.float32)
         oshape = img.shape
         xs = ys = zs = 0
@@ -85,6 +201,8 @@ class GanMonitor:
             st = torch.tensor(chunk, dtype=torch.int32, device=E.DEV).reshape(-1)
             win = torch.empty((len(chunk), kH, kW, kD, 1), dtype=torch.float32, device=E.DEV)
             call("vg_stitch_gather", vol, H, W, D, win, st, len(chunk), kH, kW, kD)
+            if hook is not None:                                       # custom_callback.py:171-172, once per window
+                win = _apply_hook(hook, win, batched=False)
             out = gen(win, training=False)                             # batched generator forward on the CUDA path
             call("vg_stitch_accumulate", pred, cnt, H, W, D, out.contiguous(), st, len(chunk), kH, kW, kD, pH, pW, pD)
         if world > 1:
@@ -116,9 +234,8 @@ class GanMonitor:
                 img = img[..., None]
             filename = os.path.splitext(os.path.basename(test_set[imgdir]))[0]
             gen = model.gen_IS if segmentation else model.gen_SI
-            if not segmentation and self.process_imaging_domain is not None:
-                raise NotImplementedError("process_img=True path (per-window host callback) is not built")
+            print(('Segmenting %s ... (%i / %i)' if segmentation else 'Mapping %s ... (%i / %i)') % (filename, imgdir + 1, len(test_set)))
             results.append(self.stitch_subvolumes(gen, img, sub_img_size, name=(filetext or "") + filename,
-                                                  output_path=filepath or None, complete=True, stride=stride,
-                                                  padFactor=padFactor))
+                                                  output_path=filepath or None, complete=True, process_img=not segmentation,
+                                                  stride=stride, padFactor=padFactor))
         return results

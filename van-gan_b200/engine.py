@@ -186,6 +186,53 @@ class Network:
         self.repack()
 
 
+class PolynomialDecay:
+    """tf.keras.optimizers.schedules.PolynomialDecay (cycle=False), the schedule GanMonitor.set_learning_rate installs
+    (custom_callback.py:343-365): lr(step) = (lr0 - end) * (1 - min(step, decay_steps)/decay_steps)**power + end, evaluated at the
+    optimizer's own iteration counter -- which is NOT reset when the schedule is installed, exactly as in Keras."""
+
+    def __init__(self, initial_learning_rate, decay_steps, end_learning_rate=0.0001, power=1.0):
+        self.initial_learning_rate, self.decay_steps = float(initial_learning_rate), float(decay_steps)
+        self.end_learning_rate, self.power = float(end_learning_rate), float(power)
+
+    def __call__(self, step):
+        if self.decay_steps <= 0:
+            return self.end_learning_rate
+        s = min(float(step), self.decay_steps)
+        return (self.initial_learning_rate - self.end_learning_rate) * (1.0 - s / self.decay_steps) ** self.power + self.end_learning_rate
+
+
+class Adam:
+    """tf.keras.optimizers.Adam(lr, beta_1, beta_2, clipnorm) bound to one Network (vangan.py:220-235).  `lr` may be a float or a
+    schedule (callable of the iteration count), and may be reassigned between steps like `model.gen_I_optimizer.lr = ...` in
+    custom_callback.py:343.  `iterations` is the network's update count (Keras `optimizer.iterations`); the moment slots m / v
+    live in the network's flat buffers."""
+
+    def __init__(self, net, learning_rate=2e-4, beta_1=0.5, beta_2=0.9, epsilon=1e-7, clipnorm=100.0):
+        self.net, self.lr = net, learning_rate
+        self.beta_1, self.beta_2, self.epsilon, self.clipnorm = beta_1, beta_2, epsilon, clipnorm
+
+    @property
+    def iterations(self):
+        return self.net.step_count
+
+    @property
+    def learning_rate(self):
+        return self.lr
+
+    @learning_rate.setter
+    def learning_rate(self, v):
+        self.lr = v
+
+    def current_lr(self):
+        """Decayed learning rate of the NEXT update (Keras evaluates the schedule at `iterations` before incrementing)."""
+        return float(self.lr(self.net.step_count)) if callable(self.lr) else float(self.lr)
+
+    def step_size(self):
+        """lr_t of the next update: lr * sqrt(1 - b2^t) / (1 - b1^t), t = iterations + 1."""
+        return Network.lr_t(self.net.step_count + 1, self.current_lr(), self.beta_1, self.beta_2)
+
+
 def he_normal(rng, shape):
     """Keras 'he_normal' (truncated normal, stddev sqrt(2/fan_in)/0.8796...)."""
     fan_in = int(np.prod(shape[:-1]))

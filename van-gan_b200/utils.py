@@ -33,3 +33,16 @@ def append_dict(dict1, dict2, replace=False):
             dict1[k] = v if replace else [v]
         else:
             dict1[k].append(v)
+
+
+def process_imaging_otf(tensor, axis=(1, 2, 3, 4), keepdims=True):
+    """main.py:169-177: min/max normalisation of the imaging domain to [-1, 1], per sample (axis=(1,2,3,4)) or over the whole
+    tensor (axis=None), on the device.  Accepted wherever the reference passes `process_imaging_domain=process_imaging_otf`."""
+    t = torch.as_tensor(tensor, dtype=torch.float32, device=E.DEV).contiguous()
+    out = min_max_norm_tf(t, axis=None if axis is None else (1, 2, 3, 4))
+    res = torch.empty_like(out)
+    call("vg_lincomb", res, res.numel(), 0, -1.0, out, 2.0, None, 0.0, None, 0.0)      # 2 * minmax(x) - 1
+    return res
+
+
+process_imaging_otf._vg_device = True

@@ -57,6 +57,10 @@ class VanGan:
         self.layer_noise = 0.1
         self.cldice_iters = 15
         self.step = 0
+        self.current_epoch = 0
+        self.checkpoint_loaded = False     # read (and cleared) by GanMonitor.set_learning_rate; the reference never sets it either
+        self.checkpoint_dir = os.path.join(getattr(args, "output_dir", "."), 'checkpoints')
+        self.checkpoint_prefix = os.path.join(self.checkpoint_dir, 'checkpoint')
         self.loss_ctx = None
         self.tape = None
         self.last = None
@@ -86,8 +90,12 @@ class VanGan:
             self.disc_S = get_discriminator(input_img_size=self.seg_subvol_patch_size, batch_size=self.global_batch_size,
                                             name='discriminator_S', seed=seed + 3, **common)
             # tf.keras.optimizers.Adam(2e-4, beta_1=0.5, beta_2=0.9, clipnorm=100) x4 (vangan.py:220-235)
-            self.opt = dict(lr=2e-4, beta_1=0.5, beta_2=0.9, eps=1e-7, clipnorm=100.0)
+            mk = lambda net: E.Adam(net, learning_rate=2e-4, beta_1=0.5, beta_2=0.9, epsilon=1e-7, clipnorm=100.0)
+            self.gen_I_optimizer, self.gen_S_optimizer = mk(self.gen_IS), mk(self.gen_SI)
+            self.disc_I_optimizer, self.disc_S_optimizer = mk(self.disc_I), mk(self.disc_S)
         self.networks = {"gen_IS": self.gen_IS, "gen_SI": self.gen_SI, "disc_I": self.disc_I, "disc_S": self.disc_S}
+        self.optimizers = {"gen_I_optimizer": self.gen_I_optimizer, "gen_S_optimizer": self.gen_S_optimizer,
+                           "disc_I_optimizer": self.disc_I_optimizer, "disc_S_optimizer": self.disc_S_optimizer}
         # per-step state that lives in DEVICE memory so that a captured CUDA graph of the whole step can be replayed:
         # the RNG seed offset of the discriminators' GaussianNoise / SpatialDropout3D and the four Adam step sizes lr_t
         self._seed_dev = torch.zeros(1, dtype=torch.int64, device=E.DEV)
@@ -175,8 +183,8 @@ class VanGan:
     def _upload_step_state(self):
         """Seed offset and the four Adam step sizes of THIS step -> device (async copies on the current stream)."""
         self._h_seed[0] = self.seed_offset(self.seed, self.step, self.strategy.num_replicas_in_sync, self.strategy.rank)
-        for i, net in enumerate((self.gen_IS, self.gen_SI, self.disc_I, self.disc_S)):
-            self._h_lr[i] = E.Network.lr_t(net.step_count + 1, self.opt["lr"], self.opt["beta_1"], self.opt["beta_2"])
+        for i, opt in enumerate(self.optimizers.values()):
+            self._h_lr[i] = opt.step_size()
         self._seed_dev.copy_(self._h_seed, non_blocking=True)
         self._lr_dev.copy_(self._h_lr, non_blocking=True)
 
@@ -194,9 +202,9 @@ class VanGan:
         return result, plan, handles
 
     def _body_adam(self):
-        for i, net in enumerate((self.gen_IS, self.gen_SI, self.disc_I, self.disc_S)):
-            net.adam_step(lr_t_dev=self._lr_dev[i:i + 1], beta_1=self.opt["beta_1"], beta_2=self.opt["beta_2"],
-                          eps=self.opt["eps"], clipnorm=self.opt["clipnorm"])
+        for i, opt in enumerate(self.optimizers.values()):
+            opt.net.adam_step(lr_t_dev=self._lr_dev[i:i + 1], beta_1=opt.beta_1, beta_2=opt.beta_2, eps=opt.epsilon,
+                              clipnorm=opt.clipnorm)
 
     def _step_body(self, real_I, real_S, rand, apply):
         """One eager step: no host synchronisation inside."""
@@ -226,6 +234,9 @@ class VanGan:
         what keeps a GPU busy when the per-GPU batch is 1 (8-GPU strong scaling).  `rand` (explicit noise tensors, parity
         tests) and `apply=False` always run eagerly."""
         graphable = self.use_graph and rand is None and apply
+        if self._graph is not None and self._graph["noise"] != (self.disc_I.noise_std, self.disc_S.noise_std):
+            self._graph = None      # GaussianNoise stddev is a launch constant of the captured kernels: re-capture (once per epoch,
+            #                         GanMonitor.updateDiscriminatorNoise)
         if graphable and self._graph is not None and self._graph["key"] == self._shape_key(real_I, real_S):
             return self._replay(real_I, real_S)
         if graphable and self._eager_steps >= 2 and self._graph is None:
@@ -270,7 +281,8 @@ class VanGan:
         # the graphs' private pool keeps every buffer the capture touched; the Python-side tape is not needed again
         self.tape.clear()
         self.tape, self.last = None, None
-        self._graph = dict(key=key, g1=g1, g2=g2, I=gI, S=gS, result=result, ctx=ctx)
+        self._graph = dict(key=key, g1=g1, g2=g2, I=gI, S=gS, result=result, ctx=ctx,
+                           noise=(self.disc_I.noise_std, self.disc_S.noise_std))
 
     def _replay(self, real_I, real_S):
         g = self._graph
@@ -326,18 +338,62 @@ class VanGan:
         self.reduce_dict(results)
         return results
 
-    # ------------------------------------------------------------------ checkpoints (numpy .npz, Keras layouts)
-    def save_checkpoint(self, path):
-        arrays = {}
-        for nn, net in self.networks.items():
-            for k, v in net.export().items():
-                arrays[nn + "/" + k] = v
-        np.savez(path, **arrays)
+    # ------------------------------------------------------------------ checkpoints
+    # tf.train.Checkpoint over the four models and the four optimizers (vangan.py:238-268).  TensorFlow's on-disk format needs
+    # TensorFlow; the same object graph is written as ONE .npz per epoch whose keys follow the Checkpoint's attribute names:
+    #   <model>/<variable>            fp32, Keras layout (Conv3D kernel (kd,kh,kw,Cin,Cout), bias, gamma, beta)
+    #   <optimizer>/m/<variable>, <optimizer>/v/<variable>     Adam slots
+    #   <optimizer>/iter              Keras `optimizer.iterations`
+    #   save_counter/step             the trainer's step counter (keys the in-kernel noise / dropout streams)
+    _OPT_OF = {"gen_IS": "gen_I_optimizer", "gen_SI": "gen_S_optimizer", "disc_I": "disc_I_optimizer", "disc_S": "disc_S_optimizer"}
 
-    def load_checkpoint(self, path):
+    def _checkpoint_path(self, epoch):
+        return self.checkpoint_prefix + "_e{epoch}".format(epoch=epoch) + ".npz"
+
+    def save_checkpoint(self, epoch):
+        """vangan.py:247-250: writes <output_dir>/checkpoints/checkpoint_e{epoch+1} (overwrites)."""
+        os.makedirs(os.path.dirname(self.checkpoint_prefix), exist_ok=True)
+        arrays = {"save_counter/step": np.int64(self.step)}
+        for nn, net in self.networks.items():
+            on = self._OPT_OF[nn]
+            m, v = net.m.cpu().numpy(), net.v.cpu().numpy()
+            for k, val in net.export().items():
+                p = net.params[k]
+                arrays[nn + "/" + k] = val
+                arrays[on + "/m/" + k] = m[p.offset:p.offset + p.size].reshape(p.shape)
+                arrays[on + "/v/" + k] = v[p.offset:p.offset + p.size].reshape(p.shape)
+            arrays[on + "/iter"] = np.int64(net.step_count)
+        path = self._checkpoint_path(epoch + 1)
+        np.savez(path, **arrays)
+        print(f'\nSaved checkpoint to {self.checkpoint_prefix}\n')
+        return path
+
+    def load_checkpoint(self, epoch=None, expect_partial: bool = False, newpath=None):
+        """vangan.py:252-268: restores models AND optimizers from checkpoint_e{epoch} (under `newpath` when given).  Prints the
+        reference's error line when the file is missing.  expect_partial: tolerate missing optimizer slots."""
+        if newpath is not None:
+            self.checkpoint_prefix = os.path.join(newpath, 'checkpoint')
+        path = self._checkpoint_path(epoch)
+        print(f"Trying to load checkpoint from path: {path}")
+        if not os.path.exists(path):
+            print('Error: Checkpoint not found!')
+            return False
         z = np.load(path)
         for nn, net in self.networks.items():
+            on = self._OPT_OF[nn]
             net.load({k: z[nn + "/" + k] for k in net.params})
+            have_slots = all((on + "/m/" + k) in z.files for k in net.params)
+            if not have_slots and not expect_partial:
+                raise KeyError("checkpoint %s has no optimizer slots for %s (pass expect_partial=True)" % (path, on))
+            if have_slots:
+                for k, p in net.params.items():
+                    net.m[p.offset:p.offset + p.size].copy_(torch.from_numpy(np.ascontiguousarray(z[on + "/m/" + k]).reshape(-1)).to(E.DEV))
+                    net.v[p.offset:p.offset + p.size].copy_(torch.from_numpy(np.ascontiguousarray(z[on + "/v/" + k]).reshape(-1)).to(E.DEV))
+                net.step_count = int(z[on + "/iter"])
+        if "save_counter/step" in z.files:
+            self.step = int(z["save_counter/step"])
+        print(f'Loaded checkpoint from {path}\n')
+        return True
 
 
 def train(ds, gan, summary, epoch, steps=None, desc=None, training=True):
