@@ -63,6 +63,14 @@ typedef struct {
 size_t vg_conv3d_packed_bytes(const vg_conv3d_desc* d, int for_dgrad);
 /* w_keras fp32 (K,K,K,Cin,Cout) -> packed bf16 operand layouts (call after every optimizer step) */
 int vg_conv3d_pack_weights(const vg_conv3d_desc* d, const float* w_keras, void* w_fwd, void* w_dgrad, void* stream);
+/* The same refresh for a whole network in ONE launch (after every optimizer step: 4 launches per train step instead of ~400).
+ * vg_conv3d_pack_jobs expands one layer into packing jobs (HOST call, no CUDA work; jobs_out: max_jobs * vg_pack_job_bytes() bytes,
+ * returns the number of jobs written); the caller concatenates the jobs of all layers, builds the exclusive prefix sum of
+ * vg_pack_job_total() over them, uploads both once, and calls vg_pack_run(jobs_dev, prefix_dev, njobs, total) per step. */
+int vg_conv3d_pack_jobs(const vg_conv3d_desc* d, const float* w_keras, void* w_fwd, void* w_dgrad, void* jobs_out, int max_jobs);
+size_t vg_pack_job_bytes(void);
+long long vg_pack_job_total(const void* jobs, int index);
+int vg_pack_run(const void* jobs_dev, const long long* prefix_dev, int njobs, long long total, void* stream);
 /* y = act(conv(x, w) + bias).  `w_fwd` is the packed buffer, or the fp32 Keras kernel when Cin == 1 */
 int vg_conv3d_fwd(const vg_conv3d_desc* d, const void* x, const void* w_fwd, const float* bias, void* y, void* stream);
 /* dx[N,ID,IH,IW,Cin] = conv_transpose(dy, w)  (gradient w.r.t. the PADDED input; fully overwritten).
@@ -197,6 +205,18 @@ int vg_stitch_accumulate(float* pred, float* cnt, int H, int W, int D, const flo
 int vg_stitch_finalize(const float* pred, const float* cnt, int H, int W, int D, int x0, int y0, int z0, int oH, int oW, int oD,
                        float* out, float* mm, void* enc_ws, void* stream);
 int vg_stitch_scale(float* out, size_t n, const float* mm, void* stream);
+/* Order-exact form of the same loop (custom_callback.py:142-192): every output voxel of rows [row0, row0+rows) adds the windows that
+ * cover it in the reference's enumeration order (rows, columns, depth; clamped last window repeated), sequentially in fp32, divides by
+ * the count and folds its value into the running min / max (enc_ws: 2 x u32, initialised when init_enc != 0).  wins: [slots][kH,kW,kD]
+ * generator outputs; slot_of[(i*nW + j)*nD + k]: enumeration index -> slot; starts_dev: the nH + nW + nD per-axis window starts back to
+ * back (<= 128 per axis); all DEVICE pointers.  Result is bit-identical to the numpy loop for any batching / sharding of the generator calls. */
+int vg_stitch_gather_sum(const float* wins, const int* slot_of, const int* starts_dev, int nH, int nW, int nD, int kH, int kW, int kD, int pH,
+                         int pW, int pD, int x0, int y0, int z0, int row0, int rows, int oW, int oD, float* out, void* enc_ws, int init_enc,
+                         void* stream);
+/* mm[0], mm[1] = decoded running min / max */
+int vg_stitch_minmax_decode(const void* enc_ws, float* mm, void* stream);
+/* out_u8 = (uint8)(255 * (in - mm[0]) / (mm[1] - mm[0]))   (custom_callback.py:202-205, complete=False) */
+int vg_stitch_scale_u8(const float* in, unsigned char* out, size_t n, const float* mm, void* stream);
 
 #ifdef __cplusplus
 }

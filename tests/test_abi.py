@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(names) >= 35
     for n in names:
         assert hasattr(lib, n), "missing export: %s" % n
-    assert lib.vg_abi_version() == 3
+    assert lib.vg_abi_version() == 4
 
 
 def test_ctypes_table_matches_header():

@@ -45,6 +45,10 @@ SIGNATURES = {
     "vg_tc_launch_count": (_ULL, []),
     "vg_conv3d_packed_bytes": (_Z, [_CD, _I]),
     "vg_conv3d_pack_weights": (_I, [_CD, _P, _P, _P, _P]),
+    "vg_conv3d_pack_jobs": (_I, [_CD, _P, _P, _P, _P, _I]),
+    "vg_pack_job_bytes": (_Z, []),
+    "vg_pack_job_total": (_LL, [_P, _I]),
+    "vg_pack_run": (_I, [_P, _P, _I, _LL, _P]),
     "vg_conv3d_fwd": (_I, [_CD, _P, _P, _P, _P, _P]),
     "vg_conv3d_dgrad": (_I, [_CD, _P, _P, _P, _P]),
     "vg_conv3d_wgrad": (_I, [_CD, _P, _P, _P, _P, _P]),
@@ -84,6 +88,9 @@ SIGNATURES = {
     "vg_stitch_accumulate": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_stitch_finalize": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "vg_stitch_scale": (_I, [_P, _Z, _P, _P]),
+    "vg_stitch_gather_sum": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "vg_stitch_minmax_decode": (_I, [_P, _P, _P]),
+    "vg_stitch_scale_u8": (_I, [_P, _P, _Z, _P, _P]),
 }
 
 _lib = None

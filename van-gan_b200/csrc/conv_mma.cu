@@ -20,6 +20,7 @@
 // general-shape path and the numerical cross-check for it.
 #include <stdlib.h>
 
+#include "pack_elem.cuh"
 #include "common.cuh"
 
 namespace {
@@ -434,39 +435,35 @@ int launch_wgrad_t(const WGrad& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------ weight packing
 // fwd pack: Wf[t][Np][Cin] (row = output channel, K contiguous); dgrad pack: per parity class,
 // Wd[class][t'][NpI][Cout] (row = input channel, K = output channel contiguous)
-__global__ void pack_fwd_kernel(const float* __restrict__ w, bf16* __restrict__ out, int T, int Cin, int Cout, int Np) {
-    size_t total = (size_t)T * Np * Cin;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        int ci = (int)(i % Cin);
-        int co = (int)((i / Cin) % Np);
-        int t = (int)(i / ((size_t)Cin * Np));
-        out[i] = __float2bfloat16(co < Cout ? w[((size_t)t * Cin + ci) * Cout + co] : 0.f);
-    }
+// one job per launch (per-layer API) ...
+__global__ void pack_job_kernel(const vg_pack_job job) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)job.total; i += (size_t)gridDim.x * blockDim.x)
+        job.out[i] = __float2bfloat16(pack_elem(job, i));
 }
 
-__global__ void pack_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ out, int K, int stride, int Cin, int Cout,
-                                  int NpI) {
-    // one launch handles every class; classes are laid out back to back
-    size_t base = 0;
-    for (int ad = 0; ad < stride; ad++)
-        for (int ah = 0; ah < stride; ah++)
-            for (int aw = 0; aw < stride; aw++) {
-                int td = (K - ad + stride - 1) / stride, th = (K - ah + stride - 1) / stride, tw = (K - aw + stride - 1) / stride;
-                if (K <= ad) td = 0;
-                if (K <= ah) th = 0;
-                if (K <= aw) tw = 0;
-                size_t cnt = (size_t)td * th * tw * NpI * Cout;
-                for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (size_t)gridDim.x * blockDim.x) {
-                    int co = (int)(i % Cout);
-                    int ci = (int)((i / Cout) % NpI);
-                    int tt = (int)(i / ((size_t)Cout * NpI));
-                    int w_ = tt % tw, h_ = (tt / tw) % th, d_ = tt / (tw * th);
-                    int kd = ad + stride * d_, kh = ah + stride * h_, kw = aw + stride * w_;
-                    int t = (kd * K + kh) * K + kw;
-                    out[base + i] = __float2bfloat16(ci < Cin ? w[((size_t)t * Cin + ci) * Cout + co] : 0.f);
-                }
-                base += cnt;
+// ... or every job of a network in ONE launch.  The packed elements of all jobs form one global index range; a block takes a
+// contiguous span of it (so a 16x16 shortcut and the 8.4 M-element PatchGAN layer load the grid equally), finds the job of its first
+// element by binary search in the prefix array and walks on from there.
+constexpr int PACK_SPAN = 4096;   // elements per block iteration
+__global__ void __launch_bounds__(256) pack_multi_kernel(const vg_pack_job* __restrict__ jobs, const long long* __restrict__ prefix, int njobs,
+                                                         long long total) {
+    for (long long s0 = (long long)blockIdx.x * PACK_SPAN; s0 < total; s0 += (long long)gridDim.x * PACK_SPAN) {
+        const long long s1 = s0 + PACK_SPAN < total ? s0 + PACK_SPAN : total;
+        int lo = 0, hi = njobs - 1;                 // last job with prefix[j] <= s0
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (prefix[mid] <= s0) lo = mid; else hi = mid - 1;
+        }
+        for (int j = lo; j < njobs && prefix[j] < s1; j++) {
+            const vg_pack_job job = jobs[j];
+            const long long b = prefix[j] > s0 ? prefix[j] : s0;
+            const long long e = prefix[j] + job.total < s1 ? prefix[j] + job.total : s1;
+            for (long long g = b + threadIdx.x; g < e; g += 256) {
+                const size_t i = (size_t)(g - prefix[j]);
+                job.out[i] = __float2bfloat16(pack_elem(job, i));
             }
+        }
+    }
 }
 
 inline int class_taps(int K, int stride, int a) { return K <= a ? 0 : (K - a + stride - 1) / stride; }
@@ -831,7 +828,7 @@ inline size_t rup256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" {
 
-int vg_abi_version(void) { return 3; }
+int vg_abi_version(void) { return 4; }
 
 size_t vg_conv3d_packed_bytes(const vg_conv3d_desc* d, int for_dgrad) {
     if (!desc_ok(d)) return 0;
@@ -850,41 +847,87 @@ size_t vg_conv3d_packed_bytes(const vg_conv3d_desc* d, int for_dgrad) {
     return bytes;
 }
 
-int vg_conv3d_pack_weights(const vg_conv3d_desc* d, const float* w, void* w_fwd, void* w_dgrad, void* stream) {
-    VG_REQUIRE(desc_ok(d) && w);
-    cudaStream_t st = (cudaStream_t)stream;
-    int T = d->K * d->K * d->K;
+// Expands one layer into its packing jobs (host only, no CUDA call).  Returns the number of jobs written, or a negative error.
+int vg_conv3d_pack_jobs(const vg_conv3d_desc* d, const float* w, void* w_fwd, void* w_dgrad, void* jobs_out, int max_jobs) {
+    VG_REQUIRE(desc_ok(d) && w && jobs_out && max_jobs > 0);
+    vg_pack_job* jobs = (vg_pack_job*)jobs_out;
+    int n = 0;
+    const int T = d->K * d->K * d->K, s_ = d->stride;
+    auto push = [&](const vg_pack_job& j) -> bool {
+        if (j.total <= 0) return true;
+        if (n >= max_jobs) return false;
+        jobs[n++] = j;
+        return true;
+    };
     if (w_fwd && d->Cin != 1) {
-        int Np = rup(d->Cout, NPAD);
-        pack_fwd_kernel<<<vg_grid_for((long long)T * Np * d->Cin, 256, 4), 256, 0, st>>>(w, (bf16*)w_fwd, T, d->Cin, d->Cout, Np); VG_LAUNCHED(1);
+        vg_pack_job j{};
+        j.w = w; j.out = (bf16*)w_fwd; j.kind = 0; j.K = d->K; j.stride = s_; j.Cin = d->Cin; j.Cout = d->Cout;
+        j.Np = rup(d->Cout, NPAD); j.T = T; j.total = (long long)T * j.Np * d->Cin;
+        if (!push(j)) return VG_ERR_WORKSPACE;
     }
     if (w_dgrad && d->Cout != 1) {
-        int NpI = rup(d->Cin, NPAD);
-        pack_dgrad_kernel<<<vg_grid_for((long long)T * NpI * d->Cout, 256, 4), 256, 0, st>>>(w, (bf16*)w_dgrad, d->K, d->stride,
-                                                                                          d->Cin, d->Cout, NpI); VG_LAUNCHED(1);
+        const int NpI = rup(d->Cin, NPAD);
+        bf16* dst = (bf16*)w_dgrad;
+        for (int a = 0; a < s_; a++)
+            for (int b = 0; b < s_; b++)
+                for (int c = 0; c < s_; c++) {
+                    vg_pack_job j{};
+                    j.w = w; j.out = dst; j.kind = 1; j.K = d->K; j.stride = s_; j.Cin = d->Cin; j.Cout = d->Cout;
+                    j.ad = a; j.ah = b; j.aw = c; j.td = class_taps(d->K, s_, a); j.th = class_taps(d->K, s_, b); j.tw = class_taps(d->K, s_, c);
+                    j.Np = NpI; j.total = (long long)j.td * j.th * j.tw * NpI * d->Cout;
+                    if (!push(j)) return VG_ERR_WORKSPACE;
+                    dst += j.total;
+                }
     }
     if (w_fwd && tc_fwd_ok(d)) {
         bf16* dst = (bf16*)((char*)w_fwd + rup256(mma_fwd_elems(d) * 2));
-        if (tc_fwd_s2(d)) {
-            if (vg_tc_pack(w, dst, d->K, 2, d->Cin, d->Cout, 2, 0, 0, 0, 2, 2, 2, st) != VG_OK) return VG_ERR_CUDA;
-        } else if (vg_tc_pack(w, dst, d->K, 1, d->Cin, d->Cout, 0, 0, 0, 0, d->K, d->K, d->K, st) != VG_OK) return VG_ERR_CUDA;
+        vg_pack_job j;
+        const bool ok = tc_fwd_s2(d) ? vg_tc_pack_job(w, dst, d->K, 2, d->Cin, d->Cout, 2, 0, 0, 0, 2, 2, 2, &j)
+                                     : vg_tc_pack_job(w, dst, d->K, 1, d->Cin, d->Cout, 0, 0, 0, 0, d->K, d->K, d->K, &j);
+        if (!ok) return VG_ERR_CUDA;
+        if (!push(j)) return VG_ERR_WORKSPACE;
     }
     if (w_dgrad && tc_dgrad_ok(d)) {
         char* dst = (char*)w_dgrad + rup256(mma_dgrad_elems(d) * 2);
-        const int s_ = d->stride;
         for (int a = 0; a < s_; a++)
             for (int b = 0; b < s_; b++)
                 for (int c = 0; c < s_; c++) {
                     size_t el = tc_dgrad_class_elems(d, a, b, c);
                     if (!el) continue;
-                    if (vg_tc_pack(w, (bf16*)dst, d->K, s_, d->Cin, d->Cout, 1, a, b, c, class_taps(d->K, s_, a), class_taps(d->K, s_, b),
-                                   class_taps(d->K, s_, c), st) != VG_OK)
+                    vg_pack_job j;
+                    if (!vg_tc_pack_job(w, (bf16*)dst, d->K, s_, d->Cin, d->Cout, 1, a, b, c, class_taps(d->K, s_, a), class_taps(d->K, s_, b),
+                                        class_taps(d->K, s_, c), &j))
                         return VG_ERR_CUDA;
+                    if (!push(j)) return VG_ERR_WORKSPACE;
                     dst += rup256(el * 2);
                 }
-        if (vg_tc_s2dgrad_ok(d->K, s_, d->Cin, d->Cout) &&
-            vg_tc_pack(w, (bf16*)dst, d->K, s_, d->Cin, d->Cout, 3, 0, 0, 0, 2, 2, 2, st) != VG_OK)   // fused classes, after the class packs
-            return VG_ERR_CUDA;
+        if (vg_tc_s2dgrad_ok(d->K, s_, d->Cin, d->Cout)) {   // fused classes, after the class packs
+            vg_pack_job j;
+            if (!vg_tc_pack_job(w, (bf16*)dst, d->K, s_, d->Cin, d->Cout, 3, 0, 0, 0, 2, 2, 2, &j)) return VG_ERR_CUDA;
+            if (!push(j)) return VG_ERR_WORKSPACE;
+        }
+    }
+    return n;
+}
+
+size_t vg_pack_job_bytes(void) { return sizeof(vg_pack_job); }
+
+long long vg_pack_job_total(const void* jobs, int index) { return ((const vg_pack_job*)jobs)[index].total; }
+
+int vg_pack_run(const void* jobs_dev, const long long* prefix_dev, int njobs, long long total, void* stream) {
+    VG_REQUIRE(jobs_dev && prefix_dev && njobs > 0 && total > 0);
+    pack_multi_kernel<<<vg_grid_for((total + PACK_SPAN - 1) / PACK_SPAN, 1, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const vg_pack_job*)jobs_dev, prefix_dev, njobs, total); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_conv3d_pack_weights(const vg_conv3d_desc* d, const float* w, void* w_fwd, void* w_dgrad, void* stream) {
+    vg_pack_job jobs[24];
+    const int n = vg_conv3d_pack_jobs(d, w, w_fwd, w_dgrad, jobs, 24);
+    if (n < 0) return n;
+    for (int i = 0; i < n; i++) {
+        pack_job_kernel<<<vg_grid_for(jobs[i].total, 256, 4), 256, 0, (cudaStream_t)stream>>>(jobs[i]); VG_LAUNCHED(1);
     }
     VG_CHECK_LAUNCH();
     return VG_OK;

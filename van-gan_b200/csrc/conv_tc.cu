@@ -35,6 +35,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include "pack_elem.cuh"
 #include "tc_ptx.cuh"
 
 namespace {
@@ -60,7 +61,7 @@ struct TcParams {
     int cls_cin;  // fused stride-2 dgrad: the GEMM columns are (parity class, input channel); cls_cin = Cin, 0 = off
     int dsplit;   // d-split: the kd taps become extra K-chunks (chunk = (kd, 16 channels)), each staging a BD-slice brick shifted by kd
     int dm_order[12];   // d-march: issue order of the source slices (overlapping TMEM windows kept >= 3 instructions apart)
-    int dm_lean;  // d-march issue loop driven by a per-slice table in shared memory (VG_TC_DMLEAN=1; not yet validated on a GPU)
+    int dm_lean;  // d-march issue sequence unrolled with immediate per-slice constants (default; VG_TC_DMLEAN=0 = round-1 loop)
     int dm;   // d-march: the TD taps along d are folded into the MMA N dimension (N = cnt * NCTA, sliding TMEM window)
     int stages, act, use_tma, dbg;   // dbg: bit0 = skip brick/weight loads, bit1 = skip MMA issue (timing experiments only)
     const bf16* x;        // source tensor (gather loader)
@@ -157,6 +158,47 @@ __device__ __forceinline__ void tc_st16_zero(uint32_t taddr) {
                  : "memory");
 }
 __device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+
+// d-march issue order.  Source slice s feeds the output tiles max(0, s-TD+1) .. min(BD-1, s); two slices whose TMEM windows overlap
+// (|s - s'| < TD) must not be issued back to back (an MMA that accumulates into columns a recent MMA wrote waits for it), so the slices
+// go out in the order s_i = (i * g) mod ED with the step g that maximises the smallest cyclic distance between overlapping windows.
+constexpr int dm_gcd(int a, int b) { return b == 0 ? a : dm_gcd(b, a % b); }
+constexpr int dm_step(int ED, int TD) {
+    int best_g = 1, best_d = -1;
+    for (int g = 1; g < ED; g++) {
+        if (dm_gcd(g, ED) != 1) continue;
+        int dmin = ED;
+        for (int i = 0; i < ED; i++)
+            for (int k = 1; k < ED; k++) {
+                const int si = (i * g) % ED, sj = ((i + k) * g) % ED;
+                const int ds = si > sj ? si - sj : sj - si;
+                if (ds < TD && k < dmin) dmin = k;
+            }
+        if (dmin > best_d) { best_d = dmin; best_g = g; }
+    }
+    return best_g;
+}
+
+// One (th, tw) tap of a d-march chunk: ED = BD + TD - 1 instructions, fully unrolled so that the slice index, its first output tile
+// and its width are immediates.  Measured (scripts/micro/mma_issue2/3): an issue loop that fetches these per-slice values from a
+// table (one dependent LDS per instruction, the VG_TC_DMLEAN experiment) or recomputes them from kernel parameters runs at 70-90
+// cycles per tcgen05.mma -- above the 44 cycles an N = 48 instruction needs -- so the loop, not the tensor pipe, set the pace of
+// the 16-channel layers.  Here an instruction costs two uniform multiply-adds.
+template <int BD, int TD>
+__device__ __forceinline__ void dm_issue_tap(uint32_t d0, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc0,
+                                             uint32_t tile_step, uint32_t ncta) {
+    constexpr int ED = BD + TD - 1;
+    constexpr int G = dm_step(ED, TD);
+#pragma unroll
+    for (int i = 0; i < ED; i++) {
+        const int sl = (i * G) % ED;
+        const int m_lo = sl - TD + 1 > 0 ? sl - TD + 1 : 0;
+        const int m_hi = sl < BD - 1 ? sl : BD - 1;
+        tc_mma(d0 + (uint32_t)m_lo * ncta, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)sl * tile_step),
+               ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)(TD - 1 - sl + m_lo) * ncta), idesc0 | ((((uint32_t)(m_hi - m_lo + 1) * ncta) >> 3) << 17), 1u);
+    }
+}
 
 template <int BD>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
@@ -325,21 +367,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         const uint32_t b_step = (2 * lbo_b) >> 4;
         const int sgn = p.st > 0 ? 1 : -1;
         const int aoff0 = p.st > 0 ? 0 : ((p.TD - 1) * p.EH + (p.TH - 1)) * p.EW + (p.TW - 1);
-        // lean d-march: everything that depends only on the slice (A offset, B offset, first TMEM column, instruction descriptor)
-        // is computed once, one table entry per issue position; the issue loop then costs one LDS.128 and two adds per MMA
-        uint4* s_dm = reinterpret_cast<uint4*>(bar_base + TC_TAIL - 192);
-        if (p.dm && p.dm_lean) {
-            const int EDl = BD + p.TD - 1;
-            if (lane < EDl) {
-                const int sl = p.dm_order[lane];
-                const int m_lo = sl - p.TD + 1 > 0 ? sl - p.TD + 1 : 0;
-                const int m_hi = sl < BD - 1 ? sl : BD - 1;
-                const uint32_t ncols = (uint32_t)((m_hi - m_lo + 1) * p.NCTA);
-                s_dm[lane] = make_uint4((uint32_t)(sl * tile_step), (uint32_t)((p.TD - 1 - sl + m_lo) * p.NCTA), (uint32_t)(m_lo * p.NCTA),
-                                        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24) | ((ncols >> 3) << 17));
-            }
-            __syncwarp();
-        }
         for (int wk = blockIdx.x; wk < p.nwork; wk += gridDim.x, it++) {
             const int buf = it & 1;
             // d-march: the epilogue hands every buffer over ZEROED (and pre-arrives once at start), so use n waits for completion n
@@ -366,16 +393,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                     int aoff_q = p.st > 0 ? 0 : (p.TH - 1) * p.EW + (p.TW - 1);
                     uint32_t bq = b_addr;
                     if (p.dm_lean) {
+                        // unrolled issue (default): per-slice constants are immediates, see dm_issue_tap
                         for (int th = 0; th < p.TH; th++) {
                             for (int tw = 0; tw < p.TW; tw++) {
                                 if (leader && !(p.dbg & 2)) {
                                     const uint32_t a_lo = a_lo_lbo | (a_base + (uint32_t)aoff_q);   // 14-bit address field: no carry below 256 KB
                                     const uint32_t b_lo = b_lbo_dm | bq;
-#pragma unroll 2
-                                    for (int i = 0; i < ED; i++) {
-                                        const uint4 e = s_dm[i];
-                                        tc_mma(d0 + e.z, ((uint64_t)a_hi << 32) | (a_lo + e.x), ((uint64_t)b_hi << 32) | (b_lo + e.y), e.w, 1u);
-                                    }
+                                    if (p.TD == 3) dm_issue_tap<BD, 3>(d0, a_hi, a_lo, b_hi, b_lo, idesc0, (uint32_t)tile_step, (uint32_t)p.NCTA);
+                                    else dm_issue_tap<BD, 2>(d0, a_hi, a_lo, b_hi, b_lo, idesc0, (uint32_t)tile_step, (uint32_t)p.NCTA);
                                 }
                                 aoff_q += sgn;
                                 bq += 2 * ntot;
@@ -687,9 +712,9 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
     static int dm_lean = -1;
     if (dm_lean < 0) {
         const char* e = getenv("VG_TC_DMLEAN");
-        dm_lean = (e && e[0] == '1') ? 1 : 0;
+        dm_lean = (e && e[0] == '0') ? 0 : 1;   // VG_TC_DMLEAN=0: the round-1 loop that recomputes the per-slice values (A/B testing)
     }
-    p.dm_lean = (p.dm && dm_lean && (size_t)p.nblk * ncta * sizeof(float) + 128 + 192 <= (size_t)TC_TAIL) ? 1 : 0;   // table = last 192 B of the tail
+    p.dm_lean = (p.dm && dm_lean) ? 1 : 0;
     static int bd_max = -1;   // d-march amortises its TD-1 edge slices over BD tiles: deeper bricks pay (VG_TC_BD overrides)
     if (bd_max < 0) {
         const char* e = getenv("VG_TC_BD");
@@ -768,75 +793,36 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
     return VG_OK;
 }
 
-// pack kernel for the tensor-core layout: out[nb][c][t][kh][n][j] = src(t, k = c*16+kh*8+j, col = nb*NCTA+n)
-// fwd:   src(t,k,col) = w[t][k][col]            (K = Cin, cols = Cout)
-// dgrad: src(t',k,col) = w[tap(t')][col][k]      (K = Cout, cols = Cin), taps restricted to one stride-parity class
-// fwd stride 2 (dgrad == 2): chunk c = (parity class a,b,c ; 16-channel chunk), taps t' in 2x2x2, src = w[2t'+a][k][col] (0 if >= K)
-__global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int K, int stride, int Cin, int Cout, int dgrad,
-                               int ad, int ah, int aw, int td, int th, int tw, int ncta, int nblk, int dm, int dsplit) {
-    const int T = dsplit ? th * tw : td * th * tw;
-    // dgrad == 3: fused stride-2 parity classes -- columns are (class, ci), every class padded to 2x2x2 taps
-    const int Kt = (dgrad == 1 || dgrad == 3) ? Cout : Cin, ncols = dgrad == 1 ? Cin : (dgrad == 3 ? 8 * Cin : Cout);
-    const int cpc = Kt / 16;
-    const int nchunks = (dgrad == 2 ? 8 : (dsplit ? td : 1)) * cpc;
-    size_t total = (size_t)nblk * nchunks * T * 2 * ncta * 8;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        size_t r = i;
-        int j = (int)(r % 8); r /= 8;
-        int n = (int)(r % ncta); r /= ncta;
-        int w_, h_, d_, kh;
-        if (dm) {
-            // d-march layout [q = (th, tw)][K half][pos][n][8]: position pos along N holds the tap that maps source slice s to output
-            // tile m_lo + pos, i.e. loop index td = TD-1-pos for a forward gather (slice = m + td) and td = pos for dgrad
-            int pos = (int)(r % td); r /= td;
-            kh = (int)(r % 2); r /= 2;
-            int q = (int)(r % (th * tw)); r /= (th * tw);
-            w_ = q % tw; h_ = q / tw;
-            d_ = dgrad == 1 ? pos : td - 1 - pos;
-        } else {
-            kh = (int)(r % 2); r /= 2;
-            int t = (int)(r % T); r /= T;
-            w_ = t % tw; h_ = (t / tw) % th; d_ = t / (tw * th);   // d-split: t < th*tw, d_ = 0 here, set from the chunk below
-        }
-        int c = (int)(r % nchunks);
-        int nb = (int)(r / nchunks);
-        int col = nb * ncta + n;
-        int k, kd, kh2, kw;
-        if (dgrad == 2) {
-            const int cls = c / cpc, cc = c - cls * cpc;
-            k = cc * 16 + kh * 8 + j;
-            kd = 2 * d_ + ((cls >> 2) & 1); kh2 = 2 * h_ + ((cls >> 1) & 1); kw = 2 * w_ + (cls & 1);
-        } else {
-            int cc = c;
-            if (dsplit) { d_ = c / cpc; cc = c - d_ * cpc; }
-            k = cc * 16 + kh * 8 + j;
-            kd = dgrad ? ad + stride * d_ : d_; kh2 = dgrad ? ah + stride * h_ : h_; kw = dgrad ? aw + stride * w_ : w_;
-        }
-        int ci = col;
-        if (dgrad == 3) {
-            const int cls = col / Cin;
-            ci = col - cls * Cin;
-            kd = ((cls >> 2) & 1) + 2 * d_; kh2 = ((cls >> 1) & 1) + 2 * h_; kw = (cls & 1) + 2 * w_;
-        }
-        int tap = (kd * K + kh2) * K + kw;
-        float v = 0.f;
-        if (col < ncols && kd < K && kh2 < K && kw < K)
-            v = (dgrad == 1 || dgrad == 3) ? w[((size_t)tap * Cin + ci) * Cout + k] : w[((size_t)tap * Cin + k) * Cout + col];
-        out[i] = __float2bfloat16(v);
-    }
+// pack kernel for the tensor-core layout (element function in pack_elem.cuh)
+__global__ void tc_pack_kernel(const vg_pack_job job) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)job.total; i += (size_t)gridDim.x * blockDim.x)
+        job.out[i] = __float2bfloat16(pack_elem_tc(job, i));
 }
 
-int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, int dgrad, int ad, int ah, int aw, int td, int th,
-               int tw, cudaStream_t st) {
+bool vg_tc_pack_job(const float* w, bf16* out, int K, int stride, int Cin, int Cout, int dgrad, int ad, int ah, int aw, int td, int th, int tw,
+                    vg_pack_job* job) {
     const int T = td * th * tw;
     const int ncols = dgrad == 1 ? Cin : (dgrad == 3 ? 8 * Cin : Cout);
     const bool dsplit = dgrad != 2 && dgrad != 3 && stride == 1 && vg_tc_dsplit(ncols, td, th, tw);
     const int ncta = dgrad == 3 ? 128 : (dsplit ? 64 : vg_tc_ncta(ncols, T));
-    if (!ncta) return VG_ERR_UNSUPPORTED;
-    const int nblk = (ncols + ncta - 1) / ncta;
-    size_t total = dgrad == 3 ? vg_tc_s2dgrad_elems(Cin, Cout) : vg_tc_pack_elems(ncols, dgrad == 1 ? Cout : (dgrad == 2 ? 8 * Cin : Cin), T);
-    tc_pack_kernel<<<vg_grid_for((long long)total, 256, 4), 256, 0, st>>>(w, out, K, stride, Cin, Cout, dgrad, ad, ah, aw, td, th, tw, ncta,
-                                                                          nblk, (dgrad != 3 && vg_tc_dmarch(ncta, td)) ? 1 : 0, dsplit ? 1 : 0);
+    if (!ncta) return false;
+    vg_pack_job j{};
+    j.w = w; j.out = out; j.kind = 2;
+    j.K = K; j.stride = stride; j.Cin = Cin; j.Cout = Cout;
+    j.dgrad = dgrad; j.ad = ad; j.ah = ah; j.aw = aw; j.td = td; j.th = th; j.tw = tw;
+    j.ncta = ncta; j.nblk = (ncols + ncta - 1) / ncta;
+    j.dm = (dgrad != 3 && vg_tc_dmarch(ncta, td)) ? 1 : 0;
+    j.dsplit = dsplit ? 1 : 0;
+    j.total = (long long)(dgrad == 3 ? vg_tc_s2dgrad_elems(Cin, Cout) : vg_tc_pack_elems(ncols, dgrad == 1 ? Cout : (dgrad == 2 ? 8 * Cin : Cin), T));
+    *job = j;
+    return true;
+}
+
+int vg_tc_pack(const float* w, bf16* out, int K, int stride, int Cin, int Cout, int dgrad, int ad, int ah, int aw, int td, int th,
+               int tw, cudaStream_t st) {
+    vg_pack_job job;
+    if (!vg_tc_pack_job(w, out, K, stride, Cin, Cout, dgrad, ad, ah, aw, td, th, tw, &job)) return VG_ERR_UNSUPPORTED;
+    tc_pack_kernel<<<vg_grid_for(job.total, 256, 4), 256, 0, st>>>(job);
     VG_LAUNCHED(1);
     return VG_OK;
 }

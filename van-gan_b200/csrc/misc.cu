@@ -287,6 +287,66 @@ __global__ void __launch_bounds__(NT) stitch_scale_kernel(float* __restrict__ ou
         out[i] = __fmul_rn(255.f, __fdiv_rn(__fsub_rn(out[i], mn), r));   // 255 * (data - dmin) / (dmax - dmin)
 }
 
+
+// Order-exact stitching (custom_callback.py:142-192 restated in gather form).  The reference adds the windows into `pred` one after the
+// other in enumeration order (i over rows, j over columns, k over depth; the clamped last window repeats).  Here every output voxel walks
+// the windows that cover it in that same order and adds their values sequentially in fp32, so the sum -- and hence pred / count, the global
+// min / max and the final uint8 cast -- is bit-identical to the numpy loop, whatever the batching, the rank count or the launch order.
+// Window outputs live in `wins[slot]`; `slot_of[(i * nW + j) * nD + k]` maps an enumeration index to its slot (duplicates share one).
+constexpr int ST_MAXW = 128;   // windows per axis (with the duplicated clamped window)
+__global__ void __launch_bounds__(NT) stitch_gather_sum_kernel(const float* __restrict__ wins, const int* __restrict__ slot_of,
+                                                               const int* __restrict__ starts, int nH, int nW, int nD, int kH, int kW,
+                                                               int kD, int pH, int pW, int pD, int x0, int y0, int z0, int row0, int rows,
+                                                               int oW, int oD, float* __restrict__ out, uint32_t* enc) {
+    __shared__ int s_start[3][ST_MAXW];   // window starts per axis, enumeration order (non-decreasing)
+    for (int i = threadIdx.x; i < nH + nW + nD; i += NT) {
+        if (i < nH) s_start[0][i] = starts[i];
+        else if (i < nH + nW) s_start[1][i - nH] = starts[i];
+        else s_start[2][i - nH - nW] = starts[i];
+    }
+    __syncthreads();
+    const size_t total = (size_t)rows * oW * oD;
+    const size_t per = (size_t)kH * kW * kD;
+    float mn = INFINITY, mx = -INFINITY;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        const int z = (int)(i % oD) + z0, y = (int)((i / oD) % oW) + y0, x = (int)(i / ((size_t)oD * oW)) + row0 + x0;
+        float acc = 0.f, cnt = 0.f;
+        for (int a = 0; a < nH; a++) {
+            const int lx = x - s_start[0][a];
+            if (lx < pH || lx >= kH - pH) continue;
+            for (int b = 0; b < nW; b++) {
+                const int ly = y - s_start[1][b];
+                if (ly < pW || ly >= kW - pW) continue;
+                for (int c = 0; c < nD; c++) {
+                    const int lz = z - s_start[2][c];
+                    if (lz < pD || lz >= kD - pD) continue;
+                    const int slot = slot_of[(a * nW + b) * nD + c];
+                    acc = __fadd_rn(acc, wins[(size_t)slot * per + ((size_t)lx * kW + ly) * kD + lz]);
+                    cnt += 1.f;
+                }
+            }
+        }
+        const float v = __fdiv_rn(acc, cnt);   // np.true_divide(pred, pix_tracker); 0 / 0 = NaN as in numpy
+        out[i] = v;
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(enc, enc_f(mn));
+        atomicMax(enc + 1, enc_f(mx));
+    }
+}
+
+// 255 * min_max_norm(pred) (custom_callback.py:202) and, for complete=False, .astype('uint8') (:204-205) in the same pass
+__global__ void __launch_bounds__(NT) stitch_scale_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, size_t n,
+                                                             const float* __restrict__ mm) {
+    const float mn = mm[0], r = __fsub_rn(mm[1], mn);
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n; i += (size_t)gridDim.x * NT)
+        out[i] = (uint8_t)__fmul_rn(255.f, __fdiv_rn(__fsub_rn(in[i], mn), r));
+}
+
 }  // namespace
 
 extern "C" {
@@ -421,6 +481,34 @@ int vg_stitch_finalize(const float* pred, const float* cnt, int H, int W, int D,
 int vg_stitch_scale(float* out, size_t n, const float* mm, void* stream) {
     VG_REQUIRE(out && mm);
     stitch_scale_kernel<<<vg_grid_for(n, NT, 16), NT, 0, (cudaStream_t)stream>>>(out, n, mm); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_stitch_gather_sum(const float* wins, const int* slot_of, const int* starts_dev, int nH, int nW, int nD, int kH, int kW, int kD, int pH,
+                         int pW, int pD, int x0, int y0, int z0, int row0, int rows, int oW, int oD, float* out, void* enc_ws, int init_enc,
+                         void* stream) {
+    VG_REQUIRE(wins && slot_of && starts_dev && out && enc_ws);
+    VG_REQUIRE(nH > 0 && nW > 0 && nD > 0 && nH <= ST_MAXW && nW <= ST_MAXW && nD <= ST_MAXW && rows > 0 && oW > 0 && oD > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (init_enc) { stitch_init_kernel<<<1, 1, 0, st>>>((uint32_t*)enc_ws); VG_LAUNCHED(1); }
+    stitch_gather_sum_kernel<<<vg_grid_for((size_t)rows * oW * oD, NT, 16), NT, 0, st>>>(wins, slot_of, starts_dev, nH, nW, nD, kH, kW, kD, pH, pW,
+                                                                                        pD, x0, y0, z0, row0, rows, oW, oD, out,
+                                                                                        (uint32_t*)enc_ws); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_stitch_minmax_decode(const void* enc_ws, float* mm, void* stream) {
+    VG_REQUIRE(enc_ws && mm);
+    stitch_decode_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const uint32_t*)enc_ws, mm); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_stitch_scale_u8(const float* in, unsigned char* out, size_t n, const float* mm, void* stream) {
+    VG_REQUIRE(in && out && mm);
+    stitch_scale_u8_kernel<<<vg_grid_for(n, NT, 16), NT, 0, (cudaStream_t)stream>>>(in, out, n, mm); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }

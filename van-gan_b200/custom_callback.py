@@ -21,6 +21,25 @@ from ._lib import call
 from .distribute import Strategy
 
 
+class _GraphedForward:
+    """One generator forward for a fixed window-batch shape, captured into a CUDA graph and replayed per batch: the ~150 kernel
+    launches of a forward cost more host time than device time at batch 4 (the serial loop of custom_callback.py:174-175 is
+    launch-bound on a B200)."""
+
+    def __init__(self, gen, shape):
+        self.x = torch.zeros(shape, dtype=torch.float32, device=E.DEV)
+        for _ in range(2):                      # warm-up outside the capture (allocator, lazy kernel attributes)
+            gen(self.x, training=False)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.y = gen(self.x, training=False)
+
+    def replay(self):
+        self.graph.replay()
+        return self.y
+
+
 def _apply_hook(hook, win, batched):
     """The reference's `process_imaging_domain` hook (main.py:169-177 passes `process_imaging_otf`).  The stitcher calls it per
     window as hook(arr, axis=None, keepdims=False) (custom_callback.py:171-172), the plotter as hook(sample) on a batch of one
@@ -68,6 +87,7 @@ class GanMonitor:
         self.model_path = getattr(args, "output_dir", None)
         self.strategy = strategy if strategy is not None else Strategy()
         self.window_batch = window_batch
+        self.use_graph = os.environ.get("VG_GRAPH", "1") != "0"
         self.last_stats = None
         self.last_panels = None
 
@@ -165,9 +185,16 @@ class GanMonitor:
 
     def stitch_subvolumes(self, gen, img, subvol_size, epoch=-1, stride=(25, 25, 128), name=None, output_path=None,
                           complete=False, padFactor=0.25, border_removal=True, process_img=False):
-        """img: (H,W,D,1) float array (host).  gen: a generator model of this package (ResUNetModel).
-        Returns the stitched prediction (float32, or uint8 when complete=False) exactly as the reference
-        computes it before its TIFF write."""
+        """img: (H,W,D,1) float array (host).  gen: a generator model of this package.  Returns, on rank 0, the stitched prediction
+        (float32, or uint8 when complete=False) exactly as the reference computes it before its TIFF write (None on other ranks).
+
+        How the reference's serial loop (custom_callback.py:142-190) is executed: the window grid is enumerated exactly as there
+        (including the repeated clamped window), every UNIQUE window is run through the generator once -- batched, forward-only,
+        replayed from one captured CUDA graph -- and kept in HBM; then every output voxel adds the windows covering it in the
+        reference's order (vg_stitch_gather_sum), so the result is bit-identical to the numpy loop driven by the same generator.
+        Ranks take contiguous blocks of the unique-window list, upload only the rows of the volume their windows read, exchange the
+        window outputs with one all-gather and each finalise a slab of rows; min / max are combined with a 2-float all-reduce."""
+        import torch.distributed as dist
         hook = self.process_imaging_domain if (process_img and self.process_imaging_domain is not None) else None
         img = np.asarray(img, dtype=np.float32)
         oshape = img.shape
@@ -179,8 +206,8 @@ class GanMonitor:
             else:
                 zs = int(padFactor * img.shape[2])
                 img = np.pad(img, ((xs, xs), (ys, ys), (zs, zs), (0, 0)), "symmetric")
-        H, W, D, C = img.shape
-        assert C == 1
+        H, W, D, Cc = img.shape
+        assert Cc == 1
         kH, kW, kD = subvol_size[1], subvol_size[2], subvol_size[3]
         if not complete or not border_removal:
             pH = pW = pD = 0
@@ -188,39 +215,77 @@ class GanMonitor:
             pH, pW, pD = int(0.1 * kH), int(0.1 * kW), int(0.1 * kD)
             if kD == D:
                 pD = 0
-        starts = [(r, c, d) for r in window_starts(H, kH, stride[0]) for c in window_starts(W, kW, stride[1])
-                  for d in window_starts(D, kD, stride[2])]
+        sh, sw, sd = window_starts(H, kH, stride[0]), window_starts(W, kW, stride[1]), window_starts(D, kD, stride[2])
+        starts = [(r, c, d) for r in sh for c in sw for d in sd]       # the reference's enumeration, duplicates included
+        uniq, slot_of_start = [], {}
+        for st in starts:
+            if st not in slot_of_start:
+                slot_of_start[st] = len(uniq)
+                uniq.append(st)
         rank, world = self.strategy.rank, self.strategy.num_replicas_in_sync
-        mine = starts[rank::world]                                     # windows are independent: shard round-robin
-        vol = torch.from_numpy(np.ascontiguousarray(img[..., 0])).to(E.DEV)
-        pred = torch.zeros((H, W, D), dtype=torch.float32, device=E.DEV)
-        cnt = torch.zeros((H, W, D), dtype=torch.float32, device=E.DEV)
-        B = self.window_batch
-        for i in range(0, len(mine), B):
-            chunk = mine[i:i + B]
-            st = torch.tensor(chunk, dtype=torch.int32, device=E.DEV).reshape(-1)
-            win = torch.empty((len(chunk), kH, kW, kD, 1), dtype=torch.float32, device=E.DEV)
-            call("vg_stitch_gather", vol, H, W, D, win, st, len(chunk), kH, kW, kD)
-            if hook is not None:                                       # custom_callback.py:171-172, once per window
-                win = _apply_hook(hook, win, batched=False)
-            out = gen(win, training=False)                             # batched generator forward on the CUDA path
-            call("vg_stitch_accumulate", pred, cnt, H, W, D, out.contiguous(), st, len(chunk), kH, kW, kD, pH, pW, pD)
+        per = -(-len(uniq) // world)                                    # unique windows per rank (contiguous block, last one ragged)
+        mine = uniq[rank * per:(rank + 1) * per]
+        # slot of unique window u in the exchanged buffer: rank-major blocks of `per`
+        slot_of = torch.tensor([slot_of_start[st] for st in starts], dtype=torch.int32, device=E.DEV)
+        wins = torch.empty((per * world, kH, kW, kD), dtype=torch.float32, device=E.DEV)
+        if mine:
+            lo, hi = min(st[0] for st in mine), max(st[0] for st in mine) + kH
+            vol = torch.from_numpy(np.ascontiguousarray(img[lo:hi, :, :, 0])).to(E.DEV)     # only the rows this rank's windows read
+            B = min(self.window_batch, len(mine))
+            fwd = _GraphedForward(gen, (B, kH, kW, kD, 1)) if (len(mine) >= 2 * B and hook is None and self.use_graph) else None
+            for i in range(0, len(mine), B):
+                chunk = mine[i:i + B]
+                st = torch.tensor([(a - lo, b_, c) for a, b_, c in chunk], dtype=torch.int32, device=E.DEV).reshape(-1)
+                if fwd is not None and len(chunk) == B:
+                    call("vg_stitch_gather", vol, hi - lo, W, D, fwd.x, st, B, kH, kW, kD)
+                    out = fwd.replay()
+                else:
+                    win = torch.empty((len(chunk), kH, kW, kD, 1), dtype=torch.float32, device=E.DEV)
+                    call("vg_stitch_gather", vol, hi - lo, W, D, win, st, len(chunk), kH, kW, kD)
+                    if hook is not None:                               # custom_callback.py:171-172, once per window
+                        win = _apply_hook(hook, win, batched=False)
+                    out = gen(win, training=False)
+                wins[rank * per + i:rank * per + i + len(chunk)].copy_(out.reshape(len(chunk), kH, kW, kD))
+            del vol
         if world > 1:
-            self.strategy.reduce("SUM", pred)
-            self.strategy.reduce("SUM", cnt)
+            dist.all_gather_into_tensor(wins, wins[rank * per:(rank + 1) * per].clone(), group=self.strategy.group)
         oH, oW, oD = (oshape[0], oshape[1], oshape[2]) if complete else (H, W, D)
         if complete and stride[2] == 1:
             oD = D
-        out = torch.empty((oH, oW, oD), dtype=torch.float32, device=E.DEV)
-        mm = torch.empty(2, dtype=torch.float32, device=E.DEV)
+        rows_per = -(-oH // world)
+        row0 = min(rank * rows_per, oH)
+        rows = min(rows_per, oH - row0)
+        slab = torch.empty((max(rows, 1), oW, oD), dtype=torch.float32, device=E.DEV)
+        mm = torch.tensor([float("inf"), float("-inf")], dtype=torch.float32, device=E.DEV)
         enc = torch.empty(2, dtype=torch.int32, device=E.DEV)
-        call("vg_stitch_finalize", pred, cnt, H, W, D, xs, ys, zs, oH, oW, oD, out, mm, enc)
-        call("vg_stitch_scale", out, out.numel(), mm)
-        self.last_stats = dict(windows=len(starts), unique=len(set(starts)), local_windows=len(mine))
-        if not complete:
-            out = out.to(torch.uint8)        # custom_callback.py:204-205 (astype('uint8')): cast on the device, 4x less D2H
-        res = out.cpu().numpy()[..., None]
-        if output_path is not None and name is not None and rank == 0:
+        if rows > 0:
+            axes = torch.tensor(list(sh) + list(sw) + list(sd), dtype=torch.int32, device=E.DEV)
+            call("vg_stitch_gather_sum", wins, slot_of, axes, len(sh), len(sw), len(sd), kH, kW, kD, pH, pW, pD,
+                 xs, ys, zs, row0, rows, oW, oD, slab, enc, 1)
+            call("vg_stitch_minmax_decode", enc, mm)
+        if world > 1:
+            mn, mx = mm[0:1].clone(), mm[1:2].clone()
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.strategy.group)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.strategy.group)
+            mm = torch.cat([mn, mx])
+        as_u8 = not complete                                           # custom_callback.py:204-205 (astype('uint8'))
+        if as_u8:
+            res_d = torch.empty(slab.shape, dtype=torch.uint8, device=E.DEV)
+            call("vg_stitch_scale_u8", slab, res_d, slab.numel(), mm)
+        else:
+            res_d = slab
+            call("vg_stitch_scale", res_d, res_d.numel(), mm)
+        if world > 1:                                                   # slabs -> rank 0
+            full = torch.empty((rows_per * world, oW, oD), dtype=res_d.dtype, device=E.DEV) if rank == 0 else None
+            padded = res_d if res_d.shape[0] == rows_per else torch.cat(
+                [res_d[:rows], torch.zeros((rows_per - rows, oW, oD), dtype=res_d.dtype, device=E.DEV)])
+            dist.gather(padded.contiguous(), list(full.split(rows_per)) if rank == 0 else None, dst=0, group=self.strategy.group)
+            res_d = full[:oH] if rank == 0 else None
+        self.last_stats = dict(windows=len(starts), unique=len(uniq), local_windows=len(mine))
+        if rank != 0:
+            return None
+        res = res_d.cpu().numpy()[..., None]
+        if output_path is not None and name is not None:
             np.save(os.path.join(output_path, "{name}.npy".format(name=name)), res)
         return res
 

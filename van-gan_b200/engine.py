@@ -140,6 +140,7 @@ class Network:
             p.w = self.w[p.offset:p.offset + p.size].view(p.shape)
             p.grad = self.g[p.offset:p.offset + p.size].view(p.shape)
         self.convs = []
+        self._pack = False        # operand-pack job table: built lazily, invalidated when a layer registers
         self.step_count = 0
 
     @property
@@ -160,9 +161,38 @@ class Network:
     def export_grads(self):
         return {n: p.grad.detach().cpu().numpy().copy() for n, p in self.params.items()}
 
-    def repack(self):
+    def build_pack_plan(self):
+        """Job table of every bf16 operand copy of this network (one entry per packed buffer) + exclusive prefix of their sizes,
+        uploaded once; `repack` then refreshes all of them with ONE launch (vg_pack_run)."""
+        import ctypes as C
+        L = _lib.lib()
+        jb = L.vg_pack_job_bytes()
+        chunks, totals = [], []
         for c in self.convs:
-            c.repack()
+            if c.wf is None and c.wd is None:
+                continue
+            buf = C.create_string_buffer(jb * 24)
+            n = L.vg_conv3d_pack_jobs(C.byref(c.desc(1, 8, 8, 8)), c.w.w.data_ptr(), c.wf.data_ptr() if c.wf is not None else None,
+                                      c.wd.data_ptr() if c.wd is not None else None, buf, 24)
+            if n < 0:
+                raise _lib.VgError("vg_conv3d_pack_jobs failed (%d)" % n)
+            for i in range(n):
+                totals.append(L.vg_pack_job_total(buf, i))
+            chunks.append(buf.raw[:jb * n])
+        if not totals:
+            self._pack = None
+            return
+        prefix = np.concatenate([[0], np.cumsum(totals)]).astype(np.int64)
+        raw = np.frombuffer(b"".join(chunks), dtype=np.uint8).copy()
+        self._pack = (torch.from_numpy(raw).to(DEV), torch.from_numpy(prefix[:-1].copy()).to(DEV), len(totals), int(prefix[-1]))
+
+    def repack(self):
+        """bf16 operand copies <- fp32 master weights (after load / every optimizer step)."""
+        if self._pack is False:
+            self.build_pack_plan()
+        if self._pack is not None:
+            jobs, prefix, n, total = self._pack
+            call("vg_pack_run", jobs, prefix, n, total)
 
     def zero_grad(self):
         self.g.zero_()
@@ -276,6 +306,7 @@ class Conv3D:
         self.wf = torch.empty(max(nb_f, 2) // 2, dtype=torch.bfloat16, device=DEV) if nb_f else None
         self.wd = torch.empty(max(nb_d, 2) // 2, dtype=torch.bfloat16, device=DEV) if nb_d else None
         net.convs.append(self)
+        net._pack = False
 
     def desc(self, n, d, h, w):
         return ConvDesc(n, d, h, w, self.cin, self.cout, self.k, self.stride, self.x_dtype, self.y_dtype, self.act,
