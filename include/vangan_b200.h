@@ -28,7 +28,7 @@ enum { VG_F32 = 0, VG_BF16 = 1 };
 /* OR-ed into the dtype of the vg_instnorm_* calls: the tensor being normalised is relu(x) — the producer was a
  * Conv3D(activation='relu') (vnet_model.py:118-126,133-141) whose ReLU is applied on load, and whose gradient mask is
  * applied to dx */
-enum { VG_IN_RELU_INPUT = 0x100 };
+enum { VG_IN_RELU_INPUT = 0x100, VG_IN_BATCH_STATS = 0x200 /* backward reductions over the whole batch: BatchNormalization */ };
 enum { VG_ACT_NONE = 0, VG_ACT_RELU = 1, VG_ACT_LEAKY = 2, VG_ACT_TANH = 3 };
 enum { VG_PAD_ZERO = 0, VG_PAD_REFLECT = 1 };
 
@@ -192,6 +192,33 @@ int vg_clip_adam_step(float* w, const float* g, float* m, float* v, const long l
  * carry it as a launch argument) */
 int vg_clip_adam_step_dev(float* w, const float* g, float* m, float* v, const long long* seg_offsets, int nseg, long long total,
                           const float* lr_t_dev, float beta1, float beta2, float eps, float clipnorm, double* norm_ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * V-Net gen_SI variant (vangan.py:135-149): BatchNormalization (vnet_model.py:127-128,142-143) and Conv3DTranspose k2 s2
+ * (vnet_model.py:245).
+ *
+ * BatchNormalization(axis=-1, momentum=0.99, epsilon=1e-3), per-replica batch statistics.  The arithmetic is the InstanceNorm one
+ * with statistics over N*D*H*W: vg_batchnorm_stats writes them replicated per (n, c) (training: batch statistics + Keras moving
+ * averages; inference: from the moving values), vg_instnorm_apply applies them, vg_batchnorm_bwd is vg_instnorm_bwd with the
+ * reductions taken over the whole batch (VG_IN_BATCH_STATS).  ws: vg_batchnorm_workspace_bytes.
+ *
+ * Conv3DTranspose((2,2,2), strides 2, 'same'): the eight outputs of an input voxel do not overlap, so the layer is one pointwise GEMM
+ * with 8*Cout columns ordered (a,b,c,co) -- vg_conv3d_fwd / dgrad / wgrad with K = 1 on a kernel stored as (1,1,1,Cin,8*Cout) --
+ * plus a depth-to-space scatter that adds the bias (forward) / a space-to-depth gather that also reduces the bias gradient (backward).
+ * The Keras kernel (2,2,2,Cout,Cin) maps to the GEMM layout by w1[ci][((a*2+b)*2+c)*Cout + co] = wk[a][b][c][co][ci].
+ * ------------------------------------------------------------------------------------------- */
+size_t vg_batchnorm_workspace_bytes(int N, int D, int H, int W, int C);
+int vg_batchnorm_stats(const void* x, int dtype, int N, int D, int H, int W, int C, float* mean_nc, float* rstd_nc, float* moving_mean,
+                       float* moving_var, float momentum, int training, void* ws, size_t ws_bytes, void* stream);
+int vg_batchnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, const float* mean_nc, const float* rstd_nc,
+                     const float* gamma, const float* beta, const float* drop, void* dx, int accumulate_dx, void* dres, float* dgamma,
+                     float* dbeta, void* ws, size_t ws_bytes, void* stream);
+/* y[N,2D,2H,2W,Cout] = depth_to_space(t[N,D,H,W,8*Cout]) + bias */
+int vg_conv3d_transpose_k2s2_scatter(const void* t, const float* bias, void* y, int N, int D, int H, int W, int Cout, void* stream);
+/* dt = space_to_depth(dy); dbias (optional, fp32[Cout]) += sum dy */
+int vg_conv3d_transpose_k2s2_gather(const void* dy, void* dt, float* dbias, int N, int D, int H, int W, int Cout, void* stream);
+/* dir 0: gemm[Cin][8*Cout] = permute(keras[2][2][2][Cout][Cin]); dir 1: keras_grad += permute(gemm_grad) */
+int vg_conv3d_transpose_k2s2_weights(const float* src, float* dst, int Cin, int Cout, int dir, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Sliding-window stitching (custom_callback.py:123,165-166,177-183,192,202).

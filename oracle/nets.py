@@ -290,19 +290,28 @@ def disc_forward(p, x, noise=None, masks=None, taps=None):
     return conv3d(h, p["dout.conv.w"], p["dout.conv.b"], padding="same")
 
 
-# --------------------------------------------------------------------------- V-Net (gen_IS variant)
-def vnet_param_shapes(filters=32, num_layers=4, cin=1):
-    """Trainable variables of custom_vnet(use_batch_norm=False, upsample_mode='upsample') in call order
-    (vnet_model.py:199-264 with the arguments at vangan.py:97-110)."""
-    P = OrderedDict()
+# --------------------------------------------------------------------------- V-Net (both variants VanGan builds)
+BN_EPS, BN_MOMENTUM = 1e-3, 0.99   # keras.layers.BatchNormalization defaults (vnet_model.py:127-128 passes none)
 
-    def conv(name, k, ci, co):
+
+def vnet_param_shapes(filters=32, num_layers=4, cin=1, use_batch_norm=False, deconv=False):
+    """Trainable variables of custom_vnet in call order (vnet_model.py:199-264).  gen_IS arguments (vangan.py:97-110):
+    use_batch_norm=False, upsample_mode='upsample', filters=32.  gen_SI arguments (vangan.py:135-149): use_batch_norm=True (block
+    convolutions get use_bias=False, vnet_model.py:124,139), upsample_mode='deconv' (Conv3DTranspose kernel (2,2,2,Cout,Cin) + bias,
+    vnet_model.py:245), filters=16."""
+    P = OrderedDict()
+    nk = "bn" if use_batch_norm else "in"
+
+    def conv(name, k, ci, co, bias=True):
         P[name + ".w"] = (k, k, k, ci, co)
-        P[name + ".b"] = (co,)
+        if bias:
+            P[name + ".b"] = (co,)
 
     def block(name, ci, co):
-        conv(name + ".c1.conv", 3, ci, co); P[name + ".c1.in.gamma"] = (co,); P[name + ".c1.in.beta"] = (co,)
-        conv(name + ".c2.conv", 3, co, co); P[name + ".c2.in.gamma"] = (co,); P[name + ".c2.in.beta"] = (co,)
+        for j, c_in in ((1, ci), (2, co)):
+            conv("%s.c%d.conv" % (name, j), 3, c_in, co, bias=not use_batch_norm)
+            P["%s.c%d.%s.gamma" % (name, j, nk)] = (co,)
+            P["%s.c%d.%s.beta" % (name, j, nk)] = (co,)
 
     f, ci = filters, cin
     for l in range(num_layers):
@@ -311,7 +320,11 @@ def vnet_param_shapes(filters=32, num_layers=4, cin=1):
     block("bridge", ci, f)
     for l in reversed(range(num_layers)):
         f //= 2
-        conv("dec%d.up.conv" % l, 3, 2 * f, f)
+        if deconv:
+            P["dec%d.up.w" % l] = (2, 2, 2, f, 2 * f)
+            P["dec%d.up.b" % l] = (f,)
+        else:
+            conv("dec%d.up.conv" % l, 3, 2 * f, f)
         block("dec%d" % l, 2 * f, f)
     conv("head", 1, f, 1)
     return P
@@ -323,35 +336,86 @@ def make_vnet_masks(rng, n, filters=32, num_layers=4, rate=0.5, dtype=torch.floa
             for l in range(num_layers + 1)]
 
 
-def _vnet_block(p, name, x, mask=None):
-    """conv3d_block (vnet_model.py:80-146): pad -> Conv3D(relu) -> InstanceNorm -> [SpatialDropout3D] -> pad ->
-    Conv3D(relu) -> InstanceNorm."""
-    c = torch.relu(conv3d(reflect_pad(x), p[name + ".c1.conv.w"], p[name + ".c1.conv.b"]))
-    c = instance_norm(c, p[name + ".c1.in.gamma"], p[name + ".c1.in.beta"])
+def batch_norm(x, gamma, beta, state=None, key=None, training=True):
+    """keras.layers.BatchNormalization(axis=-1, momentum=0.99, epsilon=1e-3) on NDHWC.  training: biased batch statistics over
+    N,D,H,W; the moving averages in `state` ({key + '.moving_mean' / '.moving_variance'}) are updated in place with
+    moving = m*moving + (1-m)*batch, the variance Bessel-corrected (Keras' fused 5-D path, recalled).  inference: the moving values."""
+    if training:
+        mu = x.mean(dim=(0, 1, 2, 3), keepdim=True)
+        var = ((x - mu) ** 2).mean(dim=(0, 1, 2, 3), keepdim=True)
+        if state is not None:
+            cnt = x.numel() // x.shape[-1]
+            with torch.no_grad():
+                mm, mv = state[key + ".moving_mean"], state[key + ".moving_variance"]
+                mm.mul_(BN_MOMENTUM).add_((1 - BN_MOMENTUM) * mu.reshape(-1).to(mm.dtype))
+                mv.mul_(BN_MOMENTUM).add_((1 - BN_MOMENTUM) * (var.reshape(-1) * (cnt / max(cnt - 1, 1))).to(mv.dtype))
+    else:
+        mu, var = state[key + ".moving_mean"].to(x.dtype), state[key + ".moving_variance"].to(x.dtype)
+    return (x - mu) * torch.rsqrt(var + BN_EPS) * gamma + beta
+
+
+def conv3d_transpose_k2s2(x, w, b):
+    """Keras Conv3DTranspose(filters, (2,2,2), strides 2, 'same') on NDHWC with kernel (2,2,2,Cout,Cin):
+    y[n, 2d+a, 2h+b, 2w+c, co] = sum_ci x[n,d,h,w,ci] * w[a,b,c,co,ci] + bias[co]."""
+    wt = _qw(w).permute(4, 3, 0, 1, 2)          # -> (Cin, Cout, kd, kh, kw)
+    return _qa(_ndhwc(F.conv_transpose3d(_ncdhw(x), wt, b, stride=2)))
+
+
+def vnet_bn_state(filters=16, num_layers=4, dtype=torch.float32):
+    """Fresh moving statistics (zeros / ones) of every BatchNormalization, keyed like the CUDA network's buffers."""
+    st = OrderedDict()
+    names = ["enc%d" % l for l in range(num_layers)] + ["bridge"] + ["dec%d" % l for l in range(num_layers)]
+    widths = [filters * 2 ** l for l in range(num_layers)] + [filters * 2 ** num_layers] + [filters * 2 ** l for l in range(num_layers)]
+    for nme, c in zip(names, widths):
+        for j in (1, 2):
+            st["%s.c%d.bn.moving_mean" % (nme, j)] = torch.zeros(c, dtype=dtype)
+            st["%s.c%d.bn.moving_variance" % (nme, j)] = torch.ones(c, dtype=dtype)
+    return st
+
+
+def _vnet_block(p, name, x, mask=None, bn_state=None, training=True):
+    """conv3d_block (vnet_model.py:80-146): pad -> Conv3D(relu) -> norm -> [SpatialDropout3D] -> pad -> Conv3D(relu) -> norm, norm =
+    InstanceNormalization or (bn_state given) BatchNormalization."""
+    bn = (name + ".c1.bn.gamma") in p
+
+    def norm(c, j):
+        if bn:
+            k = "%s.c%d.bn" % (name, j)
+            return batch_norm(c, p[k + ".gamma"], p[k + ".beta"], bn_state, k, training)
+        k = "%s.c%d.in" % (name, j)
+        return instance_norm(c, p[k + ".gamma"], p[k + ".beta"])
+
+    c = torch.relu(conv3d(reflect_pad(x), p[name + ".c1.conv.w"], p.get(name + ".c1.conv.b")))
+    c = norm(c, 1)
     if mask is not None:
         c = c * mask
     c = _qa(c)
-    c = torch.relu(conv3d(reflect_pad(c), p[name + ".c2.conv.w"], p[name + ".c2.conv.b"]))
-    return _qa(instance_norm(c, p[name + ".c2.in.gamma"], p[name + ".c2.in.beta"]))
+    c = torch.relu(conv3d(reflect_pad(c), p[name + ".c2.conv.w"], p.get(name + ".c2.conv.b")))
+    return _qa(norm(c, 2))
 
 
-def vnet_forward(p, x, num_layers=4, masks=None, taps=None):
-    """custom_vnet(..., use_batch_norm=False, upsample_mode='upsample', dropout=0.5, filters=F, num_layers=4,
-    output_activation='tanh') (vnet_model.py:199-264).  masks=None is inference mode (dropout inactive)."""
+def vnet_forward(p, x, num_layers=4, masks=None, taps=None, bn_state=None, training=None):
+    """custom_vnet(..., dropout=0.5, num_layers=4, output_activation='tanh') (vnet_model.py:199-264); the variant (InstanceNorm +
+    UpSampling3D/Conv3D, or BatchNorm + Conv3DTranspose) follows from the variables present in `p`.  masks=None is inference mode for
+    dropout; `training` (default: masks is not None) selects batch vs moving statistics of BatchNormalization."""
+    training = (masks is not None) if training is None else training
     down = []
     for l in range(num_layers):
-        x = _vnet_block(p, "enc%d" % l, x, None if masks is None else masks[l])
+        x = _vnet_block(p, "enc%d" % l, x, None if masks is None else masks[l], bn_state, training)
         down.append(x)
         if taps is not None:
             taps["enc%d" % l] = x
         x = _ndhwc(F.max_pool3d(_ncdhw(x), 2))                      # MaxPooling3D((2,2,2))
-    x = _vnet_block(p, "bridge", x, None if masks is None else masks[num_layers])
+    x = _vnet_block(p, "bridge", x, None if masks is None else masks[num_layers], bn_state, training)
     if taps is not None:
         taps["bridge"] = x
     for l in reversed(range(num_layers)):
-        x = conv3d(upsample2(x), p["dec%d.up.conv.w" % l], p["dec%d.up.conv.b" % l], padding="same")
+        if ("dec%d.up.w" % l) in p:
+            x = conv3d_transpose_k2s2(x, p["dec%d.up.w" % l], p["dec%d.up.b" % l])
+        else:
+            x = conv3d(upsample2(x), p["dec%d.up.conv.w" % l], p["dec%d.up.conv.b" % l], padding="same")
         x = torch.cat([x, down[l]], dim=-1)
-        x = _vnet_block(p, "dec%d" % l, x)
+        x = _vnet_block(p, "dec%d" % l, x, None, bn_state, training)
         if taps is not None:
             taps["dec%d" % l] = x
     return torch.tanh(conv3d(x, p["head.w"], p["head.b"], padding="same"))

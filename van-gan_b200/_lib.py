@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libvangan_b200.so")
 
 VG_F32, VG_BF16 = 0, 1
 IN_RELU_INPUT = 0x100
+IN_BATCH_STATS = 0x200
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT = 0, 1
 _ERR = {-1: "invalid argument", -2: "unsupported shape", -3: "workspace too small", -4: "CUDA error"}
@@ -62,6 +63,12 @@ SIGNATURES = {
     "vg_gather_pad_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_maxpool2_pad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_maxpool2_pad_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vg_batchnorm_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "vg_batchnorm_stats": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P, _Z, _P]),
+    "vg_batchnorm_bwd": (_I, [_ID, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    "vg_conv3d_transpose_k2s2_scatter": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vg_conv3d_transpose_k2s2_gather": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vg_conv3d_transpose_k2s2_weights": (_I, [_P, _P, _I, _I, _I, _P]),
     "vg_pad_noise": (_I, [_P, _P, _I, _I, _I, _I, _P, _F, _ULL, _P, _P]),
     "vg_dropout_mask": (_I, [_P, _I, _F, _ULL, _P, _P]),
     "vg_pad_fold": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

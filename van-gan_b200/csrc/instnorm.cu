@@ -323,27 +323,65 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_partial_kernel(const T* __restri
     }
 }
 
-// sums[(n*C+c)*2+{0,1}] = S1, S2; dgamma[c] += S2, dbeta[c] += S1  (one warp per (n,c); N <= a few atomics per channel)
+// sums[(n*C+c)*2+{0,1}] = S1, S2; dgamma[c] += S2, dbeta[c] += S1  (one warp per (n,c); N <= a few atomics per channel).
+// batch != 0 (BatchNormalization: statistics over N*D*H*W): one warp per channel adds the partials of ALL samples and stores
+// total / N for every n, so that the apply pass (which divides by the per-sample voxel count V) sees total / (N*V).
 __global__ void __launch_bounds__(256) in_bwd_final_kernel(const float* __restrict__ partial, int nblk, int N, int C,
                                                            float* __restrict__ sums, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta) {
+                                                           float* __restrict__ dbeta, int batch) {
     int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (i >= N * C) return;
+    if (i >= (batch ? C : N * C)) return;
     int c = i % C;
     int n = i / C;
     double s1 = 0, s2 = 0;
-    for (int b = lane; b < nblk; b += 32) {
-        const float* p = partial + (((size_t)n * nblk + b) * C + c) * 2;
-        s1 += p[0];
-        s2 += p[1];
-    }
+    const int n0 = batch ? 0 : n, n1 = batch ? N : n + 1;
+    for (int nn = n0; nn < n1; nn++)
+        for (int b = lane; b < nblk; b += 32) {
+            const float* p = partial + (((size_t)nn * nblk + b) * C + c) * 2;
+            s1 += p[0];
+            s2 += p[1];
+        }
     s1 = warp_sum_d(s1);
     s2 = warp_sum_d(s2);
     if (lane == 0) {
-        sums[(size_t)i * 2] = (float)s1;
-        sums[(size_t)i * 2 + 1] = (float)s2;
+        if (batch) {
+            for (int nn = 0; nn < N; nn++) {
+                sums[((size_t)nn * C + c) * 2] = (float)(s1 / N);
+                sums[((size_t)nn * C + c) * 2 + 1] = (float)(s2 / N);
+            }
+        } else {
+            sums[(size_t)i * 2] = (float)s1;
+            sums[(size_t)i * 2 + 1] = (float)s2;
+        }
         if (dgamma) atomicAdd(dgamma + c, (float)s2);
         if (dbeta) atomicAdd(dbeta + c, (float)s1);
+    }
+}
+
+// BatchNormalization statistics: stat[c] (computed as ONE instance over the N stacked samples) -> replicated per (n, c), and the
+// Keras moving averages: moving = momentum * moving + (1 - momentum) * batch value.  training == 0: mean / rstd from the moving values.
+__global__ void bn_expand_kernel(const float* __restrict__ mean_c, const float* __restrict__ rstd_c, int N, int C, float* __restrict__ mean_nc,
+                                 float* __restrict__ rstd_nc, float* __restrict__ moving_mean, float* __restrict__ moving_var, float momentum,
+                                 int training, float bessel) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float m, r;
+    if (training) {
+        m = mean_c[c];
+        r = rstd_c[c];
+        if (moving_mean) {
+            // Keras' fused path (5-D NDHWC input) feeds the moving variance with the Bessel-corrected batch variance
+            const float var = (1.f / (r * r) - IN_EPS) * bessel;
+            moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * m;
+            moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * var;
+        }
+    } else {
+        m = moving_mean[c];
+        r = rsqrtf(moving_var[c] + IN_EPS);
+    }
+    for (int n = 0; n < N; n++) {
+        mean_nc[n * C + c] = m;
+        rstd_nc[n * C + c] = r;
     }
 }
 
@@ -758,7 +796,7 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
     VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT && d->pad_lo >= 0 && d->pad_hi >= 0);
     if (d->pad_mode == VG_PAD_REFLECT && (d->pad_lo || d->pad_hi))
         VG_REQUIRE(d->pad_lo == 1 && d->pad_hi == 1 && d->D >= 2 && d->H >= 2 && d->W >= 2);
-    const int dtype = d->dtype & ~VG_IN_RELU_INPUT;
+    const int dtype = d->dtype & ~(VG_IN_RELU_INPUT | VG_IN_BATCH_STATS);
     Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode, (d->dtype & VG_IN_RELU_INPUT) ? 1 : 0};
     ApplyArgs a{mean, rstd, gamma, beta, drop, noise, d->slope, d->noise_std, d->act, d->seed, d->seed_dev};
     const int pp = d->pad_lo + d->pad_hi;
@@ -794,7 +832,8 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
     VG_REQUIRE(d && dy && x && mean && rstd && gamma && beta && dx && ws);
     VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT);
-    const int dtype = d->dtype & ~VG_IN_RELU_INPUT;
+    const int dtype = d->dtype & ~(VG_IN_RELU_INPUT | VG_IN_BATCH_STATS);
+    const int batch = (d->dtype & VG_IN_BATCH_STATS) ? 1 : 0;
     Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode, (d->dtype & VG_IN_RELU_INPUT) ? 1 : 0};
     BwdArgs a{mean, rstd, gamma, beta, drop, d->slope, d->act};
     const int pp = d->pad_lo + d->pad_hi;
@@ -816,22 +855,22 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
     }
     if (sp == 1) {
         in_bwd_partial_sp_kernel<bf16, 1><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
-        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta);
+        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta, batch);
         in_bwd_apply_sp_kernel<bf16, 1><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
         VG_LAUNCHED(3);
     } else if (sp == 2) {
         in_bwd_partial_sp_kernel<bf16, 2><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
-        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta);
+        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta, batch);
         in_bwd_apply_sp_kernel<bf16, 2><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
         VG_LAUNCHED(3);
     } else if (dtype == VG_BF16) {
         in_bwd_partial_kernel<bf16><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial); VG_LAUNCHED(1);
-        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta); VG_LAUNCHED(1);
+        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta, batch); VG_LAUNCHED(1);
         in_bwd_apply_kernel<bf16><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres,
                                                          accumulate_dx); VG_LAUNCHED(1);
     } else if (dtype == VG_F32) {
         in_bwd_partial_kernel<float><<<dim3(nblk, d->N), nthr, smem, st>>>((const float*)dy, (const float*)x, g, a, partial); VG_LAUNCHED(1);
-        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta); VG_LAUNCHED(1);
+        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta, batch); VG_LAUNCHED(1);
         in_bwd_apply_kernel<float><<<grid2, nthr, 0, st>>>((const float*)dy, (const float*)x, g, a, sums, (float*)dx, (float*)dres,
                                                           accumulate_dx); VG_LAUNCHED(1);
     } else {
@@ -839,6 +878,45 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
     }
     VG_CHECK_LAUNCH();
     return VG_OK;
+}
+
+// BatchNormalization (vnet_model.py:127-128,142-143: Keras defaults axis=-1, momentum 0.99, epsilon 1e-3, per-replica batch
+// statistics).  The normalisation itself is the InstanceNorm arithmetic with statistics taken over the whole local batch, so the
+// apply / backward passes are vg_instnorm_apply / vg_instnorm_bwd with (n, c)-replicated statistics and, for the backward,
+// VG_IN_BATCH_STATS set in desc.dtype (reductions over N*D*H*W).  mean_nc / rstd_nc: [N*C]; moving_*: [C] (may be NULL when training);
+// ws: vg_instnorm_workspace_bytes(1, N*D, H, W, C) + 2*C floats.
+int vg_batchnorm_stats(const void* x, int dtype, int N, int D, int H, int W, int C, float* mean_nc, float* rstd_nc, float* moving_mean,
+                       float* moving_var, float momentum, int training, void* ws, size_t ws_bytes, void* stream) {
+    VG_REQUIRE(x && mean_nc && rstd_nc && N > 0 && C % 8 == 0 && (training || (moving_mean && moving_var)));
+    float* mc = nullptr;
+    float* rc = nullptr;
+    const double cnt = (double)N * D * H * W;
+    if (training) {
+        VG_REQUIRE(ws && ws_bytes >= (size_t)2 * C * sizeof(float));
+        const size_t tail = (size_t)2 * C * sizeof(float);
+        mc = (float*)((char*)ws + ws_bytes - tail);
+        rc = mc + C;
+        int rc_ = vg_instnorm_stats(x, dtype, 1, N * D, H, W, C, mc, rc, ws, ws_bytes - tail, stream);
+        if (rc_ != VG_OK) return rc_;
+    }
+    bn_expand_kernel<<<vg_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(mc, rc, N, C, mean_nc, rstd_nc, moving_mean, moving_var, momentum,
+                                                                      training, cnt > 1.0 ? (float)(cnt / (cnt - 1.0)) : 1.f); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+size_t vg_batchnorm_workspace_bytes(int N, int D, int H, int W, int C) {
+    const size_t a = vg_instnorm_workspace_bytes(1, N * D, H, W, C), b = vg_instnorm_workspace_bytes(N, D, H, W, C);
+    return (a > b ? a : b) + (size_t)2 * C * sizeof(float);
+}
+
+int vg_batchnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, const float* mean_nc, const float* rstd_nc,
+                     const float* gamma, const float* beta, const float* drop, void* dx, int accumulate_dx, void* dres, float* dgamma,
+                     float* dbeta, void* ws, size_t ws_bytes, void* stream) {
+    VG_REQUIRE(d);
+    vg_instnorm_desc e = *d;
+    e.dtype |= VG_IN_BATCH_STATS;
+    return vg_instnorm_bwd(&e, dy, x, mean_nc, rstd_nc, gamma, beta, drop, dx, accumulate_dx, dres, dgamma, dbeta, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

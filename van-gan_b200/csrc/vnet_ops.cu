@@ -194,6 +194,82 @@ inline bool pad_ok(int D, int H, int W, int pad, int mode) {
     return true;
 }
 
+
+// Conv3DTranspose(filters, (2,2,2), strides 2, 'same') (vnet_model.py:245): the eight output positions of an input voxel do not
+// overlap, so the layer is ONE pointwise GEMM with 8*Cout columns ordered (a, b, c, co) -- run by vg_conv3d_fwd / dgrad / wgrad with
+// K = 1 on the tensor cores -- followed by a depth-to-space scatter that also adds the bias.  t: [N, D, H, W, 8*Cout] bf16;
+// y: [N, 2D, 2H, 2W, Cout] bf16.  One thread moves 8 channels (128 bits).
+__global__ void __launch_bounds__(NT) ct_scatter_kernel(const bf16* __restrict__ t, const float* __restrict__ bias, bf16* __restrict__ y, int N,
+                                                        int D, int H, int W, int Co) {
+    const int cg = Co / 8;
+    const size_t total = (size_t)N * 8 * D * H * W * cg;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        const int c8 = (int)(i % cg);
+        size_t v = i / cg;
+        const int ow = (int)(v % (2 * W)); v /= 2 * W;
+        const int oh = (int)(v % (2 * H)); v /= 2 * H;
+        const int od = (int)(v % (2 * D));
+        const int n = (int)(v / (2 * D));
+        const int pos = ((od & 1) * 2 + (oh & 1)) * 2 + (ow & 1);
+        float f[8];
+        load8<bf16>(t + ((((size_t)n * D + (od >> 1)) * H + (oh >> 1)) * W + (ow >> 1)) * (8 * Co) + pos * Co + c8 * 8, f);
+        if (bias) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) f[k] += bias[c8 * 8 + k];
+        }
+        store8<bf16>(y + i * 8, f);
+    }
+}
+
+// backward of the scatter: dt = space-to-depth(dy); dbias[co] += sum of dy over every output voxel (block partials, one atomic per
+// channel per block)
+__global__ void __launch_bounds__(NT) ct_gather_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dt, float* __restrict__ dbias, int N,
+                                                       int D, int H, int W, int Co) {
+    extern __shared__ float sb[];   // Co floats
+    const int cg = Co / 8;
+    for (int i = threadIdx.x; i < Co; i += NT) sb[i] = 0.f;
+    __syncthreads();
+    const size_t total = (size_t)N * 8 * D * H * W * cg;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int my_c8 = -1;
+    // NT * gridDim.x is a multiple of cg (cg divides NT: Co in {16..256}), so a thread always sees the same channel group
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        const int c8 = (int)(i % cg);
+        my_c8 = c8;
+        size_t v = i / cg;
+        const int ow = (int)(v % (2 * W)); v /= 2 * W;
+        const int oh = (int)(v % (2 * H)); v /= 2 * H;
+        const int od = (int)(v % (2 * D));
+        const int n = (int)(v / (2 * D));
+        const int pos = ((od & 1) * 2 + (oh & 1)) * 2 + (ow & 1);
+        float f[8];
+        load8<bf16>(dy + i * 8, f);
+        store8<bf16>(dt + ((((size_t)n * D + (od >> 1)) * H + (oh >> 1)) * W + (ow >> 1)) * (8 * Co) + pos * Co + c8 * 8, f);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] += f[k];
+    }
+    if (dbias && my_c8 >= 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) atomicAdd(sb + my_c8 * 8 + k, acc[k]);
+    }
+    __syncthreads();
+    if (dbias)
+        for (int i = threadIdx.x; i < Co; i += NT) atomicAdd(dbias + i, sb[i]);
+}
+
+
+// Conv3DTranspose kernel layouts: Keras (2,2,2,Cout,Cin) <-> pointwise-GEMM (Cin, 8*Cout) with columns (a,b,c,co).
+// dir 0: gemm = permute(keras) (after load / every optimizer step); dir 1: keras_grad += permute(gemm_grad) (after the wgrad).
+__global__ void ct_weights_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cin, int Cout, int dir) {
+    const int total = 8 * Cin * Cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % Cin, co = (i / Cin) % Cout, pos = i / (Cin * Cout);        // i indexes the Keras layout
+        const int j = ci * (8 * Cout) + pos * Cout + co;                               // the GEMM layout
+        if (dir == 0) dst[j] = src[i];
+        else dst[i] += src[j];
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -238,6 +314,30 @@ int vg_maxpool2_pad_bwd(const void* x, const void* dy, void* dx, int N, int D, i
     const size_t total = (size_t)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
     maxpool2_pad_bwd_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, N, D, H, W, C,
                                                                                         pad, pad_mode); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_conv3d_transpose_k2s2_scatter(const void* t, const float* bias, void* y, int N, int D, int H, int W, int Cout, void* stream) {
+    VG_REQUIRE(t && y && N > 0 && D > 0 && H > 0 && W > 0 && Cout % 8 == 0 && NT % (Cout / 8) == 0);
+    const long long total = (long long)N * 8 * D * H * W * (Cout / 8);
+    ct_scatter_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>((const bf16*)t, bias, (bf16*)y, N, D, H, W, Cout); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_conv3d_transpose_k2s2_gather(const void* dy, void* dt, float* dbias, int N, int D, int H, int W, int Cout, void* stream) {
+    VG_REQUIRE(dy && dt && N > 0 && D > 0 && H > 0 && W > 0 && Cout % 8 == 0 && NT % (Cout / 8) == 0);
+    const long long total = (long long)N * 8 * D * H * W * (Cout / 8);
+    ct_gather_kernel<<<vg_grid_for(total, NT, 8), NT, (size_t)Cout * sizeof(float), (cudaStream_t)stream>>>((const bf16*)dy, (bf16*)dt, dbias, N,
+                                                                                                     D, H, W, Cout); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_conv3d_transpose_k2s2_weights(const float* src, float* dst, int Cin, int Cout, int dir, void* stream) {
+    VG_REQUIRE(src && dst && Cin > 0 && Cout > 0 && (dir == 0 || dir == 1));
+    ct_weights_kernel<<<vg_cdiv(8 * Cin * Cout, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, Cin, Cout, dir); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }

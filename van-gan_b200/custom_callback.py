@@ -90,6 +90,7 @@ class GanMonitor:
         self.use_graph = os.environ.get("VG_GRAPH", "1") != "0"
         self.last_stats = None
         self.last_panels = None
+        self._fwd_cache = {}
 
     # ------------------------------------------------------------------ epoch callbacks (custom_callback.py:33-45,326-464)
     def save_model(self, model, epoch):
@@ -194,7 +195,16 @@ class GanMonitor:
         reference's order (vg_stitch_gather_sum), so the result is bit-identical to the numpy loop driven by the same generator.
         Ranks take contiguous blocks of the unique-window list, upload only the rows of the volume their windows read, exchange the
         window outputs with one all-gather and each finalise a slab of rows; min / max are combined with a 2-float all-reduce."""
+        import time
         import torch.distributed as dist
+        prof = os.environ.get("VG_STITCH_PROFILE") == "1"
+        marks = []
+
+        def mark(label):
+            if prof:
+                torch.cuda.synchronize()
+                marks.append((label, time.perf_counter()))
+        mark("start")
         hook = self.process_imaging_domain if (process_img and self.process_imaging_domain is not None) else None
         img = np.asarray(img, dtype=np.float32)
         oshape = img.shape
@@ -228,11 +238,21 @@ class GanMonitor:
         # slot of unique window u in the exchanged buffer: rank-major blocks of `per`
         slot_of = torch.tensor([slot_of_start[st] for st in starts], dtype=torch.int32, device=E.DEV)
         wins = torch.empty((per * world, kH, kW, kD), dtype=torch.float32, device=E.DEV)
+        mark("host prep")
         if mine:
             lo, hi = min(st[0] for st in mine), max(st[0] for st in mine) + kH
             vol = torch.from_numpy(np.ascontiguousarray(img[lo:hi, :, :, 0])).to(E.DEV)     # only the rows this rank's windows read
+            mark("upload")
             B = min(self.window_batch, len(mine))
-            fwd = _GraphedForward(gen, (B, kH, kW, kD, 1)) if (len(mine) >= 2 * B and hook is None and self.use_graph) else None
+            fwd = None
+            if len(mine) >= 2 * B and hook is None and self.use_graph:
+                # captured once per (generator, window-batch shape): the graph reads the packed weights in place, so it stays
+                # valid across optimizer steps and checkpoint loads
+                key = (id(gen), B, kH, kW, kD)
+                if key not in self._fwd_cache:
+                    self._fwd_cache[key] = _GraphedForward(gen, (B, kH, kW, kD, 1))
+                fwd = self._fwd_cache[key]
+            mark("graph capture")
             for i in range(0, len(mine), B):
                 chunk = mine[i:i + B]
                 st = torch.tensor([(a - lo, b_, c) for a, b_, c in chunk], dtype=torch.int32, device=E.DEV).reshape(-1)
@@ -247,6 +267,7 @@ class GanMonitor:
                     out = gen(win, training=False)
                 wins[rank * per + i:rank * per + i + len(chunk)].copy_(out.reshape(len(chunk), kH, kW, kD))
             del vol
+            mark("windows")
         if world > 1:
             dist.all_gather_into_tensor(wins, wins[rank * per:(rank + 1) * per].clone(), group=self.strategy.group)
         oH, oW, oD = (oshape[0], oshape[1], oshape[2]) if complete else (H, W, D)
@@ -282,9 +303,14 @@ class GanMonitor:
             dist.gather(padded.contiguous(), list(full.split(rows_per)) if rank == 0 else None, dst=0, group=self.strategy.group)
             res_d = full[:oH] if rank == 0 else None
         self.last_stats = dict(windows=len(starts), unique=len(uniq), local_windows=len(mine))
+        mark("finalize")
         if rank != 0:
             return None
         res = res_d.cpu().numpy()[..., None]
+        mark("download")
+        if prof:
+            self.last_stats["phases_ms"] = {b[0]: round((b[1] - a[1]) * 1e3, 2) for a, b in zip(marks[:-1], marks[1:])}
+            print("[stitch]", self.last_stats)
         if output_path is not None and name is not None:
             np.save(os.path.join(output_path, "{name}.npy".format(name=name)), res)
         return res

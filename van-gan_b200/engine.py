@@ -141,6 +141,8 @@ class Network:
             p.grad = self.g[p.offset:p.offset + p.size].view(p.shape)
         self.convs = []
         self._pack = False        # operand-pack job table: built lazily, invalidated when a layer registers
+        self.pre_pack = []        # callables run before the operand pack (Conv3DTranspose: Keras layout -> GEMM layout)
+        self.buffers = {}         # non-trainable state by name (BatchNormalization moving_mean / moving_variance), checkpointed
         self.step_count = 0
 
     @property
@@ -188,6 +190,8 @@ class Network:
 
     def repack(self):
         """bf16 operand copies <- fp32 master weights (after load / every optimizer step)."""
+        for hook in self.pre_pack:
+            hook()
         if self._pack is False:
             self.build_pack_plan()
         if self._pack is not None:
@@ -292,10 +296,11 @@ def default_init(shapes, seed):
 class Conv3D:
     """keras.layers.Conv3D(filters, k, strides, padding='valid') over an explicitly padded input."""
 
-    def __init__(self, net, name, k, stride, cin, cout, use_bias=True, act=ACT_NONE, dx_crop=(0, 0)):
-        """dx_crop=(lo, hi): the input carries `lo`/`hi` voxels of ZERO padding per side, so dgrad may skip them."""
+    def __init__(self, net, name, k, stride, cin, cout, use_bias=True, act=ACT_NONE, dx_crop=(0, 0), w_param=None):
+        """dx_crop=(lo, hi): the input carries `lo`/`hi` voxels of ZERO padding per side, so dgrad may skip them.
+        w_param: kernel variable to use instead of net.params[name + '.w'] (Conv3DTranspose's GEMM-layout shadow)."""
         self.dx_crop = dx_crop
-        self.w = net.params[name + ".w"]
+        self.w = w_param if w_param is not None else net.params[name + ".w"]
         self.b = net.params[name + ".b"] if use_bias else None
         self.k, self.stride, self.cin, self.cout, self.act = k, stride, cin, cout, act
         self.x_dtype = _lib.VG_F32 if cin == 1 else _lib.VG_BF16
@@ -394,6 +399,94 @@ class InstanceNorm:
                 accumulate(residual, dres)
 
         tape.record(ins, [out], [self.gamma, self.beta], bwd, "instnorm")
+        return out
+
+
+class BatchNorm:
+    """keras.layers.BatchNormalization() (vnet_model.py:127-128,142-143: axis=-1, momentum=0.99, epsilon=1e-3) followed by the
+    SpatialDropout3D / padding the reference applies before the next convolution.  Training: statistics of the LOCAL batch
+    (MirroredStrategy keeps BatchNormalization per replica) and the Keras moving-average update; inference: the moving values.
+    The arithmetic is InstanceNorm's with the reductions taken over N*D*H*W (vg_batchnorm_stats / vg_batchnorm_bwd)."""
+
+    MOMENTUM = 0.99
+
+    def __init__(self, net, name, c):
+        self.gamma = net.params[name + ".gamma"]
+        self.beta = net.params[name + ".beta"]
+        self.c = c
+        self.moving_mean = net.buffers.setdefault(name + ".moving_mean", torch.zeros(c, dtype=torch.float32, device=DEV))
+        self.moving_var = net.buffers.setdefault(name + ".moving_variance", torch.ones(c, dtype=torch.float32, device=DEV))
+
+    def __call__(self, tape, x, training=True, act=ACT_NONE, slope=0.2, pad=(0, 0, PAD_ZERO), drop=None, relu_input=False):
+        n, d, h, w, c = x.shape
+        assert c == self.c
+        dt = dtype_code(x.data) | (_lib.IN_RELU_INPUT if relu_input else 0)
+        ws_bytes = _lib.lib().vg_batchnorm_workspace_bytes(n, d, h, w, c)
+        ws = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
+        mean = torch.empty(n * c, dtype=torch.float32, device=DEV)
+        rstd = torch.empty(n * c, dtype=torch.float32, device=DEV)
+        es, nin = x.data.element_size(), x.data.numel()
+        call("vg_batchnorm_stats", x.data, dt, n, d, h, w, c, mean, rstd, self.moving_mean, self.moving_var, self.MOMENTUM,
+             1 if training else 0, ws, ws_bytes, work=float(es * nin) if training else 0.0)
+        desc = InDesc(n, d, h, w, c, dt, act, slope, pad[0], pad[1], pad[2], 0.0, 0, None)
+        pp = pad[0] + pad[1]
+        y = torch.empty((n, d + pp, h + pp, w + pp, c), dtype=x.data.dtype, device=DEV)
+        call("vg_instnorm_apply", desc, x.data, None, y, mean, rstd, self.gamma.w, self.beta.w, drop, None,
+             work=float(es * (nin + y.numel())))
+        out = Var(y)
+
+        def bwd(in_needs, p_needs):
+            assert training, "BatchNormalization backward is only defined for the batch-statistics (training) path"
+            dx = torch.empty_like(x.data)
+            ws2 = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
+            call("vg_batchnorm_bwd", desc, out.grad, x.data, mean, rstd, self.gamma.w, self.beta.w, drop, dx, 0, None,
+                 self.gamma.grad if p_needs else None, self.beta.grad if p_needs else None, ws2, ws_bytes,
+                 work=float(es * (2 * (nin + y.numel()) + nin)))
+            if in_needs[0]:
+                accumulate(x, dx)
+
+        tape.record([x], [out], [self.gamma, self.beta], bwd, "batchnorm")
+        return out
+
+
+class Conv3DTranspose:
+    """keras.layers.Conv3DTranspose(filters, (2,2,2), strides=(2,2,2), padding='same') (vnet_model.py:245).  The eight outputs of an
+    input voxel do not overlap, so the layer is ONE pointwise GEMM with 8*Cout columns (a,b,c,co) on the tensor cores (the K = 1
+    Conv3D path) followed by a depth-to-space scatter that adds the bias.  The trainable kernel stays in Keras layout
+    (2,2,2,Cout,Cin); a GEMM-layout fp32 shadow is refreshed before every operand pack and its gradient is folded back."""
+
+    def __init__(self, net, name, cin, cout):
+        self.w = net.params[name + ".w"]           # (2, 2, 2, cout, cin)
+        self.b = net.params[name + ".b"]
+        self.cin, self.cout = cin, cout
+        shadow = Param(name + ".w.gemm", (1, 1, 1, cin, 8 * cout), 0)
+        shadow.w = torch.zeros(shadow.shape, dtype=torch.float32, device=DEV)
+        shadow.grad = torch.zeros(shadow.shape, dtype=torch.float32, device=DEV)
+        self.shadow = shadow
+        self.gemm = Conv3D(net, name, 1, 1, cin, 8 * cout, use_bias=False, w_param=shadow)
+        net.pre_pack.append(lambda: call("vg_conv3d_transpose_k2s2_weights", self.w.w, shadow.w, cin, cout, 0))
+
+    def __call__(self, tape, x):
+        n, d, h, w, c = x.shape
+        inner = Tape(enabled=tape.enabled)
+        t = self.gemm(inner, x)
+        t.src = None                                       # no Var <-> Node cycle: the inner node is only reachable from bwd
+        y = torch.empty((n, 2 * d, 2 * h, 2 * w, self.cout), dtype=torch.bfloat16, device=DEV)
+        call("vg_conv3d_transpose_k2s2_scatter", t.data, self.b.w, y, n, d, h, w, self.cout)
+        out = Var(y)
+
+        def bwd(in_needs, p_needs):
+            dt = torch.empty_like(t.data)
+            call("vg_conv3d_transpose_k2s2_gather", out.grad, dt, self.b.grad if p_needs else None, n, d, h, w, self.cout)
+            t.grad = dt
+            if p_needs:
+                self.shadow.grad.zero_()
+            inner.nodes[0].bwd(in_needs, p_needs)          # pointwise wgrad (into the shadow) and dgrad (accumulates into x)
+            t.grad = None
+            if p_needs:
+                call("vg_conv3d_transpose_k2s2_weights", self.shadow.grad, self.w.grad, self.cin, self.cout, 1)
+
+        tape.record([x], [out], [self.w, self.b], bwd, "conv_transpose")
         return out
 
 

@@ -67,10 +67,9 @@ class VanGan:
         self.keep_last = False   # tests set this to inspect fake/cycled volumes after a step
 
         with self.strategy.scope():
-            if gen_i2s not in ('resUnet', 'vnet') or gen_s2i != 'resUnet':
-                raise NotImplementedError("generators: 'resUnet' (what main.py:196-200 selects) for both, and 'vnet' for "
-                                          "gen_i2s (vangan.py:97-110) are built; 'resnet' and the BatchNorm/deconv 'vnet' "
-                                          "gen_s2i variant are listed under next steps in DESIGN.md")
+            if gen_i2s not in ('resUnet', 'vnet') or gen_s2i not in ('resUnet', 'vnet'):
+                raise NotImplementedError("generators: 'resUnet' (what main.py:196-200 selects) and 'vnet' (vangan.py:97-110 for "
+                                          "gen_i2s, :135-149 for gen_s2i) are built; 'resnet' is listed under next steps in DESIGN.md")
             if gen_i2s == 'vnet':
                 self.gen_IS = custom_vnet(input_shape=self.subvol_patch_size, activation='relu', use_batch_norm=False,
                                           upsample_mode='upsample', dropout=0.5, dropout_change_per_layer=0.0,
@@ -80,9 +79,16 @@ class VanGan:
                 self.gen_IS = ResUNet(input_shape=self.subvol_patch_size, upsample_mode='simple', dropout=0.1,
                                       dropout_change_per_layer=0.1, dropout_type='none', use_attention_gate=False,
                                       filters=16, num_layers=4, name='generator_IS', seed=seed)
-            self.gen_SI = ResUNet(input_shape=self.seg_subvol_patch_size, upsample_mode='simple', dropout=0.1,
-                                  dropout_change_per_layer=0.1, dropout_type='none', use_attention_gate=False,
-                                  filters=16, num_layers=4, use_input_noise=False, name='generator_SI', seed=seed + 1)
+            if gen_s2i == 'vnet':
+                self.gen_SI = custom_vnet(input_shape=self.subvol_patch_size, activation='relu', use_batch_norm=True,
+                                          upsample_mode='deconv', dropout=0.5, dropout_change_per_layer=0.0,
+                                          dropout_type='spatial', use_dropout_on_upsampling=False, use_attention_gate=False,
+                                          filters=16, num_layers=4, output_activation='tanh', addnoise=False,
+                                          name='generator_SI', seed=seed + 1)
+            else:
+                self.gen_SI = ResUNet(input_shape=self.seg_subvol_patch_size, upsample_mode='simple', dropout=0.1,
+                                      dropout_change_per_layer=0.1, dropout_type='none', use_attention_gate=False,
+                                      filters=16, num_layers=4, use_input_noise=False, name='generator_SI', seed=seed + 1)
             common = dict(filters=64, use_dropout=True, dropout_rate=0.2, wasserstein=False, use_SN=False,
                           use_input_noise=True, use_layer_noise=True, noise_std=self.layer_noise)
             self.disc_I = get_discriminator(input_img_size=self.subvol_patch_size, batch_size=self.global_batch_size,
@@ -104,7 +110,7 @@ class VanGan:
         self._h_lr = torch.zeros(4, dtype=torch.float32).pin_memory()
         self.seed = seed
         # CUDA graph of one full train step (captured on the third eligible call; VG_GRAPH=0 disables)
-        self.use_graph = os.environ.get("VG_GRAPH", "1") != "0" and not isinstance(self.gen_IS, VNetModel)
+        self.use_graph = os.environ.get("VG_GRAPH", "1") != "0" and not isinstance(self.gen_IS, VNetModel) and not isinstance(self.gen_SI, VNetModel)
         self._graph = None
         self._eager_steps = 0
         self.launches_per_replay = 0
@@ -363,6 +369,8 @@ class VanGan:
                 arrays[on + "/m/" + k] = m[p.offset:p.offset + p.size].reshape(p.shape)
                 arrays[on + "/v/" + k] = v[p.offset:p.offset + p.size].reshape(p.shape)
             arrays[on + "/iter"] = np.int64(net.step_count)
+            for k, buf in net.buffers.items():          # non-trainable variables (BatchNormalization moving statistics)
+                arrays[nn + "/" + k] = buf.cpu().numpy()
         path = self._checkpoint_path(epoch + 1)
         np.savez(path, **arrays)
         print(f'\nSaved checkpoint to {self.checkpoint_prefix}\n')
@@ -382,6 +390,8 @@ class VanGan:
         for nn, net in self.networks.items():
             on = self._OPT_OF[nn]
             net.load({k: z[nn + "/" + k] for k in net.params})
+            for k, buf in net.buffers.items():
+                buf.copy_(torch.from_numpy(np.ascontiguousarray(z[nn + "/" + k])).to(E.DEV))
             have_slots = all((on + "/m/" + k) in z.files for k in net.params)
             if not have_slots and not expect_partial:
                 raise KeyError("checkpoint %s has no optimizer slots for %s (pass expect_partial=True)" % (path, on))
