@@ -19,13 +19,21 @@
 //     consecutive h-rows of a CC-channel chunk: D rows (j, ci) accumulate the taps th = th_base + j.
 //   * td-fold (N side): the dY planes are laid out [h][d][plane][w] with K-1 zero slices on either side,
 //     so an N = K*CO operand holds K consecutive d-slices: D columns (r, co) accumulate td = K-1-r.
+//   * tw-fold (N side, 16-wide co blocks: K*K*CO <= 256): every dY slice is staged K times, copy c shifted by c voxels along w
+//     ([h][d][copy][plane][w]), so D columns (r, c, co) accumulate (td, tw) = (K-1-r, c) and ONE MMA of N = K*K*CO covers what
+//     took K accumulators before: an MMA costs (operand fetch) ~ M/4 + N/4 cycles whatever part of it is useful.
+//     The X brick then needs no w halo; bricks tile the X w-axis (OW + K - 1 voxels).
+// Folded slices that fall outside the brick are not staged as zeros: the edge X slices issue a narrower MMA (fewer r blocks).
 // The remaining tap index (tw, and th_base / td when not folded) selects the TMEM accumulator.
 // A CTA owns a set of accumulators (<= 512 TMEM columns) for one (ci-block, co-block, tap-set) tile and a
 // split-K share of the voxel bricks; it finishes with fp32 red.global.add into dW (Keras layout).
 //
-// Roles (416 threads): warps 0-7 gather the X halo brick and the dY brick (16-byte cp.async, zero fill
-// outside the tensors), warp 8 issues tcgen05.mma (one elected lane) and owns TMEM, warps 9-12 drain the
-// accumulators at the end.  Stages form a full/empty mbarrier ring released by tcgen05.commit.
+// Roles (416 threads): warps 0-11 gather the X halo brick and the dY brick (16-byte cp.async, zero fill
+// outside the tensors), warp 12 issues tcgen05.mma (one elected lane) and owns TMEM; when the bricks are
+// done warps 0-3 drain the accumulators.  Stages form a full/empty mbarrier ring released by tcgen05.commit.
+// ncu (profiles/r02_ncu_full_wg_16-16_*_call8.txt) showed the kernel bound by the PRODUCERS' instruction streams (8 warps x ~1 200
+// dependent instructions per brick, tensor pipe 24-35 % busy), hence: 12 producer warps (the drain warps used to spin on the final
+// barrier for the whole kernel), an incremental row decode and a bounds-free inner loop for rows that lie inside the tensor.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -35,9 +43,9 @@ namespace {
 
 using namespace tcp;
 
-constexpr int WG_NPROD = 256;                 // producer threads: warps 0..7
-constexpr int WG_MMA_WARP = WG_NPROD / 32;    // warp 8 issues the MMAs, warps 9..12 drain TMEM
-constexpr int WG_THREADS = WG_NPROD + 32 + 128;
+constexpr int WG_NPROD = 384;                 // producer threads: warps 0..11 (warps 0..3 also drain TMEM at the end)
+constexpr int WG_MMA_WARP = WG_NPROD / 32;    // warp 12 issues the MMAs
+constexpr int WG_THREADS = WG_NPROD + 32;
 constexpr int WG_MAXACC = 16;
 constexpr int WG_KW = 16;   // voxels along w per MMA (K of the bf16 MMA)
 // Plane pitches (in 16-byte cells) are ODD: for a fixed k the MMA reads one 16-byte row from every M/N-group, i.e. addresses
@@ -52,11 +60,12 @@ struct WgParams {
     float* dw;
     int Nb, XD, XH, XW, Cx, OD, OH, OW, Cy, K, st;   // st: convolution stride (1 or 2)
     int M, CC, R, PLC, NCH, CB;     // MMA M; channels per chunk; rows folded; planes per chunk; chunks per CTA; CB = NCH*CC
-    int CO, NF, Nmma, NPLy;         // co block; slices folded (1 or K); MMA N = NF*CO; dY planes = CO/8
+    int CO, NF, NW, KW, Nmma, NPLy; // co block; slices folded (1 or K); w-shifted dY copies (1 or K); KW = taps along w that select an
+                                    // accumulator (K, or 1 with the tw-fold); MMA N = NF*NW*CO; dY planes = CO/8
     int nth, NTA, TPC, nsets;       // th bases; tap-accumulators in total / per CTA; tap sets
     int n_co_blocks, tiles, ksplit;
     int BDo, BHo, bd_tiles, bh_tiles, bw_tiles, nbricks;
-    int XDb, XHb, XHu, XWb, YDb, nB, ypad;   // XHu: rows that carry useful taps (<= XHb)
+    int XDb, XHb, XHu, XWb, YDb, nB;         // XHu: rows that carry useful taps (<= XHb)
     int x_sd, x_sc, x_spar, x_sh, x_nw;      // X stage strides (cells): slice, chunk, w-parity plane set (stride 2), row; voxels per row
     uint32_t x_bytes, stage_bytes, tmem_cols;
     int stages;
@@ -76,37 +85,52 @@ struct Region {
 };
 
 // 16-byte cp.async per cell (zero fill outside the tensor): no register staging, so a whole stage is in flight per SM.
-// A warp owns whole region rows: the row decode is warp-uniform and every lane keeps a fixed (plane, voxel phase), so the
-// per-cell work is two adds, a bounds test and the copy.
+// A warp owns whole region rows (row = warp, warp + 12, ...): (d, c, h) are carried incrementally, every lane keeps a fixed
+// (plane, voxel phase), and a row that lies inside the tensor runs a loop of copy + two adds per cell.
 __device__ __forceinline__ void gather_region(const Region& r, uint32_t dst_base, int warp, int lane) {
+    constexpr int NWARP = WG_NPROD / 32;
     const int P = 1 << r.lgp;
     const int pl = lane & (P - 1), wl = lane >> r.lgp, wps = 32 >> r.lgp;
     const int rows = r.nd * r.nc * r.nh;
     const uint32_t lane_dst = (uint32_t)(pl * r.sp + (r.s2 ? (wl & 1) * r.spar + (wl >> 1) : wl)) * 16u;
     const uint32_t dst_step = (uint32_t)(r.s2 ? wps >> 1 : wps) * 16u;
     const int lane_src = wl * r.C + pl * 8;
-    for (int row = warp; row < rows; row += WG_NPROD / 32) {
-        const uint32_t d = r.by_cnh.div(row), rem = row - d * (r.nc * r.nh);
-        const uint32_t c = r.by_nh.div(rem), h = rem - c * r.nh;
-        const int gd = r.gd0 + (int)d, gh = r.gh0 + (int)h;
+    const int wstep_src = wps * r.C;
+    const bool w_inside = r.gw0 >= 0 && r.gw0 + r.nw <= r.GW;
+    int d = (int)r.by_cnh.div(warp), rem = warp - d * (r.nc * r.nh);
+    int c = (int)r.by_nh.div(rem), h = rem - c * r.nh;
+    for (int row = warp; row < rows; row += NWARP) {
+        const int gd = r.gd0 + d, gh = r.gh0 + h;
         const bool rowok = (unsigned)gd < (unsigned)r.GD && (unsigned)gh < (unsigned)r.GH;
-        const bf16* src = r.g + (((size_t)(rowok ? gd : 0) * r.GH + (rowok ? gh : 0)) * r.GW + r.gw0) * r.C + (c << (r.lgp + 3)) + lane_src;
+        const bf16* src = r.g + (ptrdiff_t)(((rowok ? gd : 0) * r.GH + (rowok ? gh : 0)) * r.GW + r.gw0) * r.C + ((c << (r.lgp + 3)) + lane_src);
         uint32_t dst = dst_base + (uint32_t)(d * r.sd + c * r.sc + h * r.sh) * 16u + lane_dst;
-        const int wstep_src = wps * r.C;
-#pragma unroll 4
-        for (int w = wl; w < r.nw; w += wps) {
-            const bool ok = rowok && (unsigned)(r.gw0 + w) < (unsigned)r.GW;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(ok ? src : r.g), "r"(ok ? 16 : 0) : "memory");
-            src += wstep_src;
-            dst += dst_step;
+        if (rowok && w_inside) {
+#pragma unroll 2
+            for (int w = wl; w < r.nw; w += wps) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+                src += wstep_src;
+                dst += dst_step;
+            }
+        } else {
+            for (int w = wl; w < r.nw; w += wps) {
+                const bool ok = rowok && (unsigned)(r.gw0 + w) < (unsigned)r.GW;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(ok ? src : r.g), "r"(ok ? 16 : 0) : "memory");
+                src += wstep_src;
+                dst += dst_step;
+            }
+        }
+        h += NWARP;
+        while (h >= r.nh) {
+            h -= r.nh;
+            if (++c == r.nc) { c = 0; d++; }
         }
     }
 }
 
 struct IssueCtx {
     uint64_t a_desc0, b_desc0;
-    uint32_t idesc, leader, tmem_base, sbase16, stage16, x16, full0, empty0, done_bar;
-    int a_sd, a_sh, b_sd, b_sh, nB, BHo, Nmma, stages, first, nbricks, step;
+    uint32_t idesc[5], leader, tmem_base, sbase16, stage16, x16, full0, empty0, done_bar;   // idesc[n]: n folded slices in N
+    int a_sd, a_sh, b_sd, b_sh, nB, BHo, BDo, NF, colr, Nmma, stages, first, nbricks, step;   // colr: D columns per folded slice
 };
 
 // The MMA warp's whole life: for every brick of this CTA wait for the stage, issue nB x BHo x NACC MMAs, release the stage.
@@ -121,24 +145,27 @@ __device__ __forceinline__ void issue_bricks(const IssueCtx& c, const int* s_aof
         tm[a] = c.tmem_base + (uint32_t)(a * c.Nmma);
     }
     int stage = 0;
-    uint32_t phase = 0, accflag = 0;
+    uint32_t phase = 0;
     for (int brick = c.first; brick < c.nbricks; brick += c.step) {
         mbar_wait(c.full0 + 8 * stage, phase);
         tc_fence_after();
         const uint32_t xs16 = c.sbase16 + stage * c.stage16;
-        uint32_t a_row = xs16, b_row = xs16 + c.x16;
+        uint32_t a_row = xs16;
         for (int bs = 0; bs < c.nB; bs++) {
-            uint32_t a_pos = a_row, b_pos = b_row;
+            // td-fold: X slice bs meets the dY slices bs-(NF-1)+r, r = 0..NF-1, that exist in the brick -> r_lo..r_hi
+            const int r_lo = max(0, c.NF - 1 - bs), r_hi = min(c.NF - 1, c.BDo + c.NF - 2 - bs), cnt = r_hi - r_lo + 1;
+            const uint32_t idesc = cnt == 1 ? c.idesc[1] : (cnt == 2 ? c.idesc[2] : (cnt == 3 ? c.idesc[3] : c.idesc[4]));
+            const uint32_t dcol = (uint32_t)(r_lo * c.colr);
+            uint32_t a_pos = a_row, b_pos = xs16 + c.x16 + (uint32_t)((bs - (c.NF - 1) + r_lo) * c.b_sd);
             for (int h = 0; h < c.BHo; h++) {
                 if (c.leader) {
                     const uint64_t bdesc = c.b_desc0 + b_pos;
 #pragma unroll
-                    for (int a = 0; a < NACC; a++) tc_mma(tm[a], adesc[a] + a_pos, bdesc, c.idesc, accflag);
+                    for (int a = 0; a < NACC; a++) tc_mma(tm[a] + dcol, adesc[a] + a_pos, bdesc, idesc, 1u);
                 }
-                accflag = 1u;
                 a_pos += c.a_sh; b_pos += c.b_sh;
             }
-            a_row += c.a_sd; b_row += c.b_sd;
+            a_row += c.a_sd;
         }
         __syncwarp();
         if (c.leader) tc_commit(c.empty0 + 8 * stage);
@@ -169,7 +196,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
     int td_min = 1 << 30, thb_min = 1 << 30, tw_min = 1 << 30;
     for (int i = 0; i < nq; i++) {
         const int q = q0 + i;
-        const int tw = q % p.K, thb = (q / p.K) % p.nth, td = q / (p.K * p.nth);
+        const int tw = q % p.KW, thb = (q / p.KW) % p.nth, td = q / (p.KW * p.nth);
         td_min = min(td_min, td); thb_min = min(thb_min, thb); tw_min = min(tw_min, tw);
     }
     if (fold) td_min = 0;
@@ -184,13 +211,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
         mbar_init_fence();
         for (int i = 0; i < nq; i++) {
             const int q = q0 + i;
-            const int tw = q % p.K, thb = (q / p.K) % p.nth, td = fold ? 0 : q / (p.K * p.nth);
+            const int tw = q % p.KW, thb = (q / p.KW) % p.nth, td = fold ? 0 : q / (p.KW * p.nth);
             for (int c = 0; c < p.NCH; c++)
                 s_aoff[i * p.NCH + c] = (td - td_min) * p.x_sd + c * p.x_sc + (thb - thb_min) * p.R * p.x_sh +
                                         (p.st == 2 ? ((tw - tw_org) & 1) * p.x_spar + ((tw - tw_org) >> 1) : tw - tw_org);
         }
     }
-    // zero the stages once: the dY pad slices (td-fold) are never written again
+    // zero the stages once (pad cells of the odd plane pitches are never written)
     for (uint32_t o = threadIdx.x * 16u; o < (uint32_t)p.stages * p.stage_bytes; o += WG_THREADS * 16u)
         asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(sbase + o), "r"(0) : "memory");
     fence_async_smem();
@@ -199,6 +226,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // every MMA accumulates (the edge slices of a td-folded brick touch only part of the columns, so "first MMA overwrites" does
+    // not cover them): the drain warps hand the accumulators over zeroed
+    if (warp < 4) {
+        for (uint32_t col = 0; col < p.tmem_cols; col += 16) tc_st16_zero(tmem_base + ((uint32_t)(warp * 32) << 16) + col);
+        tc_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     if (warp < WG_MMA_WARP) {
         // ------------------------------------------------------------------ gather producers
@@ -213,7 +249,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
         ry.GD = p.OD; ry.GH = p.OH; ry.GW = p.OW; ry.C = p.Cy;
         ry.nd = p.BDo; ry.nc = 1; ry.nh = p.BHo; ry.nw = WG_KW; ry.lgp = lgy;
         ry.s2 = 0; ry.spar = 0;
-        ry.sd = p.NPLy * WG_YP; ry.sc = 0; ry.sh = p.YDb * p.NPLy * WG_YP; ry.sp = WG_YP;
+        ry.sd = p.NW * p.NPLy * WG_YP; ry.sc = 0; ry.sh = p.YDb * ry.sd; ry.sp = WG_YP;
         ry.by_cnh = FastDiv(ry.nh); ry.by_nh = FastDiv(ry.nh);
         int stage = 0, prev_stage = -1;
         uint32_t phase = 0;
@@ -226,11 +262,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
             rx.g = p.x + (size_t)n * p.XD * p.XH * p.XW * p.Cx + (size_t)cib * p.CB;
             rx.gd0 = bd * p.BDo * p.st + td_min; rx.gh0 = bh * p.BHo * p.st + thb_min * p.R; rx.gw0 = bw * WG_KW * p.st + tw_org;
             ry.g = p.dy + (size_t)n * p.OD * p.OH * p.OW * p.Cy + (size_t)cob * p.CO;
-            ry.gd0 = bd * p.BDo; ry.gh0 = bh * p.BHo; ry.gw0 = bw * WG_KW;
+            ry.gd0 = bd * p.BDo; ry.gh0 = bh * p.BHo;
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t xs = sbase + stage * p.stage_bytes;
             gather_region(rx, xs, warp, lane);
-            gather_region(ry, xs + p.x_bytes + (uint32_t)p.ypad * p.NPLy * WG_YP * 16u, warp, lane);
+            for (int c = 0; c < p.NW; c++) {   // tw-fold: copy c holds dY shifted by c voxels (zero fill outside the tensor)
+                ry.gw0 = bw * WG_KW - c;
+                gather_region(ry, xs + p.x_bytes + (uint32_t)(c * p.NPLy * WG_YP) * 16u, warp, lane);
+            }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
             if (p.stages >= 3) {
                 // lagged publish: hand over the previous brick while this one is in flight
@@ -253,18 +292,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
             fence_async_smem();
             mbar_arrive(full0 + 8 * prev_stage);
         }
-    } else if (warp == WG_MMA_WARP) {
+    }
+    if (warp == WG_MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
         // One elected lane issues; the loops are warp-uniform so descriptors stay in uniform registers.  The issue loop is
         // the critical resource of this kernel (one MMA is only 24-128 tensor-pipe cycles), hence the compile-time NACC.
         IssueCtx c;
-        c.idesc = make_idesc_bf16(p.M, p.Nmma, 1, 1);
+        for (int n = 1; n <= 4; n++) c.idesc[n] = make_idesc_bf16(p.M, (p.NF > 1 ? n : 1) * p.NW * p.CO, 1, 1);
         c.leader = elect_one();
         c.a_desc0 = ((uint64_t)((uint32_t)p.XWb | (1u << 14)) << 32) | (8u << 16);   // SBO = X plane pitch | version ; LBO = 128 B
         c.b_desc0 = ((uint64_t)((uint32_t)WG_YP | (1u << 14)) << 32) | (8u << 16);   // SBO = dY plane pitch
         c.a_sd = p.st * p.x_sd; c.a_sh = p.st * p.x_sh;
-        c.b_sd = p.NPLy * WG_YP; c.b_sh = p.YDb * p.NPLy * WG_YP;
-        c.nB = p.nB; c.BHo = p.BHo; c.Nmma = p.Nmma; c.tmem_base = tmem_base;
+        c.b_sd = p.NW * p.NPLy * WG_YP; c.b_sh = p.YDb * c.b_sd;
+        c.nB = p.nB; c.BHo = p.BHo; c.BDo = p.BDo; c.NF = p.NF; c.colr = p.NW * p.CO; c.Nmma = p.Nmma; c.tmem_base = tmem_base;
         c.sbase16 = sbase >> 4; c.stage16 = p.stage_bytes >> 4; c.x16 = p.x_bytes >> 4; c.stages = p.stages;
         c.full0 = full0; c.empty0 = empty0; c.done_bar = done_bar;
         c.first = split; c.nbricks = p.nbricks; c.step = p.ksplit;
@@ -286,9 +326,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
             case 15: issue_bricks<15>(c, s_aoff); break;
             default: issue_bricks<16>(c, s_aoff); break;
         }
-    } else {
+    } else if (warp < 4) {
         // ------------------------------------------------------------------ epilogue: TMEM -> red.global.add
-        const int qd = warp & 3;                      // TMEM lane quarter this warp may access
+        const int qd = warp;                          // TMEM lane quarter this warp may access
         mbar_wait(done_bar, 0);
         tc_fence_after();
         // lane -> MMA row m.  M = 128: m = 32*qd + lane.  M = 64: rows live in lanes 0-15 of each quarter, m = 16*qd + lane.
@@ -298,7 +338,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
         for (int a = 0; a < nacc; a++) {
             const int i = a / p.NCH, c = a - i * p.NCH;
             const int q = q0 + i;
-            const int tw = q % p.K, thb = (q / p.K) % p.nth, tdq = q / (p.K * p.nth);
+            const int twq = q % p.KW, thb = (q / p.KW) % p.nth, tdq = q / (p.KW * p.nth);
             const int th = thb * p.R + j;
             const bool row_ok = lane_ok && th < p.K;
             const int ci = cib * p.CB + c * p.CC + cil;
@@ -306,7 +346,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
                 uint32_t v[16];
                 tc_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * p.Nmma + n0), v);
                 if (row_ok) {
-                    const int r = n0 / p.CO, col = n0 - r * p.CO;
+                    const int blk = n0 / p.CO, col = n0 - blk * p.CO;
+                    const int r = blk / p.NW, tw = p.NW > 1 ? blk - r * p.NW : twq;
                     const int td = fold ? p.K - 1 - r : tdq;
                     float* o = p.dw + ((size_t)((td * p.K + th) * p.K + tw) * p.Cx + ci) * p.Cy + cob * p.CO + col;
 #pragma unroll
@@ -359,10 +400,20 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
     p.CO = (co256 || stride == 2) ? largest_div(Cy, cos, 5) : largest_div(Cy, cos + 1, 4);   // measured: 256->512 k4 s1 0.96 -> 0.69 ms, 128->256 k4 s2 0.51 -> 0.55 ms (kept at 256)
     p.NPLy = p.CO / 8;
     p.NF = (stride == 1 && K > 1 && K * p.CO <= 256) ? K : 1;
-    p.Nmma = p.NF * p.CO;
+    // tw-fold: opt-in (VG_WG_NW=1).  Measured on B200 (profiles/r02_wgrad_twfold_call9.txt): 3x fewer MMAs but 16->16 0.77 -> 1.14 ms,
+    // because the kernel is bound by the 16-byte cp.async gather (~1.5 cycles per cell per SM, one L2 sector request per cell) and
+    // the K shifted dY copies add 44 % more cells per brick.
+    static int nwfold = -1;
+    if (nwfold < 0) {
+        const char* e = getenv("VG_WG_NW");
+        nwfold = (e && e[0] == '1') ? 1 : 0;
+    }
+    p.NW = (nwfold && p.NF > 1 && K * K * p.CO <= 256) ? K : 1;
+    p.KW = p.NW > 1 ? 1 : K;
+    p.Nmma = p.NF * p.NW * p.CO;
     if (p.M == 128 && p.Nmma % 16) return VG_ERR_UNSUPPORTED;
     p.nth = (K + p.R - 1) / p.R;
-    p.NTA = (p.NF > 1 ? 1 : K) * p.nth * K;
+    p.NTA = (p.NF > 1 ? 1 : K) * p.nth * p.KW;
     int maxacc = 512 / p.Nmma;
     if (maxacc > WG_MAXACC) maxacc = WG_MAXACC;
     const int nch_tot = Cx / p.CC;
@@ -386,27 +437,35 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
         for (int s = 0; s < p.nsets; s++) {
             int tdl = 1 << 30, tdh = -1, thl = 1 << 30, thh = -1;
             for (int q = s * p.TPC; q < p.NTA && q < (s + 1) * p.TPC; q++) {
-                int thb = (q / K) % p.nth, td = q / (K * p.nth);
+                int thb = (q / p.KW) % p.nth, td = q / (p.KW * p.nth);
                 tdl = td < tdl ? td : tdl; tdh = td > tdh ? td : tdh;
                 thl = thb < thl ? thb : thl; thh = thb > thh ? thb : thh;
             }
             if (tdh - tdl > tdspan) tdspan = tdh - tdl;
             if (thh - thl > thspan) thspan = thh - thl;
         }
-        p.XWb = WG_XW;
+        p.XWb = p.NW > 1 ? WG_YP : WG_XW;   // tw-fold: no w halo on the X side
+        const int ow_ext = p.NW > 1 ? OW + K - 1 : OW;   // w extent the bricks tile
+        static int fb_d = -1, fb_h = -1;                 // VG_WG_BRICK=d,h forces the brick (tuning)
+        if (fb_d < 0) {
+            fb_d = fb_h = 0;
+            const char* e = getenv("VG_WG_BRICK");
+            if (e) sscanf(e, "%d,%d", &fb_d, &fb_h);
+        }
         const int want = 148 / p.tiles > 0 ? 148 / p.tiles : 1;
         int best = -1;
         for (int ci = 0; ci < 7; ci++) {
             const int bdo = cand[ci][0], bho = cand[ci][1];
+            if (fb_d > 0 && (bdo != fb_d || bho != fb_h)) continue;
             if (bdo > 1 && bdo >= 2 * OD) continue;
             if (bho > 1 && bho >= 2 * OH) continue;
             const int xdb = p.NF > 1 ? bdo + K - 1 : (bdo - 1) * stride + tdspan + 1;
             const int xhb = (bho - 1) * stride + thspan * p.R + p.R;
-            const int ydb = p.NF > 1 ? bdo + 2 * (K - 1) : bdo;
+            const int ydb = bdo;
             const size_t xb = (size_t)xdb * p.NCH * stride * xhb * p.PLC * p.XWb * 16;
-            const size_t yb = (size_t)bho * ydb * p.NPLy * WG_YP * 16;
+            const size_t yb = (size_t)bho * ydb * p.NW * p.NPLy * WG_YP * 16;
             if (2 * (xb + yb) + 256 > smem_cap) continue;
-            const long long nbr = (long long)Nb * ((OD + bdo - 1) / bdo) * ((OH + bho - 1) / bho) * ((OW + WG_KW - 1) / WG_KW);
+            const long long nbr = (long long)Nb * ((OD + bdo - 1) / bdo) * ((OH + bho - 1) / bho) * ((ow_ext + WG_KW - 1) / WG_KW);
             best = ci;
             if (nbr >= 2LL * want) break;   // enough bricks to feed every split; else keep shrinking
         }
@@ -417,11 +476,10 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
         p.XHu = (p.BHo - 1) * stride + thspan * p.R + (p.R < K ? p.R : K);
         p.x_sh = p.PLC * p.XWb; p.x_spar = p.XHb * p.x_sh; p.x_sc = stride * p.x_spar; p.x_sd = p.NCH * p.x_sc;
         p.x_nw = stride == 2 ? 2 * (WG_KW + 1) : p.XWb;
-        p.YDb = p.NF > 1 ? p.BDo + 2 * (K - 1) : p.BDo;
-        p.ypad = p.NF > 1 ? K - 1 : 0;
+        p.YDb = p.BDo;
         p.nB = p.NF > 1 ? p.BDo + K - 1 : p.BDo;
         p.x_bytes = (uint32_t)((size_t)p.XDb * p.x_sd * 16);
-        const uint32_t yb = (uint32_t)((size_t)p.BHo * p.YDb * p.NPLy * WG_YP * 16);
+        const uint32_t yb = (uint32_t)((size_t)p.BHo * p.YDb * p.NW * p.NPLy * WG_YP * 16);
         p.stage_bytes = (p.x_bytes + yb + 127) & ~127u;
         p.stages = (int)((smem_cap - 256) / p.stage_bytes);
         if (p.stages > 4) p.stages = 4;
@@ -429,7 +487,8 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
         found = true;
     }
     if (!found) return VG_ERR_UNSUPPORTED;
-    p.bd_tiles = (OD + p.BDo - 1) / p.BDo; p.bh_tiles = (OH + p.BHo - 1) / p.BHo; p.bw_tiles = (OW + WG_KW - 1) / WG_KW;
+    p.bd_tiles = (OD + p.BDo - 1) / p.BDo; p.bh_tiles = (OH + p.BHo - 1) / p.BHo;
+    p.bw_tiles = ((p.NW > 1 ? OW + K - 1 : OW) + WG_KW - 1) / WG_KW;
     const long long nbricks = (long long)Nb * p.bd_tiles * p.bh_tiles * p.bw_tiles;
     if (nbricks > 0x3fffffff) return VG_ERR_UNSUPPORTED;
     p.nbricks = (int)nbricks;
@@ -450,8 +509,8 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
     wgrad_tc_kernel<<<p.tiles * p.ksplit, WG_THREADS, smem, stream>>>(p);
     if (getenv("VG_DEBUG")) {
         cudaError_t e = cudaPeekAtLastError();
-        fprintf(stderr, "[wgrad_tc] Cx=%d Cy=%d K=%d M=%d CC=%d NCH=%d CO=%d NF=%d N=%d TPC=%d nsets=%d tiles=%d ksplit=%d brick=%dx%d stages=%d stage=%uB tmem=%u : %s\n",
-                Cx, Cy, K, p.M, p.CC, p.NCH, p.CO, p.NF, p.Nmma, p.TPC, p.nsets, p.tiles, p.ksplit, p.BDo, p.BHo, p.stages, p.stage_bytes,
+        fprintf(stderr, "[wgrad_tc] Cx=%d Cy=%d K=%d M=%d CC=%d NCH=%d CO=%d NF=%d NW=%d N=%d TPC=%d nsets=%d tiles=%d ksplit=%d brick=%dx%d stages=%d stage=%uB tmem=%u : %s\n",
+                Cx, Cy, K, p.M, p.CC, p.NCH, p.CO, p.NF, p.NW, p.Nmma, p.TPC, p.nsets, p.tiles, p.ksplit, p.BDo, p.BHo, p.stages, p.stage_bytes,
                 p.tmem_cols, cudaGetErrorString(e));
     }
     VG_LAUNCHED(1);
