@@ -272,6 +272,14 @@ def run_gpu(args):
     ms = timed(step_resident, args.steps)
     launches = _lib.lib().vg_launch_count() - l0
     graph_on = gan._graph is not None
+    launch_mode = "eager launches"
+    if graph_on:
+        launch_mode = ("CUDA graph replay: one graph (losses, four backward sweeps, clip+Adam, operand repack)" if world == 1 else
+                       ("CUDA graph replay: one graph with the bucketed NCCL all-reduces (vg_comm) captured on the communication stream"
+                        if gan._graph["mode"] == "single" else
+                        "CUDA graph replay: one graph per backward sweep + one for clip+Adam; each network's bucketed NCCL all-reduce "
+                        "(vg_comm) is enqueued on the communication stream between the replays and overlaps the next sweep"))
+    comm_msgs = int(strategy._L.vg_comm_collectives(strategy.comm)) if strategy.comm is not None else 0
     if graph_on:                   # replays do not pass through the host-side launch counter: count what the graph holds
         launches = gan.launches_per_replay * args.steps
     clk = clocks.stop() if rank == 0 else None
@@ -299,6 +307,7 @@ def run_gpu(args):
         sliding = bc.run_sliding(gen=gan.gen_IS, strategy=strategy, cases=((False, "512x512x256, 128^3 windows, stride 64, complete=False"),))[0]
     if world > 1:
         dist.barrier()
+        strategy.destroy()
         dist.destroy_process_group()
     if rank != 0:
         return
@@ -353,11 +362,14 @@ def run_gpu(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": bench_config(S, G, world),
-            "launch_mode": "CUDA graph replay (one graph per backward sweep, NCCL all-reduce between them)" if graph_on else "eager launches",
+            "launch_mode": launch_mode,
             "clocks": clk, "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * b * S ** 3 * 4 * world),
                                    "d2h_bytes_per_step": int(64 * 8 * world), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "roofline_other_kernels": extra,
             "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    if world > 1:
+        line["comm"] = {"library": "vg_comm (NCCL %d resolved at run time)" % _lib.lib().vg_comm_nccl_version() if strategy.use_vg_comm else "torch.distributed",
+                        "messages_enqueued_outside_graph_replays": comm_msgs, "bucket_elems": __import__("van_gan_b200.distribute", fromlist=["x"]).BUCKET_ELEMS}
     if sliding is not None:
         line["sliding_window"] = {"value": sliding["Mvoxel_per_s"], "unit": "Mvoxel/s", "windows": sliding["windows"],
                                   "seconds": sliding["seconds"], "gen_fwd_TFLOPs": sliding["gen_fwd_TFLOPs"], "workload": sliding["case"]}

@@ -221,6 +221,29 @@ int vg_conv3d_transpose_k2s2_gather(const void* dy, void* dt, float* dbias, int 
 int vg_conv3d_transpose_k2s2_weights(const float* src, float* dst, int Cin, int Cout, int dir, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Data-parallel exchange (tf.distribute.MirroredStrategy: main.py:22, vangan.py:86; the gradient all-reduce hidden inside
+ * `optimizer.minimize`, vangan.py:426-438; strategy.reduce(SUM) of the result dict, vangan.py:459-473).
+ * One process per GPU; NCCL over NVLink / NVSwitch, resolved at run time (dlopen of libnccl.so.2; VG_NCCL_LIB overrides), so
+ * single-GPU users need no NCCL.  vg_comm is the library's only opaque handle.  Rank 0 obtains a 128-byte id with
+ * vg_comm_unique_id and hands it to the other ranks by any host-side channel; every rank then calls vg_comm_init (blocking
+ * rendezvous).  Collectives are enqueued on the caller's stream (a communication stream ordered by events; capturable into a CUDA
+ * graph), are in place, and SUM across ranks.  world == 1: every call is a no-op returning 0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vg_comm vg_comm;
+int vg_comm_available(void);        /* 1 when the NCCL symbols could be resolved */
+int vg_comm_nccl_version(void);     /* NCCL_VERSION_CODE of the library in use, 0 when unavailable */
+int vg_comm_unique_id(void* id128);
+int vg_comm_init(vg_comm** out, const void* id128, int world, int rank, int device);
+int vg_comm_world(const vg_comm* c);
+int vg_comm_rank(const vg_comm* c);
+unsigned long long vg_comm_collectives(const vg_comm* c);   /* messages enqueued so far */
+/* fp32 gradient buffer of one network, cut into messages of bucket_elems elements (<= 0: one message), one grouped launch */
+int vg_comm_allreduce_bucket(vg_comm* c, float* buf, long long count, long long bucket_elems, void* stream);
+/* n fp64 scalars in device memory (the ten-entry result dict) */
+int vg_comm_reduce_scalars(vg_comm* c, double* vals, int n, void* stream);
+int vg_comm_destroy(vg_comm* c);
+
+/* ---------------------------------------------------------------------------------------------
  * Sliding-window stitching (custom_callback.py:123,165-166,177-183,192,202).
  * pred/cnt: [H,W,D] fp32 volumes; win: [B,kH,kW,kD] generator outputs; starts: [B][3] window origins.
  * ------------------------------------------------------------------------------------------- */

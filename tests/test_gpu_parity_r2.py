@@ -303,20 +303,26 @@ def _fresh_gan(S, b, use_graph, seed=77):
     return gan
 
 
-def test_graph_replay_equals_eager(cuda):
-    """bench.py times CUDA-graph replay with in-kernel Philox noise / dropout and the device-resident Adam step size; the parity
+@pytest.mark.parametrize("split", [False, True])
+def test_graph_replay_equals_eager(cuda, split, monkeypatch):
+    """split=True: one graph per backward sweep + one for clip+Adam -- the capture layout of the multi-GPU step, where each network's
+    gradient all-reduce is enqueued between the replays (VG_GRAPH_SPLIT=1 selects it on one GPU).
+    bench.py times CUDA-graph replay with in-kernel Philox noise / dropout and the device-resident Adam step size; the parity
     tests above run eager launches.  From the SAME state (weights, Adam slots, step counters -> same noise keys) one replayed step
     and one eagerly launched step must give the same ten losses, the same four gradient buffers and the same updated weights.
     (Compared over ONE step: the weight-gradient kernels add with fp32 atomics, and after a few Adam updates that order noise is
     amplified like any other perturbation -- two eager runs differ by 3e-4 in D_S_loss after a single update.)"""
     from test_gpu_train_step import synth
     S, b = 32, 2
+    if split:
+        monkeypatch.setenv("VG_GRAPH_SPLIT", "1")
     rng = np.random.default_rng(31)
     batches = [synth(rng, b, S) for _ in range(4)]
     gan = _fresh_gan(S, b, True)
     for I, Sg in batches[:3]:
         gan.train_step(I.cuda(), Sg.cuda())
     assert gan._graph is not None and gan.launches_per_replay > 100, "the graph path did not engage"
+    assert gan._graph["mode"] == ("per-sweep" if split else "single") and len(gan._graph["graphs"]) == (5 if split else 1)
     snap = {k: (net.w.clone(), net.m.clone(), net.v.clone(), net.step_count) for k, net in gan.networks.items()}
     step0 = gan.step
 

@@ -69,6 +69,16 @@ SIGNATURES = {
     "vg_conv3d_transpose_k2s2_scatter": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vg_conv3d_transpose_k2s2_gather": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vg_conv3d_transpose_k2s2_weights": (_I, [_P, _P, _I, _I, _I, _P]),
+    "vg_comm_available": (_I, []),
+    "vg_comm_nccl_version": (_I, []),
+    "vg_comm_unique_id": (_I, [_P]),
+    "vg_comm_init": (_I, [C.POINTER(C.c_void_p), _P, _I, _I, _I]),
+    "vg_comm_world": (_I, [_P]),
+    "vg_comm_rank": (_I, [_P]),
+    "vg_comm_collectives": (_ULL, [_P]),
+    "vg_comm_allreduce_bucket": (_I, [_P, _P, _LL, _LL, _P]),
+    "vg_comm_reduce_scalars": (_I, [_P, _P, _I, _P]),
+    "vg_comm_destroy": (_I, [_P]),
     "vg_pad_noise": (_I, [_P, _P, _I, _I, _I, _I, _P, _F, _ULL, _P, _P]),
     "vg_dropout_mask": (_I, [_P, _I, _F, _ULL, _P, _P]),
     "vg_pad_fold": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

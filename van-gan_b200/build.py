@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
             for line in out.splitlines():
                 if "spill" in line and "0 bytes spill stores, 0 bytes spill loads" not in line:
                     sys.stderr.write("[spill] %s: %s\n" % (os.path.basename(src), line.strip()))
-    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     return OUT
 
 

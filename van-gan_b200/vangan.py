@@ -201,8 +201,7 @@ class VanGan:
         plan = self._plan(total_I, total_S, dI, dS)
         handles = []
         for net, loss in plan:
-            net.zero_grad()
-            self.tape.backward(loss.seeds(), net.trainable_variables)
+            self._sweep(net, loss)
             # MirroredStrategy's gradient all-reduce: launched as soon as this network's sweep ends, overlapping the next sweep
             handles.append(self.strategy.all_reduce_async(net.g) if overlap_allreduce else None)
         return result, plan, handles
@@ -269,26 +268,67 @@ class VanGan:
         return (tuple(a.shape), tuple(b.shape))
 
     def _capture(self, real_I, real_S):
-        """Two graphs: (1) losses + four backward sweeps, (2) clip+Adam + operand repack.  The gradient all-reduce (world > 1)
-        runs between the two replays as ordinary NCCL calls: collectives are kept out of the capture on purpose."""
+        """The step as CUDA graphs.
+        World 1: ONE graph -- losses, the four backward sweeps, clip+Adam, operand repack.
+        World > 1: one graph per backward sweep (the first also holds the forward pass and the losses) + one for clip+Adam.  Between
+        the replays each network's bucketed gradient all-reduce is enqueued on the communication stream (vg_comm, ordered by
+        events), so it runs while the NEXT sweep's graph executes; the Adam graph is ordered after the last message.  The replays
+        and the collectives are all asynchronous: the host enqueues the whole step without waiting.
+        VG_GRAPH_COMM=1 captures the collectives INTO a single graph instead (measured: fine at 32^3, hangs at 4x128^3 per GPU on
+        2 GPUs -- kept opt-in for investigation)."""
         from . import _lib
         key = self._shape_key(real_I, real_S)
         gI = torch.empty(key[0], dtype=torch.float32, device=E.DEV)
         gS = torch.empty(key[1], dtype=torch.float32, device=E.DEV)
+        world = self.strategy.num_replicas_in_sync
+        in_graph_comm = world > 1 and os.environ.get("VG_GRAPH_COMM", "0") == "1" and self.strategy._ensure_comm()
         torch.cuda.synchronize()
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         l0 = _lib.lib().vg_launch_count()
-        with torch.cuda.graph(g1, capture_error_mode="thread_local"):
-            result, _plan, _h = self._body_losses_and_sweeps(E.Var(gI), E.Var(gS), None, False)
-        with torch.cuda.graph(g2, pool=g1.pool(), capture_error_mode="thread_local"):
-            self._body_adam()
+        graphs = []
+
+        def capture(fn):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=graphs[0].pool() if graphs else None, capture_error_mode="thread_local"):
+                out = fn()
+            graphs.append(g)
+            return out
+
+        split = (world > 1 and not in_graph_comm) or os.environ.get("VG_GRAPH_SPLIT") == "1"   # VG_GRAPH_SPLIT=1: per-sweep graphs at world 1 (tests)
+        if not split:
+            def whole():
+                result, _plan, handles = self._body_losses_and_sweeps(E.Var(gI), E.Var(gS), None, in_graph_comm)
+                for h in handles:
+                    if h is not None:
+                        h.wait()
+                self._body_adam()
+                return result
+            result = capture(whole)
+            mode = "single"
+        else:
+            state = {}
+
+            def first():
+                res = {}
+                res, total_I, total_S, dI, dS, _fI, _fS = self.compute_losses(E.Var(gI), E.Var(gS), res, training=True, rand=None)
+                state["plan"] = self._plan(total_I, total_S, dI, dS)
+                self._sweep(*state["plan"][0])
+                return res
+            result = capture(first)
+            for net, loss in state["plan"][1:]:
+                capture(lambda net=net, loss=loss: self._sweep(net, loss))
+            capture(self._body_adam)
+            mode = "per-sweep"
         self.launches_per_replay = int(_lib.lib().vg_launch_count() - l0)
         ctx = self.loss_ctx
         # the graphs' private pool keeps every buffer the capture touched; the Python-side tape is not needed again
         self.tape.clear()
         self.tape, self.last = None, None
-        self._graph = dict(key=key, g1=g1, g2=g2, I=gI, S=gS, result=result, ctx=ctx,
+        self._graph = dict(key=key, graphs=graphs, mode=mode, I=gI, S=gS, result=result, ctx=ctx,
                            noise=(self.disc_I.noise_std, self.disc_S.noise_std))
+
+    def _sweep(self, net, loss):
+        net.zero_grad()
+        self.tape.backward(loss.seeds(), net.trainable_variables)
 
     def _replay(self, real_I, real_S):
         g = self._graph
@@ -297,11 +337,17 @@ class VanGan:
         g["I"].copy_(a, non_blocking=True)        # H2D (pinned host batch) or D2D
         g["S"].copy_(b, non_blocking=True)
         self._upload_step_state()
-        g["g1"].replay()
-        if self.strategy.num_replicas_in_sync > 1:
-            for net in (self.gen_IS, self.gen_SI, self.disc_I, self.disc_S):
-                self.strategy.reduce("SUM", net.g)
-        g["g2"].replay()
+        if g["mode"] == "single":
+            g["graphs"][0].replay()
+        else:
+            handles = []
+            for gr, net in zip(g["graphs"][:4], (self.gen_IS, self.gen_SI, self.disc_I, self.disc_S)):
+                gr.replay()
+                handles.append(self.strategy.all_reduce_async(net.g))     # runs beside the next sweep's graph
+            for h in handles:
+                if h is not None:
+                    h.wait()
+            g["graphs"][4].replay()
         g["ctx"].host = None
         return self._finish_step(g["result"], g["ctx"], True)
 
