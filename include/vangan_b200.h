@@ -28,7 +28,12 @@ enum { VG_F32 = 0, VG_BF16 = 1 };
 /* OR-ed into the dtype of the vg_instnorm_* calls: the tensor being normalised is relu(x) — the producer was a
  * Conv3D(activation='relu') (vnet_model.py:118-126,133-141) whose ReLU is applied on load, and whose gradient mask is
  * applied to dx */
-enum { VG_IN_RELU_INPUT = 0x100, VG_IN_BATCH_STATS = 0x200 /* backward reductions over the whole batch: BatchNormalization */ };
+enum {
+    VG_IN_RELU_INPUT = 0x100,
+    VG_IN_BATCH_STATS = 0x200, /* backward reductions over the whole batch: BatchNormalization */
+    VG_IN_DY_SCRATCH = 0x400   /* vg_instnorm_bwd may overwrite dy (it folds the reflected halo into the interior in place once instead
+                                * of re-gathering it in both passes); without the flag dy is read-only */
+};
 enum { VG_ACT_NONE = 0, VG_ACT_RELU = 1, VG_ACT_LEAKY = 2, VG_ACT_TANH = 3 };
 enum { VG_PAD_ZERO = 0, VG_PAD_REFLECT = 1 };
 

@@ -32,11 +32,12 @@ for (N, S, C, pad) in shapes:
     wsb = L.vg_instnorm_workspace_bytes(N, S, S, S, C)
     ws = torch.empty(wsb // 4 + 1, device="cuda")
     desc = InDesc(N, S, S, S, C, _lib.VG_BF16, ACT_RELU if pad else ACT_NONE, 0.2, pad, pad, PAD_REFLECT, 0.0, 0)
+    desc_b = InDesc(N, S, S, S, C, _lib.VG_BF16 | _lib.IN_DY_SCRATCH, ACT_RELU if pad else ACT_NONE, 0.2, pad, pad, PAD_REFLECT, 0.0, 0)
     el = x.numel(); elp = y.numel()
     t = timeit(lambda: call("vg_instnorm_stats", x, _lib.VG_BF16, N, S, S, S, C, mean, rstd, ws, wsb))
     print("stats N=%d S=%d C=%d: %.3f ms %.0f GB/s" % (N, S, C, t, el * 2 / t / 1e6))
     t = timeit(lambda: call("vg_instnorm_apply", desc, x, res, y, mean, rstd, gamma, beta, None, None))
     print("apply N=%d S=%d C=%d pad=%d: %.3f ms %.0f GB/s" % (N, S, C, pad, t, (el * 2 * (2 if res is not None else 1) + elp * 2) / t / 1e6))
-    t = timeit(lambda: call("vg_instnorm_bwd", desc, dy, x, mean, rstd, gamma, beta, None, dx, 0, dres, dg, db, ws, wsb))
+    t = timeit(lambda: call("vg_instnorm_bwd", desc_b, dy, x, mean, rstd, gamma, beta, None, dx, 0, dres, dg, db, ws, wsb))
     byt = (el * 2 + elp * 2) * 2 + el * 2 * (2 if dres is not None else 1)
     print("bwd   N=%d S=%d C=%d pad=%d: %.3f ms %.0f GB/s" % (N, S, C, pad, t, byt / t / 1e6), flush=True)

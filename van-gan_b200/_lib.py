@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libvangan_b200.so")
 VG_F32, VG_BF16 = 0, 1
 IN_RELU_INPUT = 0x100
 IN_BATCH_STATS = 0x200
+IN_DY_SCRATCH = 0x400
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT = 0, 1
 _ERR = {-1: "invalid argument", -2: "unsupported shape", -3: "workspace too small", -4: "CUDA error"}

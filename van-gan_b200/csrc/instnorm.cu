@@ -8,6 +8,8 @@
 // (parity-test path) activations, fp32 statistics.  All kernels are HBM-bound: 128-bit accesses,
 // 8 channels per thread, per-(n,c) reductions by shared-memory tree + a deterministic
 // second-stage reduction (no floating-point atomics).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -671,7 +673,7 @@ __device__ __noinline__ void shell_fold(const T* __restrict__ dyn, const Geo& g,
 // dx = gamma*rstd*(g - S1/V - xhat*S2/V) with g = fold(dy)*drop*act'(z); dres = fold(dy) (optional).
 // fold: REFLECT -> every padded position whose mirror is this voxel (1 for interior voxels, up to 8 on the
 // shell); ZERO -> the interior only.
-template <typename T, int SP>
+template <typename T, int SP, bool FOLDED>
 __global__ void __launch_bounds__(NT, 2) in_bwd_apply_sp_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g, BwdArgs a,
                                                           const float* __restrict__ sums, T* __restrict__ dx,
                                                           T* __restrict__ dres, int accumulate_dx) {
@@ -725,7 +727,7 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_sp_kernel(const T* __restr
             unpack_raw(rx[u], f);
             unpack_raw(rg[u], gy);
             const int d = cd[u], h = ch[u], w = cw[u];
-            if (refl && (d == 1 || d == g.D - 2 || h == 1 || h == g.H - 2 || w == 1 || w == g.W - 2))
+            if (!FOLDED && refl && (d == 1 || d == g.D - 2 || h == 1 || h == g.H - 2 || w == 1 || w == g.W - 2))
                 shell_fold<T>(dyn, g, PH, PW, C, d, h, w, gy);   // shell voxel: add the mirrored halo positions (rare, not inlined)
             if (drn) store8<T>(drn + (size_t)vv * C, gy);
             float o[8];
@@ -740,6 +742,128 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_sp_kernel(const T* __restr
             }
             store8<T>(dxn + (size_t)vv * C, o);
         }
+    }
+}
+
+// ------------------------------------------------------------------ reflect-pad fold as a pass of its own (fast path)
+// dy (padded by 1, REFLECT) is folded IN PLACE: every interior voxel of the padded tensor that has a coordinate in {1, S-2}
+// receives the halo positions that mirror onto it.  Halo cells are only read and shell cells only written, so there is no
+// hazard.  One thread per (face voxel, 8-channel group); a voxel on several faces is handled by the first face that owns it
+// (d faces, then h, then w).  After this pass both backward passes read the INTERIOR of dy only, with x walked linearly --
+// the layout of the un-padded variant, which runs at 93 % of the HBM copy bandwidth (the mirrored / divergent shell accesses
+// held the padded variant at 57 %: profiles/r02_instnorm_fold_call16.txt).
+template <typename T>
+__global__ void __launch_bounds__(256) in_fold_inplace_kernel(T* __restrict__ dy, Geo g) {
+    const int C = g.C, cg = C / 8, D = g.D, H = g.H, W = g.W;
+    const int PH = H + 2, PW = W + 2;
+    const long long per_face[3] = {(long long)H * W, (long long)D * W, (long long)D * H};
+    const long long total = 2 * (per_face[0] + per_face[1] + per_face[2]) * cg;
+    T* dyn = dy + (size_t)blockIdx.y * (D + 2) * PH * PW * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cg);
+        long long v = i / cg;
+        int d, h, w;
+        if (v < 2 * per_face[0]) {                       // d faces
+            d = v < per_face[0] ? 1 : D - 2;
+            v %= per_face[0];
+            h = (int)(v / W); w = (int)(v % W);
+        } else if (v < 2 * (per_face[0] + per_face[1])) {   // h faces (voxels not on a d face)
+            v -= 2 * per_face[0];
+            h = v < per_face[1] ? 1 : H - 2;
+            v %= per_face[1];
+            d = (int)(v / W); w = (int)(v % W);
+            if (d == 1 || d == D - 2) continue;
+        } else {                                         // w faces (voxels on neither a d nor an h face)
+            v -= 2 * (per_face[0] + per_face[1]);
+            w = v < per_face[2] ? 1 : W - 2;
+            v %= per_face[2];
+            d = (int)(v / H); h = (int)(v % H);
+            if (d == 1 || d == D - 2 || h == 1 || h == H - 2) continue;
+        }
+        float gy[8];
+        T* cell = dyn + ((size_t)((d + 1) * PH + h + 1) * PW + w + 1) * C + c8 * 8;
+        load8<T>(cell, gy);
+        int dd[3], hh[3], ww[3], nd = 1, nh = 1, nw = 1;
+        dd[0] = d + 1; hh[0] = h + 1; ww[0] = w + 1;
+        if (d == 1) dd[nd++] = 0;
+        if (d == D - 2) dd[nd++] = D + 1;
+        if (h == 1) hh[nh++] = 0;
+        if (h == H - 2) hh[nh++] = H + 1;
+        if (w == 1) ww[nw++] = 0;
+        if (w == W - 2) ww[nw++] = W + 1;
+        for (int i0 = 0; i0 < nd; i0++)
+            for (int i1 = 0; i1 < nh; i1++)
+                for (int i2 = 0; i2 < nw; i2++) {
+                    if (i0 + i1 + i2 == 0) continue;
+                    float t[8];
+                    load8<T>(dyn + ((size_t)(dd[i0] * PH + hh[i1]) * PW + ww[i2]) * C + c8 * 8, t);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) gy[k] += t[k];
+                }
+        store8<T>(cell, gy);
+    }
+}
+
+// sums of g' = dy*act'(z) and g'*(x - mu) over the INTERIOR of an already folded padded gradient; x is walked linearly
+// (InstanceNorm -> ReLU -> ReflectionPadding3D, bf16, no dropout).  Same partial layout as in_bwd_partial_kernel.
+template <typename T>
+__global__ void __launch_bounds__(NT, 2) in_bwd_partial_folded_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g,
+                                                                   BwdArgs a, float* __restrict__ partial) {
+    extern __shared__ float sm[];
+    const int n = blockIdx.y, C = g.C, cg = C / 8;
+    const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
+    const int PD = g.D + 2, PH = g.H + 2, PW = g.W + 2;
+    const int V = g.D * g.H * g.W;
+    float mu[8], sc[8], sh[8], s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = c8 * 8 + k;
+        mu[k] = a.mean[n * C + c];
+        sc[k] = a.gamma[c] * a.rstd[n * C + c];
+        sh[k] = a.beta[c] - mu[k] * sc[k];
+        s1[k] = s2[k] = 0.f;
+    }
+    const T* xn = x + (size_t)n * V * C + c8 * 8;
+    const T* dyn = dy + (size_t)n * PD * PH * PW * C + c8 * 8;
+    const int S = gridDim.x * nvl;
+    VoxIter it;
+    it.init(blockIdx.x * nvl + vl, S, g.H, g.W);
+    for (int v = blockIdx.x * nvl + vl; v < V; v += U * S) {
+        Raw<T> rx[U], rg[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (v + u * S < V) {
+                load_raw<T>(xn + (size_t)(v + u * S) * C, rx[u]);
+                load_raw<T>(dyn + (size_t)(((it.pd + 1) * PH + it.ph + 1) * PW + it.pw + 1) * C, rg[u]);
+            }
+            it.next();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (v + u * S < V) {
+                float f[8], gy[8];
+                unpack_raw(rx[u], f);
+                unpack_raw(rg[u], gy);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    float gg = fmaf(f[k], sc[k], sh[k]) > 0.f ? gy[k] : 0.f;
+                    s1[k] += gg;
+                    s2[k] = fmaf(gg, f[k] - mu[k], s2[k]);
+                }
+            }
+    }
+    float* row = sm + ((size_t)vl * C + c8 * 8) * 2;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        row[2 * k] = s1[k];
+        row[2 * k + 1] = s2[k] * a.rstd[n * C + c8 * 8 + k];
+    }
+    __syncthreads();
+    float* out = partial + ((size_t)n * gridDim.x + blockIdx.x) * C * 2;
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+        float acc = 0.f;
+        for (int l = 0; l < nvl; l++) acc += sm[(size_t)l * C * 2 + i];
+        out[i] = acc;
     }
 }
 
@@ -796,7 +920,7 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
     VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT && d->pad_lo >= 0 && d->pad_hi >= 0);
     if (d->pad_mode == VG_PAD_REFLECT && (d->pad_lo || d->pad_hi))
         VG_REQUIRE(d->pad_lo == 1 && d->pad_hi == 1 && d->D >= 2 && d->H >= 2 && d->W >= 2);
-    const int dtype = d->dtype & ~(VG_IN_RELU_INPUT | VG_IN_BATCH_STATS);
+    const int dtype = d->dtype & ~(VG_IN_RELU_INPUT | VG_IN_BATCH_STATS | VG_IN_DY_SCRATCH);
     Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode, (d->dtype & VG_IN_RELU_INPUT) ? 1 : 0};
     ApplyArgs a{mean, rstd, gamma, beta, drop, noise, d->slope, d->noise_std, d->act, d->seed, d->seed_dev};
     const int pp = d->pad_lo + d->pad_hi;
@@ -832,7 +956,7 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
     VG_REQUIRE(d && dy && x && mean && rstd && gamma && beta && dx && ws);
     VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT);
-    const int dtype = d->dtype & ~(VG_IN_RELU_INPUT | VG_IN_BATCH_STATS);
+    const int dtype = d->dtype & ~(VG_IN_RELU_INPUT | VG_IN_BATCH_STATS | VG_IN_DY_SCRATCH);
     const int batch = (d->dtype & VG_IN_BATCH_STATS) ? 1 : 0;
     Geo g{d->N, d->D, d->H, d->W, d->C, d->pad_lo, d->pad_hi, d->pad_mode, (d->dtype & VG_IN_RELU_INPUT) ? 1 : 0};
     BwdArgs a{mean, rstd, gamma, beta, drop, d->slope, d->act};
@@ -853,15 +977,29 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
         if (d->act == VG_ACT_RELU && d->pad_lo == 1 && d->pad_hi == 1 && d->pad_mode == VG_PAD_REFLECT && !dres) sp = 1;
         else if (d->act == VG_ACT_NONE && d->pad_lo == 0 && d->pad_hi == 0 && dres) sp = 2;
     }
-    if (sp == 1) {
+    static int fold_on = -1;   // VG_IN_FOLD=0: keep the fold inside the two passes (A/B testing)
+    if (fold_on < 0) {
+        const char* e = getenv("VG_IN_FOLD");
+        fold_on = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (sp == 1 && fold_on && (d->dtype & VG_IN_DY_SCRATCH) && d->D >= 4 && d->H >= 4 && d->W >= 4) {
+        // the caller lets dy be overwritten: fold its reflected halo into the interior once, then two linear passes
+        const long long faces = 2LL * ((long long)d->H * d->W + (long long)d->D * d->W + (long long)d->D * d->H) * (d->C / 8);
+        const int nblk2 = pick_grid((long long)d->D * d->H * d->W, d->N, d->C);
+        in_fold_inplace_kernel<bf16><<<dim3(vg_cdiv(faces, 256), d->N), 256, 0, st>>>((bf16*)const_cast<void*>(dy), g);
+        in_bwd_partial_folded_kernel<bf16><<<dim3(nblk2, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
+        in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk2, d->N, d->C, sums, dgamma, dbeta, batch);
+        in_bwd_apply_sp_kernel<bf16, 1, true><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
+        VG_LAUNCHED(4);
+    } else if (sp == 1) {
         in_bwd_partial_sp_kernel<bf16, 1><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta, batch);
-        in_bwd_apply_sp_kernel<bf16, 1><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
+        in_bwd_apply_sp_kernel<bf16, 1, false><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
         VG_LAUNCHED(3);
     } else if (sp == 2) {
         in_bwd_partial_sp_kernel<bf16, 2><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta, batch);
-        in_bwd_apply_sp_kernel<bf16, 2><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
+        in_bwd_apply_sp_kernel<bf16, 2, false><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
         VG_LAUNCHED(3);
     } else if (dtype == VG_BF16) {
         in_bwd_partial_kernel<bf16><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial); VG_LAUNCHED(1);

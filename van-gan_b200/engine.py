@@ -381,6 +381,9 @@ class InstanceNorm:
              self.gamma.w, self.beta.w, drop, noise, work=float(es * (nin * (2 if residual is not None else 1) + y.numel())))
         out = Var(y)
         ins = [x] + ([residual] if residual is not None else [])
+        # the incoming gradient is a tape temporary that dies with this node: the kernel may fold its reflected halo in place
+        desc_b = InDesc(n, d, h, w, c, dt | _lib.IN_DY_SCRATCH, act, slope, pad[0], pad[1], pad[2], noise_std if noise is None else 0.0, seed,
+                        seed_dev.data_ptr() if seed_dev is not None else None)
 
         def bwd(in_needs, p_needs):
             dy = out.grad
@@ -390,7 +393,7 @@ class InstanceNorm:
             need_res = residual is not None and in_needs[1]
             dres = torch.empty_like(x.data) if need_res else None
             ws2 = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
-            call("vg_instnorm_bwd", desc, dy, x.data, mean, rstd, self.gamma.w, self.beta.w, drop, dx, 1 if fuse else 0, dres,
+            call("vg_instnorm_bwd", desc_b, dy, x.data, mean, rstd, self.gamma.w, self.beta.w, drop, dx, 1 if fuse else 0, dres,
                  self.gamma.grad if p_needs else None, self.beta.grad if p_needs else None, ws2, ws_bytes,
                  work=float(es * (2 * (nin + y.numel()) + nin * (2 if need_res else 1))))
             if in_needs[0] and not fuse:
