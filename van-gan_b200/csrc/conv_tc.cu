@@ -562,8 +562,13 @@ bool vg_tc_s2dgrad_ok(int K, int stride, int Cin, int Cout) {
         const char* e = getenv("VG_TC_S2FUSED");
         on = (e && e[0] == '0') ? 0 : 1;
     }
-    // k4 layers with >= 64 channels keep the per-class d-march launches (N = 128 there already)
-    return on && stride == 2 && Cin % 16 == 0 && Cout % 16 == 0 && ((K == 3 && Cin <= 128) || (K == 4 && Cin <= 32));
+    // VG_TC_S2FUSED_K4MAX=32 restores the round-1 choice (k4 layers with >= 64 channels as per-class d-march launches)
+    static int k4max = -1;
+    if (k4max < 0) {
+        const char* e = getenv("VG_TC_S2FUSED_K4MAX");
+        k4max = e ? atoi(e) : 128;   // measured (8x66^3 / 8x34^3): 64->128 0.775 -> 0.489 ms, 128->256 0.747 -> 0.395 ms against per-class launches
+    }
+    return on && stride == 2 && Cin % 16 == 0 && Cout % 16 == 0 && ((K == 3 && Cin <= 128) || (K == 4 && Cin <= k4max));
 }
 size_t vg_tc_s2dgrad_elems(int Cin, int Cout) {
     const int ncols = 8 * Cin, nblk = (ncols + 127) / 128;

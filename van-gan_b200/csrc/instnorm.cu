@@ -745,6 +745,82 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_sp_kernel(const T* __restr
     }
 }
 
+// ------------------------------------------------------------------ forward fast path: interior pass + halo pass
+// InstanceNorm -> ReLU -> ReflectionPadding3D (conv_block, resunet_model.py:42-66), bf16.  The interior of the padded output is
+// written by a pass that walks x linearly (the access pattern of the un-padded variant); the reflected halo is then copied from
+// the interior cells it mirrors (6 faces, ~5 % of the tensor, mostly L2 hits).
+template <typename T>
+__global__ void __launch_bounds__(NT, 2) in_apply_interior_kernel(const T* __restrict__ x, T* __restrict__ y, Geo g, ApplyArgs a) {
+    const int n = blockIdx.y, cg = g.C / 8;
+    const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
+    const int PD = g.D + 2, PH = g.H + 2, PW = g.W + 2;
+    const int V = g.D * g.H * g.W;
+    float scale[8], shift[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = c8 * 8 + k, sc = n * g.C + c;
+        scale[k] = a.gamma[c] * a.rstd[sc];
+        shift[k] = a.beta[c] - a.mean[sc] * scale[k];
+    }
+    const T* xn = x + (size_t)n * V * g.C + c8 * 8;
+    T* yn = y + (size_t)n * PD * PH * PW * g.C + c8 * 8;
+    const int S = gridDim.x * nvl;
+    VoxIter it;
+    it.init(blockIdx.x * nvl + vl, S, g.H, g.W);
+    for (int v = blockIdx.x * nvl + vl; v < V; v += U * S) {
+        Raw<T> rx[U];
+        int dst[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            dst[u] = ((it.pd + 1) * PH + it.ph + 1) * PW + it.pw + 1;
+            if (v + u * S < V) load_raw<T>(xn + (size_t)(v + u * S) * g.C, rx[u]);
+            it.next();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (v + u * S >= V) continue;
+            float f[8], o[8];
+            unpack_raw(rx[u], f);
+#pragma unroll
+            for (int k = 0; k < 8; k++) o[k] = fmaxf(fmaf(f[k], scale[k], shift[k]), 0.f);
+            store8<T>(yn + (size_t)dst[u] * g.C, o);
+        }
+    }
+}
+
+// y[halo cell] = y[mirrored interior cell] for a tensor padded by 1 (REFLECT); one thread per (halo cell, 8-channel group)
+template <typename T>
+__global__ void __launch_bounds__(256) pad_halo_inplace_kernel(T* __restrict__ y, Geo g) {
+    const int C = g.C, cg = C / 8;
+    const int PD = g.D + 2, PH = g.H + 2, PW = g.W + 2;
+    const long long f0 = (long long)PH * PW, f1 = (long long)(PD - 2) * PW, f2 = (long long)(PD - 2) * (PH - 2);
+    const long long total = 2 * (f0 + f1 + f2) * cg;
+    T* yn = y + (size_t)blockIdx.y * PD * PH * PW * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cg);
+        long long v = i / cg;
+        int pd, ph, pw;
+        if (v < 2 * f0) {                          // pd faces (whole planes)
+            pd = v < f0 ? 0 : PD - 1;
+            v %= f0;
+            ph = (int)(v / PW); pw = (int)(v % PW);
+        } else if (v < 2 * (f0 + f1)) {            // ph faces, pd interior
+            v -= 2 * f0;
+            ph = v < f1 ? 0 : PH - 1;
+            v %= f1;
+            pd = 1 + (int)(v / PW); pw = (int)(v % PW);
+        } else {                                   // pw faces, pd and ph interior
+            v -= 2 * (f0 + f1);
+            pw = v < f2 ? 0 : PW - 1;
+            v %= f2;
+            pd = 1 + (int)(v / (PH - 2)); ph = 1 + (int)(v % (PH - 2));
+        }
+        const int d = reflect1(pd - 1, g.D), h = reflect1(ph - 1, g.H), w = reflect1(pw - 1, g.W);
+        const uint4 val = *reinterpret_cast<const uint4*>(yn + ((size_t)((d + 1) * PH + h + 1) * PW + w + 1) * C + c8 * 8);
+        *reinterpret_cast<uint4*>(yn + ((size_t)(pd * PH + ph) * PW + pw) * C + c8 * 8) = val;
+    }
+}
+
 // ------------------------------------------------------------------ reflect-pad fold as a pass of its own (fast path)
 // dy (padded by 1, REFLECT) is folded IN PLACE: every interior voxel of the padded tensor that has a coordinate in {1, S-2}
 // receives the halo positions that mirror onto it.  Halo cells are only read and shell cells only written, so there is no
@@ -934,7 +1010,18 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
         if (d->act == VG_ACT_RELU && d->pad_lo == 1 && d->pad_hi == 1 && d->pad_mode == VG_PAD_REFLECT && !residual) sp = 1;
         else if (d->act == VG_ACT_NONE && d->pad_lo == 0 && d->pad_hi == 0 && residual) sp = 2;
     }
-    if (sp == 1) {
+    static int fold_on = -1;   // VG_IN_FOLD=0: one pass over the padded output with mirrored reads (A/B testing)
+    if (fold_on < 0) {
+        const char* e = getenv("VG_IN_FOLD");
+        fold_on = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (sp == 1 && fold_on && d->D >= 2 && d->H >= 2 && d->W >= 2) {
+        const long long V = (long long)d->D * d->H * d->W;
+        const long long halo = 2LL * ((long long)(d->H + 2) * (d->W + 2) + (long long)d->D * (d->W + 2) + (long long)d->D * d->H) * (d->C / 8);
+        in_apply_interior_kernel<bf16><<<dim3(pick_grid(V, d->N, d->C), d->N), nthr, 0, st>>>((const bf16*)x, (bf16*)y, g, a);
+        pad_halo_inplace_kernel<bf16><<<dim3(vg_cdiv(halo, 256), d->N), 256, 0, st>>>((bf16*)y, g);
+        VG_LAUNCHED(2);
+    } else if (sp == 1) {
         in_apply_sp_kernel<bf16, 1><<<grid, nthr, 0, st>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, g, a); VG_LAUNCHED(1);
     } else if (sp == 2) {
         in_apply_sp_kernel<bf16, 2><<<grid, nthr, 0, st>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, g, a); VG_LAUNCHED(1);
@@ -982,7 +1069,16 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
         const char* e = getenv("VG_IN_FOLD");
         fold_on = (e && e[0] == '0') ? 0 : 1;
     }
-    if (sp == 1 && fold_on && (d->dtype & VG_IN_DY_SCRATCH) && d->D >= 4 && d->H >= 4 && d->W >= 4) {
+    const bool can_fold = fold_on && (d->dtype & VG_IN_DY_SCRATCH) && dtype == VG_BF16 && d->pad_mode == VG_PAD_REFLECT && d->pad_lo == 1 &&
+                          d->pad_hi == 1 && d->D >= 4 && d->H >= 4 && d->W >= 4;
+    if (sp != 1 && can_fold) {
+        // generic options (LeakyReLU / dropout / residual gradient: the discriminator's norms): fold once, then the generic passes
+        // treat the halo as zero padding (no mirrored reads, no shell branch)
+        const long long faces = 2LL * ((long long)d->H * d->W + (long long)d->D * d->W + (long long)d->D * d->H) * (d->C / 8);
+        in_fold_inplace_kernel<bf16><<<dim3(vg_cdiv(faces, 256), d->N), 256, 0, st>>>((bf16*)const_cast<void*>(dy), g); VG_LAUNCHED(1);
+        g.pad_mode = VG_PAD_ZERO;
+    }
+    if (sp == 1 && can_fold) {
         // the caller lets dy be overwritten: fold its reflected halo into the interior once, then two linear passes
         const long long faces = 2LL * ((long long)d->H * d->W + (long long)d->D * d->W + (long long)d->D * d->H) * (d->C / 8);
         const int nblk2 = pick_grid((long long)d->D * d->H * d->W, d->N, d->C);
