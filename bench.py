@@ -277,8 +277,11 @@ def run_gpu(args):
         launch_mode = ("CUDA graph replay: one graph (losses, four backward sweeps, clip+Adam, operand repack)" if world == 1 else
                        ("CUDA graph replay: one graph with the bucketed NCCL all-reduces (vg_comm) captured on the communication stream"
                         if gan._graph["mode"] == "single" else
-                        "CUDA graph replay: one graph per backward sweep + one for clip+Adam; each network's bucketed NCCL all-reduce "
-                        "(vg_comm) is enqueued on the communication stream between the replays and overlaps the next sweep"))
+                        "CUDA graph replay: three graphs (forward + generator sweeps / discriminator sweeps / clip+Adam); the bucketed NCCL "
+                        "all-reduces (vg_comm) are enqueued on the communication stream between the replays, the generators' overlapping the "
+                        "discriminator sweeps"))
+        if gan.use_streams:
+            launch_mode += "; the two generator chains of the forward pass and the backward sweeps run on side streams"
     comm_msgs = int(strategy._L.vg_comm_collectives(strategy.comm)) if strategy.comm is not None else 0
     if graph_on:                   # replays do not pass through the host-side launch counter: count what the graph holds
         launches = gan.launches_per_replay * args.steps

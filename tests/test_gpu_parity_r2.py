@@ -305,8 +305,9 @@ def _fresh_gan(S, b, use_graph, seed=77):
 
 @pytest.mark.parametrize("split", [False, True])
 def test_graph_replay_equals_eager(cuda, split, monkeypatch):
-    """split=True: one graph per backward sweep + one for clip+Adam -- the capture layout of the multi-GPU step, where each network's
-    gradient all-reduce is enqueued between the replays (VG_GRAPH_SPLIT=1 selects it on one GPU).
+    """split=True: the capture layout of the multi-GPU step -- forward + generator sweeps / discriminator sweeps / clip+Adam as three
+    graphs with the gradient all-reduces enqueued between the replays (VG_GRAPH_SPLIT=1 selects it on one GPU).  Both layouts run the
+    two generator chains of the forward pass and the backward sweeps on side streams; the eager reference run does too.
     bench.py times CUDA-graph replay with in-kernel Philox noise / dropout and the device-resident Adam step size; the parity
     tests above run eager launches.  From the SAME state (weights, Adam slots, step counters -> same noise keys) one replayed step
     and one eagerly launched step must give the same ten losses, the same four gradient buffers and the same updated weights.
@@ -322,7 +323,7 @@ def test_graph_replay_equals_eager(cuda, split, monkeypatch):
     for I, Sg in batches[:3]:
         gan.train_step(I.cuda(), Sg.cuda())
     assert gan._graph is not None and gan.launches_per_replay > 100, "the graph path did not engage"
-    assert gan._graph["mode"] == ("per-sweep" if split else "single") and len(gan._graph["graphs"]) == (5 if split else 1)
+    assert gan._graph["mode"] == ("per-sweep" if split else "single") and len(gan._graph["graphs"]) == (3 if split else 1)
     snap = {k: (net.w.clone(), net.m.clone(), net.v.clone(), net.step_count) for k, net in gan.networks.items()}
     step0 = gan.step
 

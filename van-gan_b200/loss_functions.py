@@ -22,7 +22,6 @@ class LossContext:
         self.used = 0
         self.host = None
         self._norm = {}
-        self.enc_ws = torch.empty(64, dtype=torch.int32, device=E.DEV)
 
     def slot(self, n=1):
         s = self.used
@@ -47,9 +46,8 @@ class LossContext:
             n = x.shape[0]
             v = x.numel() // n
             mm = torch.empty(2 * n, dtype=torch.float32, device=E.DEV)
-            if self.enc_ws.numel() < 2 * n:
-                self.enc_ws = torch.empty(2 * n, dtype=torch.int32, device=E.DEV)
-            call("vg_minmax", x, n, v, mm, self.enc_ws)
+            enc_ws = torch.empty(max(2 * n, 64), dtype=torch.int32, device=E.DEV)   # per call: normalisations may run on different streams
+            call("vg_minmax", x, n, v, mm, enc_ws)
             nrm = torch.empty_like(x)
             call("vg_minmax_normalize", x, mm, nrm, n, v)
             self._norm[key] = (nrm, mm)

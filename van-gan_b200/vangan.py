@@ -109,6 +109,11 @@ class VanGan:
         self._h_seed = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._h_lr = torch.zeros(4, dtype=torch.float32).pin_memory()
         self.seed = seed
+        # independent branches of the step (the two generator chains of the forward pass, the four backward sweeps) are enqueued on
+        # side streams forked from / joined to the caller's stream by events, so small kernels of one branch fill the SMs another
+        # leaves idle (per-GPU batch 1 on 8 GPUs); VG_STREAMS=0 keeps everything on one stream
+        self.use_streams = os.environ.get("VG_STREAMS", "1") != "0"
+        self._side = [torch.cuda.Stream() for _ in range(4)] if self.use_streams else None
         # CUDA graph of one full train step (captured on the third eligible call; VG_GRAPH=0 disables)
         self.use_graph = os.environ.get("VG_GRAPH", "1") != "0" and not isinstance(self.gen_IS, VNetModel) and not isinstance(self.gen_SI, VNetModel)
         self._graph = None
@@ -145,24 +150,44 @@ class VanGan:
         self.tape = tape
         self.loss_ctx = LossContext()
         real_I, real_S = self._as_var(real_I), self._as_var(real_S)
-        fake_S = self._gen(self.gen_IS, tape, real_I, training, 0)
-        fake_I = self._gen(self.gen_SI, tape, real_S, training, 1)
-        cycled_S = self._gen(self.gen_IS, tape, fake_I, training, 2)
-        cycle_loss_I = self.cycle_loss_fn(self, real_S, cycled_S, typ="bce")
-        seg_loss = self.seg_loss_fn(self, real_S, cycled_S, iters=self.cldice_iters)
-        cycled_I = self._gen(self.gen_SI, tape, fake_S, training, 3)
-        cycle_loss_S = self.cycle_loss_fn(self, real_I, cycled_I, typ='mse')
-        reconstruction_loss = self.reconstruction_loss(self, real_I, cycled_I)
-
-        disc_real_S = self._disc(self.disc_S, tape, real_S, training, rand, "S_real", 0)
-        disc_fake_S = self._disc(self.disc_S, tape, fake_S, training, rand, "S_fake", 1)
-        disc_real_I = self._disc(self.disc_I, tape, real_I, training, rand, "I_real", 2)
-        disc_fake_I = self._disc(self.disc_I, tape, fake_I, training, rand, "I_fake", 3)
-
-        gen_IS_loss = self.generator_loss_fn(self, disc_fake_S, from_logits=True)
-        gen_SI_loss = self.generator_loss_fn(self, disc_fake_I, from_logits=True)
-        disc_I_loss = self.discriminator_loss_fn(self, disc_real_I, disc_fake_I, from_logits=True)
-        disc_S_loss = self.discriminator_loss_fn(self, disc_real_S, disc_fake_S, from_logits=True)
+        # Four chains on side streams: A = gen_IS applications + the S-cycle losses, B = gen_SI applications + the I-cycle losses,
+        # C = disc_S (real, then fake), D = disc_I.  They meet only where one consumes another's generated volume.
+        main = torch.cuda.current_stream()
+        par = self._side is not None and rand is None
+        sA, sB, sC, sD = self._side if par else (main, main, main, main)
+        if par:
+            self._fork(main, self._side)
+        with torch.cuda.stream(sA):
+            fake_S = self._gen(self.gen_IS, tape, real_I, training, 0)
+        with torch.cuda.stream(sB):
+            fake_I = self._gen(self.gen_SI, tape, real_S, training, 1)
+        with torch.cuda.stream(sC):
+            disc_real_S = self._disc(self.disc_S, tape, real_S, training, rand, "S_real", 0)
+        with torch.cuda.stream(sD):
+            disc_real_I = self._disc(self.disc_I, tape, real_I, training, rand, "I_real", 2)
+        if par:
+            eA, eB = torch.cuda.Event(), torch.cuda.Event()
+            eA.record(sA); eB.record(sB)
+            sA.wait_event(eB); sB.wait_event(eA)      # cycled_S needs fake_I, cycled_I needs fake_S
+            sC.wait_event(eA); sD.wait_event(eB)      # disc_S(fake_S), disc_I(fake_I)
+        with torch.cuda.stream(sA):
+            cycled_S = self._gen(self.gen_IS, tape, fake_I, training, 2)
+            cycle_loss_I = self.cycle_loss_fn(self, real_S, cycled_S, typ="bce")
+            seg_loss = self.seg_loss_fn(self, real_S, cycled_S, iters=self.cldice_iters)
+        with torch.cuda.stream(sB):
+            cycled_I = self._gen(self.gen_SI, tape, fake_S, training, 3)
+            cycle_loss_S = self.cycle_loss_fn(self, real_I, cycled_I, typ='mse')
+            reconstruction_loss = self.reconstruction_loss(self, real_I, cycled_I)
+        with torch.cuda.stream(sC):
+            disc_fake_S = self._disc(self.disc_S, tape, fake_S, training, rand, "S_fake", 1)
+            gen_IS_loss = self.generator_loss_fn(self, disc_fake_S, from_logits=True)
+            disc_S_loss = self.discriminator_loss_fn(self, disc_real_S, disc_fake_S, from_logits=True)
+        with torch.cuda.stream(sD):
+            disc_fake_I = self._disc(self.disc_I, tape, fake_I, training, rand, "I_fake", 3)
+            gen_SI_loss = self.generator_loss_fn(self, disc_fake_I, from_logits=True)
+            disc_I_loss = self.discriminator_loss_fn(self, disc_real_I, disc_fake_I, from_logits=True)
+        if par:
+            self._join(main, self._side)
 
         total_loss_I = gen_IS_loss + cycle_loss_I + seg_loss
         total_loss_S = gen_SI_loss + cycle_loss_S + reconstruction_loss
@@ -174,6 +199,37 @@ class VanGan:
         self.last = dict(fake_S=fake_S, fake_I=fake_I, cycled_S=cycled_S, cycled_I=cycled_I, disc_real_S=disc_real_S,
                          disc_fake_S=disc_fake_S, disc_real_I=disc_real_I, disc_fake_I=disc_fake_I)
         return result, total_loss_I, total_loss_S, disc_I_loss, disc_S_loss, fake_I, fake_S
+
+    @staticmethod
+    def _fork(main, sides):
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for st in sides:
+            st.wait_event(ev)
+
+    @staticmethod
+    def _join(main, sides):
+        for st in sides:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+
+    def _sweeps(self, pairs, overlap_allreduce):
+        """Backward sweeps of `pairs` = [(net, loss), ...], one side stream each (they share only read-only activations and
+        weights; every sweep writes its own network's gradient buffer and its own temporaries).  Returns the all-reduce handles."""
+        main = torch.cuda.current_stream()
+        sides = self._side[:len(pairs)] if (self._side is not None and len(pairs) > 1) else None
+        handles = []
+        if sides is not None:
+            self._fork(main, sides)
+        for i, (net, loss) in enumerate(pairs):
+            with torch.cuda.stream(sides[i] if sides is not None else main):
+                self._sweep(net, loss)
+                # MirroredStrategy's gradient all-reduce: enqueued on the communication stream as soon as this sweep ends
+                handles.append(self.strategy.all_reduce_async(net.g) if overlap_allreduce else None)
+        if sides is not None:
+            self._join(main, sides)
+        return handles
 
     def _plan(self, total_I, total_S, dI, dS):
         return ((self.gen_IS, total_I), (self.gen_SI, total_S), (self.disc_I, dI), (self.disc_S, dS))
@@ -199,11 +255,7 @@ class VanGan:
         result = {}
         result, total_I, total_S, dI, dS, _fI, _fS = self.compute_losses(real_I, real_S, result, training=True, rand=rand)
         plan = self._plan(total_I, total_S, dI, dS)
-        handles = []
-        for net, loss in plan:
-            self._sweep(net, loss)
-            # MirroredStrategy's gradient all-reduce: launched as soon as this network's sweep ends, overlapping the next sweep
-            handles.append(self.strategy.all_reduce_async(net.g) if overlap_allreduce else None)
+        handles = self._sweeps(plan, overlap_allreduce)
         return result, plan, handles
 
     def _body_adam(self):
@@ -270,10 +322,11 @@ class VanGan:
     def _capture(self, real_I, real_S):
         """The step as CUDA graphs.
         World 1: ONE graph -- losses, the four backward sweeps, clip+Adam, operand repack.
-        World > 1: one graph per backward sweep (the first also holds the forward pass and the losses) + one for clip+Adam.  Between
-        the replays each network's bucketed gradient all-reduce is enqueued on the communication stream (vg_comm, ordered by
-        events), so it runs while the NEXT sweep's graph executes; the Adam graph is ordered after the last message.  The replays
-        and the collectives are all asynchronous: the host enqueues the whole step without waiting.
+        World > 1: graph 1 = forward pass, losses and the two generator sweeps; graph 2 = the two discriminator sweeps; graph 3 =
+        clip+Adam.  Between the replays the bucketed gradient all-reduces of the networks just swept are enqueued on the
+        communication stream (vg_comm, ordered by events): the generators' messages run while the discriminator sweeps execute,
+        and the Adam graph is ordered after the last message.  Replays and collectives are all asynchronous: the host enqueues
+        the whole step without waiting.
         VG_GRAPH_COMM=1 captures the collectives INTO a single graph instead (measured: fine at 32^3, hangs at 4x128^3 per GPU on
         2 GPUs -- kept opt-in for investigation)."""
         from . import _lib
@@ -311,11 +364,10 @@ class VanGan:
                 res = {}
                 res, total_I, total_S, dI, dS, _fI, _fS = self.compute_losses(E.Var(gI), E.Var(gS), res, training=True, rand=None)
                 state["plan"] = self._plan(total_I, total_S, dI, dS)
-                self._sweep(*state["plan"][0])
+                self._sweeps(state["plan"][:2], False)          # both generator sweeps, side by side
                 return res
             result = capture(first)
-            for net, loss in state["plan"][1:]:
-                capture(lambda net=net, loss=loss: self._sweep(net, loss))
+            capture(lambda: self._sweeps(state["plan"][2:], False))   # both discriminator sweeps
             capture(self._body_adam)
             mode = "per-sweep"
         self.launches_per_replay = int(_lib.lib().vg_launch_count() - l0)
@@ -341,13 +393,13 @@ class VanGan:
             g["graphs"][0].replay()
         else:
             handles = []
-            for gr, net in zip(g["graphs"][:4], (self.gen_IS, self.gen_SI, self.disc_I, self.disc_S)):
+            for gr, nets in zip(g["graphs"][:2], ((self.gen_IS, self.gen_SI), (self.disc_I, self.disc_S))):
                 gr.replay()
-                handles.append(self.strategy.all_reduce_async(net.g))     # runs beside the next sweep's graph
+                handles += [self.strategy.all_reduce_async(net.g) for net in nets]     # run beside the next graph
             for h in handles:
                 if h is not None:
                     h.wait()
-            g["graphs"][4].replay()
+            g["graphs"][2].replay()
         g["ctx"].host = None
         return self._finish_step(g["result"], g["ctx"], True)
 
