@@ -50,9 +50,38 @@ def accumulate(var, g):
 
 
 class Tape:
+    KEEP_BYTES = 2 << 30     # weight-gradient stream: join once this many bytes of incoming gradients are being held for it
+
     def __init__(self, enabled=True):
         self.nodes = []
         self.enabled = enabled
+        self.wg_stream = None     # optional sibling stream of the current backward sweep for the weight-gradient kernels
+        self._keep, self._keep_bytes = [], 0
+
+    # A convolution's weight gradient and its input gradient both consume dy and nothing else of each other, so the weight-gradient
+    # kernel can run on a sibling stream beside the rest of the sweep.  dy is a tape temporary: it is kept referenced until the
+    # sweep stream has been ordered after the sibling again (only then may the allocator hand its memory to later kernels).
+    def side_call(self, hold, fn):
+        if self.wg_stream is None:
+            fn()
+            return
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.wg_stream.wait_event(ev)
+        with torch.cuda.stream(self.wg_stream):
+            fn()
+        self._keep.append(hold)
+        self._keep_bytes += sum(t.numel() * t.element_size() for t in hold)
+        if self._keep_bytes > self.KEEP_BYTES:
+            self.side_join()
+
+    def side_join(self):
+        if self.wg_stream is not None and self._keep:
+            ev = torch.cuda.Event()
+            ev.record(self.wg_stream)
+            torch.cuda.current_stream().wait_event(ev)
+        self._keep, self._keep_bytes = [], 0
 
     def record(self, inputs, outputs, params, bwd, name):
         if self.enabled:
@@ -98,6 +127,7 @@ class Tape:
             node.bwd(in_needs, p_needs)
             for o in outs:
                 o.grad = None
+        self.side_join()
         # inputs that are leaves keep their grads; clear everything else that may linger
         for node in self.nodes:
             for v in node.inputs:
@@ -340,7 +370,8 @@ class Conv3D:
                 call("vg_tanh_bwd", dy, out.data, t, dy.numel())
                 dy = t
             if p_needs:
-                call("vg_conv3d_wgrad", desc, x.data, dy, self.w.grad, self.b.grad if self.b else None, work=flops)
+                tape.side_call((dy,), lambda: call("vg_conv3d_wgrad", desc, x.data, dy, self.w.grad, self.b.grad if self.b else None,
+                                                   work=flops))
             if in_needs[0]:
                 dx = torch.empty_like(x.data)
                 call("vg_conv3d_dgrad", desc, dy, self.w.w if self.cout == 1 else self.wd, dx, work=flops)

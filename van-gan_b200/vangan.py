@@ -114,6 +114,8 @@ class VanGan:
         # leaves idle (per-GPU batch 1 on 8 GPUs); VG_STREAMS=0 keeps everything on one stream
         self.use_streams = os.environ.get("VG_STREAMS", "1") != "0"
         self._side = [torch.cuda.Stream() for _ in range(4)] if self.use_streams else None
+        # one more stream per sweep for the weight-gradient kernels (VG_WG_STREAM=0 disables)
+        self._wg_side = [torch.cuda.Stream() for _ in range(4)] if (self.use_streams and os.environ.get("VG_WG_STREAM", "1") != "0") else None
         # CUDA graph of one full train step (captured on the third eligible call; VG_GRAPH=0 disables)
         self.use_graph = os.environ.get("VG_GRAPH", "1") != "0" and not isinstance(self.gen_IS, VNetModel) and not isinstance(self.gen_SI, VNetModel)
         self._graph = None
@@ -224,7 +226,9 @@ class VanGan:
             self._fork(main, sides)
         for i, (net, loss) in enumerate(pairs):
             with torch.cuda.stream(sides[i] if sides is not None else main):
+                self.tape.wg_stream = self._wg_side[i] if self._wg_side is not None else None
                 self._sweep(net, loss)
+                self.tape.wg_stream = None
                 # MirroredStrategy's gradient all-reduce: enqueued on the communication stream as soon as this sweep ends
                 handles.append(self.strategy.all_reduce_async(net.g) if overlap_allreduce else None)
         if sides is not None:
