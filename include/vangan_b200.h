@@ -254,6 +254,10 @@ int vg_comm_destroy(vg_comm* c);
  * ------------------------------------------------------------------------------------------- */
 /* win[B,kH,kW,kD] = windows of vol[H,W,D] at starts[B][3] */
 int vg_stitch_gather(const float* vol, int H, int W, int D, float* win, const int* starts, int B, int kH, int kW, int kD, void* stream);
+/* the same from the UN-padded volume [H0,W0,D0] when the reference pads first (np.pad 'symmetric' by xs/ys/zs, custom_callback.py:82-104):
+ * starts are coordinates in the padded volume, every coordinate p reads sym(p - pad); vol holds the rows [row0, ...) of the volume */
+int vg_stitch_gather_sym(const float* vol, int row0, int H0, int W0, int D0, int xs, int ys, int zs, float* win, const int* starts, int B,
+                         int kH, int kW, int kD, void* stream);
 int vg_stitch_accumulate(float* pred, float* cnt, int H, int W, int D, const float* win, const int* starts, int B, int kH,
                          int kW, int kD, int pH, int pW, int pD, void* stream);
 /* out[oh,ow,od] = 255 * minmax_norm( (pred/cnt)[crop] ): two calls — divide+minmax, then scale */

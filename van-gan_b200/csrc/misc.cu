@@ -247,6 +247,22 @@ __global__ void __launch_bounds__(NT) stitch_gather_kernel(const float* __restri
     }
 }
 
+// the same extraction from the UN-padded volume when the reference first pads it with np.pad(..., 'symmetric') (custom_callback.py:82-104):
+// a padded coordinate p maps to sym(p - pad), sym(i) = -i-1 below 0 and 2n-1-i at or above n (pad < n), so the padded copy never exists
+__device__ __forceinline__ int sym_idx(int i, int n) { return i < 0 ? -i - 1 : (i >= n ? 2 * n - 1 - i : i); }
+__global__ void __launch_bounds__(NT) stitch_gather_sym_kernel(const float* __restrict__ vol, int row0, int H0, int W0, int D0, int xs, int ys, int zs,
+                                                               float* __restrict__ win, const int* __restrict__ starts, int B, int kH, int kW,
+                                                               int kD) {
+    size_t per = (size_t)kH * kW * kD, total = per * B;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        int b = (int)(i / per);
+        size_t r = i % per;
+        int z = (int)(r % kD), y = (int)((r / kD) % kW), x = (int)(r / ((size_t)kD * kW));
+        const int sx = sym_idx(starts[3 * b] + x - xs, H0), sy = sym_idx(starts[3 * b + 1] + y - ys, W0), sz = sym_idx(starts[3 * b + 2] + z - zs, D0);
+        win[i] = vol[((size_t)(sx - row0) * W0 + sy) * D0 + sz];
+    }
+}
+
 __device__ __forceinline__ uint32_t enc_f(float f) {
     uint32_t b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -452,6 +468,15 @@ int vg_stitch_gather(const float* vol, int H, int W, int D, float* win, const in
     VG_REQUIRE(vol && win && starts && B > 0);
     stitch_gather_kernel<<<vg_grid_for((size_t)B * kH * kW * kD, NT, 16), NT, 0, (cudaStream_t)stream>>>(vol, H, W, D, win, starts, B, kH,
                                                                                                    kW, kD); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_stitch_gather_sym(const float* vol, int row0, int H0, int W0, int D0, int xs, int ys, int zs, float* win, const int* starts, int B,
+                         int kH, int kW, int kD, void* stream) {
+    VG_REQUIRE(vol && win && starts && B > 0 && row0 >= 0 && xs >= 0 && ys >= 0 && zs >= 0 && xs < H0 && ys < W0 && zs < D0);
+    stitch_gather_sym_kernel<<<vg_grid_for((size_t)B * kH * kW * kD, NT, 16), NT, 0, (cudaStream_t)stream>>>(vol, row0, H0, W0, D0, xs, ys, zs, win,
+                                                                                                       starts, B, kH, kW, kD); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }

@@ -210,14 +210,14 @@ class GanMonitor:
         oshape = img.shape
         xs = ys = zs = 0
         if complete:                                                    # custom_callback.py:82-104
+            # np.pad(img, ..., "symmetric") is never materialised: the windows are extracted from the un-padded volume with the
+            # symmetric index map (vg_stitch_gather_sym); H, W, D below are the PADDED extents the enumeration runs over
             xs, ys = int(padFactor * img.shape[0]), int(padFactor * img.shape[1])
-            if stride[2] == 1:
-                img = np.pad(img, ((xs, xs), (ys, ys), (0, 0), (0, 0)), "symmetric")
-            else:
+            if stride[2] != 1:
                 zs = int(padFactor * img.shape[2])
-                img = np.pad(img, ((xs, xs), (ys, ys), (zs, zs), (0, 0)), "symmetric")
-        H, W, D, Cc = img.shape
-        assert Cc == 1
+        H0, W0, D0 = img.shape[0], img.shape[1], img.shape[2]
+        assert img.shape[3] == 1
+        H, W, D, Cc = H0 + 2 * xs, W0 + 2 * ys, D0 + 2 * zs, 1
         kH, kW, kD = subvol_size[1], subvol_size[2], subvol_size[3]
         if not complete or not border_removal:
             pH = pW = pD = 0
@@ -241,7 +241,32 @@ class GanMonitor:
         mark("host prep")
         if mine:
             lo, hi = min(st[0] for st in mine), max(st[0] for st in mine) + kH
-            vol = torch.from_numpy(np.ascontiguousarray(img[lo:hi, :, :, 0])).to(E.DEV)     # only the rows this rank's windows read
+            # only the rows this rank's windows read, uploaded in chunks on a copy stream while earlier windows run: a window batch
+            # waits (event) for the last row it reads.  Padded (complete=True): rows of the un-padded volume, mapped symmetrically.
+            sym = lambda p: -p - 1 if p < 0 else (2 * H0 - 1 - p if p >= H0 else p)
+            if xs:
+                src_rows = [sym(p - xs) for p in range(lo, hi)]
+                lo0, hi0 = min(src_rows), max(src_rows) + 1
+            else:
+                lo0, hi0 = lo, hi
+            src = torch.from_numpy(np.ascontiguousarray(img[lo0:hi0, :, :, 0]))
+            vol = torch.empty((hi0 - lo0, W0, D0), dtype=torch.float32, device=E.DEV)
+            copy_stream = self._copy_stream()
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            up = {"rows": 0}
+
+            def need_rows(p_hi):
+                """enqueue the upload of every source row that padded rows [lo, p_hi) read and order the compute stream after it"""
+                n = (max(sym(p - xs) for p in range(lo, min(p_hi, hi))) + 1 - lo0) if xs else (min(p_hi, hi) - lo)
+                if n <= up["rows"]:
+                    return
+                with torch.cuda.stream(copy_stream):
+                    vol[up["rows"]:n].copy_(src[up["rows"]:n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                torch.cuda.current_stream().wait_event(ev)
+                up["rows"] = n
+            need_rows(lo + kH)
             mark("upload")
             B = min(self.window_batch, len(mine))
             fwd = None
@@ -255,13 +280,22 @@ class GanMonitor:
             mark("graph capture")
             for i in range(0, len(mine), B):
                 chunk = mine[i:i + B]
-                st = torch.tensor([(a - lo, b_, c) for a, b_, c in chunk], dtype=torch.int32, device=E.DEV).reshape(-1)
+                need_rows(max(a for a, _b, _c in chunk) + kH)
+                padded = bool(xs or ys or zs)
+                # un-padded: starts relative to the uploaded rows; padded: starts in padded coordinates (the kernel maps them)
+                st = torch.tensor([((a if padded else a - lo), b_, c) for a, b_, c in chunk], dtype=torch.int32, device=E.DEV).reshape(-1)
+
+                def gather(dst, nb):
+                    if padded:
+                        call("vg_stitch_gather_sym", vol, lo0, H0, W0, D0, xs, ys, zs, dst, st, nb, kH, kW, kD)
+                    else:
+                        call("vg_stitch_gather", vol, hi - lo, W, D, dst, st, nb, kH, kW, kD)
                 if fwd is not None and len(chunk) == B:
-                    call("vg_stitch_gather", vol, hi - lo, W, D, fwd.x, st, B, kH, kW, kD)
+                    gather(fwd.x, B)
                     out = fwd.replay()
                 else:
                     win = torch.empty((len(chunk), kH, kW, kD, 1), dtype=torch.float32, device=E.DEV)
-                    call("vg_stitch_gather", vol, hi - lo, W, D, win, st, len(chunk), kH, kW, kD)
+                    gather(win, len(chunk))
                     if hook is not None:                               # custom_callback.py:171-172, once per window
                         win = _apply_hook(hook, win, batched=False)
                     out = gen(win, training=False)
@@ -306,7 +340,7 @@ class GanMonitor:
         mark("finalize")
         if rank != 0:
             return None
-        res = res_d.cpu().numpy()[..., None]
+        res = self._download(res_d)[..., None]
         mark("download")
         if prof:
             self.last_stats["phases_ms"] = {b[0]: round((b[1] - a[1]) * 1e3, 2) for a, b in zip(marks[:-1], marks[1:])}
@@ -314,6 +348,36 @@ class GanMonitor:
         if output_path is not None and name is not None:
             np.save(os.path.join(output_path, "{name}.npy".format(name=name)), res)
         return res
+
+    def _copy_stream(self):
+        if getattr(self, "_cstream", None) is None:
+            self._cstream = torch.cuda.Stream()
+        return self._cstream
+
+    def _download(self, t):
+        """device -> fresh numpy array through a cached pinned staging buffer, in chunks: the D2H copy of chunk i+1 (full PCIe rate)
+        overlaps the host copy of chunk i into the result."""
+        t = t.contiguous()
+        out = np.empty(tuple(t.shape), dtype=np.uint8 if t.dtype == torch.uint8 else np.float32)
+        flat_d, flat_h = t.view(-1), torch.from_numpy(out).view(-1)
+        n, step = flat_d.numel(), (16 << 20) // t.element_size()
+        if getattr(self, "_stage", None) is None or self._stage[0].dtype != t.dtype:
+            self._stage = [torch.empty(step, dtype=t.dtype).pin_memory() for _ in range(2)]
+        evs = [None, None]
+        chunks = list(range(0, n, step))
+        for k, off in enumerate(chunks + [None]):
+            if off is not None:
+                b = k & 1
+                m = min(step, n - off)
+                self._stage[b][:m].copy_(flat_d[off:off + m], non_blocking=True)
+                evs[b] = torch.cuda.Event()
+                evs[b].record()
+            if k >= 1:
+                pb, poff = (k - 1) & 1, chunks[k - 1]
+                pm = min(step, n - poff)
+                evs[pb].synchronize()
+                flat_h[poff:poff + pm].copy_(self._stage[pb][:pm])
+        return out
 
     def run_mapping(self, model, test_set, sub_img_size=(64, 64, 512, 1), segmentation=True, stride=(25, 25, 1),
                     padFactor=0.25, filetext=None, filepath=''):
