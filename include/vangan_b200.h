@@ -249,6 +249,15 @@ int vg_comm_reduce_scalars(vg_comm* c, double* vals, int n, void* stream);
 int vg_comm_destroy(vg_comm* c);
 
 /* ---------------------------------------------------------------------------------------------
+ * On-device input pipeline (dataset.py:205-251: tf.image.random_crop + random_spatial_augmentation; the random draws stay on the host).
+ * vol: [H,W,D] fp32 (a whole .npy volume, uploaded once); out: [kH,kW,kD] = rot90_k(flip_up_down(flip_left_right(crop at (x0,y0,z0)))),
+ * with tf.image's 4-D reading of a volume: left_right reverses D, up_down reverses W, rot90 turns the (W, D) plane counter-clockwise.
+ * The "retry until max >= 0.8" loop of process_seg_domain (dataset.py:226-246) tests the crop with vg_minmax.
+ * ------------------------------------------------------------------------------------------- */
+int vg_crop_augment(const float* vol, int H, int W, int D, float* out, int kH, int kW, int kD, int x0, int y0, int z0, int flip_lr,
+                    int flip_ud, int rot_k, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Sliding-window stitching (custom_callback.py:123,165-166,177-183,192,202).
  * pred/cnt: [H,W,D] fp32 volumes; win: [B,kH,kW,kD] generator outputs; starts: [B][3] window origins.
  * ------------------------------------------------------------------------------------------- */

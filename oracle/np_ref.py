@@ -110,3 +110,16 @@ def stitch_subvolumes(gen, img, subvol_size, stride=(25, 25, 128), complete=Fals
     if not complete:
         pred = pred.astype("uint8")
     return pred
+
+
+def crop_augment(vol, origin, size, flip_lr=False, flip_ud=False, rot_k=0):
+    """dataset.py:205-230 on a (H, W, D) volume: tf.image.random_crop at `origin`, then random_spatial_augmentation.  tf.image reads
+    the 4-D volume tensor (H, W, D, 1) as [batch, height, width, channels]: flip_left_right reverses axis 2 (D), flip_up_down axis 1
+    (W), rot90(k) turns the (W, D) plane k quarter turns counter-clockwise."""
+    x0, y0, z0 = origin
+    a = vol[x0:x0 + size[0], y0:y0 + size[1], z0:z0 + size[2]]
+    if flip_lr:
+        a = a[:, :, ::-1]
+    if flip_ud:
+        a = a[:, ::-1, :]
+    return np.ascontiguousarray(np.rot90(a, rot_k, axes=(1, 2)))

@@ -103,6 +103,7 @@ SIGNATURES = {
     "vg_clip_adam_step": (_I, [_P, _P, _P, _P, _P, _I, _LL, _F, _F, _F, _F, _F, _P, _P]),
     "vg_clip_adam_step_dev": (_I, [_P, _P, _P, _P, _P, _I, _LL, _P, _F, _F, _F, _F, _P, _P]),
     "vg_stitch_gather": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "vg_crop_augment": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_stitch_gather_sym": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     "vg_stitch_accumulate": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_stitch_finalize": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

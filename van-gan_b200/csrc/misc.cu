@@ -263,6 +263,29 @@ __global__ void __launch_bounds__(NT) stitch_gather_sym_kernel(const float* __re
     }
 }
 
+// On-device input pipeline (dataset.py:205-251): tf.image.random_crop + random_spatial_augmentation on a (H, W, D, 1) volume.  The
+// tf.image ops see a 4-D tensor as [batch, height, width, channels], so on a volume flip_left_right reverses axis 2 (D),
+// flip_up_down reverses axis 1 (W) and rot90(k) turns the (W, D) plane k quarter turns counter-clockwise (np.rot90(axes=(1, 2))).
+// out[x][y][z] = rot90_k( flip_ud( flip_lr( vol[x0 + x][y0 + .][z0 + .] ) ) ); odd k needs kW == kD.
+__global__ void __launch_bounds__(NT) crop_augment_kernel(const float* __restrict__ vol, int H, int W, int D, float* __restrict__ out, int kH,
+                                                          int kW, int kD, int x0, int y0, int z0, int flip_lr, int flip_ud, int rot_k) {
+    const size_t total = (size_t)kH * kW * kD;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        const int z = (int)(i % kD), y = (int)((i / kD) % kW), x = (int)(i / ((size_t)kD * kW));
+        // invert the rotation: element (y, z) of rot90^k(m) comes from m at ...
+        int sy, sz;
+        switch (rot_k & 3) {
+            case 0: sy = y; sz = z; break;
+            case 1: sy = z; sz = kD - 1 - y; break;            // rot90(m)[y][z] = m[z][n-1-y]
+            case 2: sy = kW - 1 - y; sz = kD - 1 - z; break;
+            default: sy = kW - 1 - z; sz = y; break;           // rot90^3(m)[y][z] = m[n-1-z][y]
+        }
+        if (flip_ud) sy = kW - 1 - sy;
+        if (flip_lr) sz = kD - 1 - sz;
+        out[i] = vol[((size_t)(x0 + x) * W + y0 + sy) * D + z0 + sz];
+    }
+}
+
 __device__ __forceinline__ uint32_t enc_f(float f) {
     uint32_t b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -468,6 +491,16 @@ int vg_stitch_gather(const float* vol, int H, int W, int D, float* win, const in
     VG_REQUIRE(vol && win && starts && B > 0);
     stitch_gather_kernel<<<vg_grid_for((size_t)B * kH * kW * kD, NT, 16), NT, 0, (cudaStream_t)stream>>>(vol, H, W, D, win, starts, B, kH,
                                                                                                    kW, kD); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_crop_augment(const float* vol, int H, int W, int D, float* out, int kH, int kW, int kD, int x0, int y0, int z0, int flip_lr,
+                    int flip_ud, int rot_k, void* stream) {
+    VG_REQUIRE(vol && out && kH > 0 && kW > 0 && kD > 0 && x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + kH <= H && y0 + kW <= W && z0 + kD <= D);
+    VG_REQUIRE(!(rot_k & 1) || kW == kD);
+    crop_augment_kernel<<<vg_grid_for((size_t)kH * kW * kD, NT, 16), NT, 0, (cudaStream_t)stream>>>(vol, H, W, D, out, kH, kW, kD, x0, y0, z0,
+                                                                                              flip_lr, flip_ud, rot_k); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }
