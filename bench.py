@@ -352,10 +352,10 @@ def run_gpu(args):
     roofline = {"kernel": "tc_conv_kernel (tcgen05/TMEM implicit-GEMM Conv3D: stride-1/2 forward + all dgrads)", "bound": "tensor",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": (achieved / tf_peak) if achieved else None,
                 # one `ncu --set full` capture of this kernel (d-march, BD=8) on the 48->16 k3 layer at 8x128^3
-                # (profiles/r01_ncu_full_fwd_48-16_dmarch_call37.txt): dram read 1.6875 GB + write 0.5193 GB for that launch; its
+                # (profiles/r02_ncu_full_fwd_48-16_call23.txt): dram read 1.6875 GB + write 0.5174 GB for that launch; its
                 # algorithmic bytes (bf16 in + out) are 2.22e9
-                "traffic": 2.2068e9, "traffic_launch": "fwd 48->16 k3 s1, 8x130^3 -> 8x128^3",
-                "traffic_source": "ncu --set full capture of that one launch, profiles/r01_ncu_full_fwd_48-16_dmarch_call37.txt (not re-measured by this run)",
+                "traffic": 2.2049e9, "traffic_launch": "fwd 48->16 k3 s1, 8x130^3 -> 8x128^3",
+                "traffic_source": "ncu --set full capture of that one launch, profiles/r02_ncu_full_fwd_48-16_call23.txt (not re-measured by this run)",
                 "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peak_src,
                 "calls_per_step": tc_calls / psteps, "share_of_step": tc_ms / psteps / ms_ref if ms_ref > 0 else None,
                 "conv_family_share_of_step": conv_ms / psteps / ms_ref if ms_ref > 0 else None,
