@@ -289,14 +289,16 @@ def run_gpu(args):
     ms_e2e = timed(step_e2e, args.steps)
     # per-kernel-family device times: a separate EAGER pass (CUDA events around every ABI call cannot be recorded inside a
     # graph replay); same inputs, same kernels, same launch order
-    saved = (gan._graph, gan.use_graph)
-    gan._graph, gan.use_graph = None, False
+    # ... and on ONE stream: with the branches of the step on side streams a kernel's event-to-event time would include the kernels
+    # of other branches that share the SMs with it
+    saved = (gan._graph, gan.use_graph, gan._side, gan._wg_side)
+    gan._graph, gan.use_graph, gan._side, gan._wg_side = None, False, None, None
     psteps = min(args.steps, 2)
     step_resident()
     prof = _lib.Profiler([], detail=True)   # keyed by (call, shape)
     ms_prof = timed(step_resident, psteps, prof)
     fam = prof.summary()
-    gan._graph, gan.use_graph = saved
+    gan._graph, gan.use_graph, gan._side, gan._wg_side = saved
 
     # second half of BASELINE.json's metric: sliding-window inference (config 5) through the public GanMonitor call, host volume
     # in / host result out, windows sharded over the ranks

@@ -458,9 +458,27 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const vg_pack_job* __re
             const vg_pack_job job = jobs[j];
             const long long b = prefix[j] > s0 ? prefix[j] : s0;
             const long long e = prefix[j] + job.total < s1 ? prefix[j] + job.total : s1;
-            for (long long g = b + threadIdx.x; g < e; g += 256) {
-                const size_t i = (size_t)(g - prefix[j]);
-                job.out[i] = __float2bfloat16(pack_elem(job, i));
+            // runs of 8 packed elements (innermost index of every layout: 8 consecutive k, or 8 consecutive channels) share their
+            // validity and read the source at one constant stride: two index decodes, eight loads, one 16-byte store per run
+            if (((b - prefix[j]) | (e - prefix[j])) & 7) {
+                for (long long g = b + threadIdx.x; g < e; g += 256) {
+                    const size_t i = (size_t)(g - prefix[j]);
+                    job.out[i] = __float2bfloat16(pack_elem(job, i));
+                }
+            } else {
+                for (long long g = b + 8LL * threadIdx.x; g < e; g += 8 * 256) {
+                    const size_t i = (size_t)(g - prefix[j]);
+                    const long long s0_ = pack_src(job, i);
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (s0_ >= 0) {
+                        const long long st = pack_src(job, i + 1) - s0_;
+                        float f[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) f[k] = job.w[s0_ + k * st];
+                        o.x = pack2_bf16(f[0], f[1]); o.y = pack2_bf16(f[2], f[3]); o.z = pack2_bf16(f[4], f[5]); o.w = pack2_bf16(f[6], f[7]);
+                    }
+                    *reinterpret_cast<uint4*>(job.out + i) = o;
+                }
             }
         }
     }

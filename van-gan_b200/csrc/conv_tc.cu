@@ -63,6 +63,7 @@ struct TcParams {
     int dm_order[12];   // d-march: issue order of the source slices (overlapping TMEM windows kept >= 3 instructions apart)
     int dm_lean;  // d-march issue sequence unrolled with immediate per-slice constants (default; VG_TC_DMLEAN=0 = round-1 loop)
     int dm;   // d-march: the TD taps along d are folded into the MMA N dimension (N = cnt * NCTA, sliding TMEM window)
+    int ca;       // cp.async.ca instead of .cg in the gather loader (VG_CPASYNC=ca)
     int stages, act, use_tma, dbg;   // dbg: bit0 = skip brick/weight loads, bit1 = skip MMA issue (timing experiments only)
     const bf16* x;        // source tensor (gather loader)
     int XD, XH, XW, Cx;
@@ -199,8 +200,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                         const bf16* src = ok ? xc + (((size_t)sd * p.XH + sh) * p.XW + sw) * p.Cx : xc;
                         const uint32_t d0 = dst + (uint32_t)v * 16;
                         const int nbytes = ok ? 16 : 0;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d0), "l"(src), "r"(nbytes) : "memory");
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d0 + p.plane_bytes), "l"(src + 8), "r"(nbytes) : "memory");
+                        if (p.ca) {
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(d0), "l"(src), "r"(nbytes) : "memory");
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(d0 + p.plane_bytes), "l"(src + 8), "r"(nbytes) : "memory");
+                        } else {
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d0), "l"(src), "r"(nbytes) : "memory");
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d0 + p.plane_bytes), "l"(src + 8), "r"(nbytes) : "memory");
+                        }
                     }
                     asm volatile("cp.async.commit_group;\n" ::: "memory");
                     if (p.stages >= 3) {
@@ -607,6 +613,12 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
         dbg = e ? atoi(e) : 0;
     }
     TcParams p{};
+    static int ca = -1;
+    if (ca < 0) {
+        const char* e = getenv("VG_CPASYNC");
+        ca = (e && e[0] == 'c' && e[1] == 'a') ? 1 : 0;
+    }
+    p.ca = ca;
     p.use_tma = (ss == 2 || dsplit) ? 2 : loader;   // strided views / shifted bricks are only implemented by the cp.async gather
     p.dsplit = dsplit ? TD_full : 0;
     p.dbg = dbg;
@@ -714,7 +726,7 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
 // pack kernel for the tensor-core layout (element function in pack_elem.cuh)
 __global__ void tc_pack_kernel(const vg_pack_job job) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)job.total; i += (size_t)gridDim.x * blockDim.x)
-        job.out[i] = __float2bfloat16(pack_elem_tc(job, i));
+        job.out[i] = __float2bfloat16(pack_elem(job, i));
 }
 
 bool vg_tc_pack_job(const float* w, bf16* out, int K, int stride, int Cin, int Cout, int dgrad, int ad, int ah, int aw, int td, int th, int tw,

@@ -193,16 +193,41 @@ __global__ void __launch_bounds__(NT) clip_adam_kernel(float* __restrict__ w, co
                                                        const double* __restrict__ norms, float lr_t, float b1, float b2,
                                                        float eps, float clip, long long total, const float* __restrict__ lr_t_dev) {
     if (lr_t_dev) lr_t = *lr_t_dev;    // bias-corrected step size kept in device memory (changes every step under graph replay)
-    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        int lo = find_seg(off, nseg, i);
-        float nrm = (float)sqrt(norms[lo]);
-        float scale = clip / fmaxf(nrm, clip);   // tf.clip_by_norm
-        float gi = g[i] * scale;
-        float mi = b1 * m[i] + (1.f - b1) * gi;
-        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    // four consecutive parameters per thread: one segment search and 128-bit accesses when they belong to one variable
+    const long long nq = (total + 3) / 4;
+    for (long long q = (long long)blockIdx.x * NT + threadIdx.x; q < nq; q += (long long)gridDim.x * NT) {
+        const long long i = 4 * q;
+        const int lo = find_seg(off, nseg, i);
+        if (i + 4 <= total && off[lo + 1] >= i + 4) {
+            const float nrm = (float)sqrt(norms[lo]);
+            const float scale = clip / fmaxf(nrm, clip);   // tf.clip_by_norm
+            const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+            float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i),
+                   w4 = *reinterpret_cast<const float4*>(w + i);
+            const float gi[4] = {g4.x * scale, g4.y * scale, g4.z * scale, g4.w * scale};
+            float* mp = &m4.x; float* vp = &v4.x; float* wp = &w4.x;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                mp[k] = b1 * mp[k] + (1.f - b1) * gi[k];
+                vp[k] = b2 * vp[k] + (1.f - b2) * gi[k] * gi[k];
+                wp[k] -= lr_t * mp[k] / (sqrtf(vp[k]) + eps);
+            }
+            *reinterpret_cast<float4*>(m + i) = m4;
+            *reinterpret_cast<float4*>(v + i) = v4;
+            *reinterpret_cast<float4*>(w + i) = w4;
+        } else {
+            for (long long e = i; e < i + 4 && e < total; e++) {
+                const int l2 = find_seg(off, nseg, e);
+                const float nrm = (float)sqrt(norms[l2]);
+                const float scale = clip / fmaxf(nrm, clip);
+                const float gi = g[e] * scale;
+                const float mi = b1 * m[e] + (1.f - b1) * gi;
+                const float vi = b2 * v[e] + (1.f - b2) * gi * gi;
+                m[e] = mi;
+                v[e] = vi;
+                w[e] -= lr_t * mi / (sqrtf(vi) + eps);
+            }
+        }
     }
 }
 
@@ -463,7 +488,7 @@ static int clip_adam_impl(float* w, const float* g, float* m, float* v, const lo
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(norm_ws, 0, (size_t)nseg * sizeof(double), st) != cudaSuccess) return VG_ERR_CUDA;
     seg_sqnorm_kernel<<<vg_grid_for(total / 4 + 1, NT, 8), NT, 0, st>>>(g, seg_offsets, nseg, norm_ws, total); VG_LAUNCHED(1);
-    clip_adam_kernel<<<vg_grid_for(total, NT, 16), NT, 0, st>>>(w, g, m, v, seg_offsets, nseg, norm_ws, lr_t, beta1, beta2, eps,
+    clip_adam_kernel<<<vg_grid_for((total + 3) / 4, NT, 16), NT, 0, st>>>(w, g, m, v, seg_offsets, nseg, norm_ws, lr_t, beta1, beta2, eps,
                                                                clipnorm, total, lr_t_dev); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;

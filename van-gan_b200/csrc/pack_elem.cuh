@@ -17,21 +17,22 @@ struct vg_pack_job {
     int Np, T;                           // kind 0 / 1: padded row count, taps
 };
 
-__device__ __forceinline__ float pack_elem_mma_fwd(const vg_pack_job& j, size_t i) {
+// pack_src_*: index into the fp32 Keras kernel of packed element i, or -1 for a zero (padding) element
+__device__ __forceinline__ long long pack_src_mma_fwd(const vg_pack_job& j, size_t i) {
     const int ci = (int)(i % j.Cin);
     const int co = (int)((i / j.Cin) % j.Np);
     const int t = (int)(i / ((size_t)j.Cin * j.Np));
-    return co < j.Cout ? j.w[((size_t)t * j.Cin + ci) * j.Cout + co] : 0.f;
+    return co < j.Cout ? (long long)(((size_t)t * j.Cin + ci) * j.Cout + co) : -1;
 }
 
-__device__ __forceinline__ float pack_elem_mma_dgrad(const vg_pack_job& j, size_t i) {
+__device__ __forceinline__ long long pack_src_mma_dgrad(const vg_pack_job& j, size_t i) {
     const int co = (int)(i % j.Cout);
     const int ci = (int)((i / j.Cout) % j.Np);
     const int tt = (int)(i / ((size_t)j.Cout * j.Np));
     const int w_ = tt % j.tw, h_ = (tt / j.tw) % j.th, d_ = tt / (j.tw * j.th);
     const int kd = j.ad + j.stride * d_, kh = j.ah + j.stride * h_, kw = j.aw + j.stride * w_;
     const int t = (kd * j.K + kh) * j.K + kw;
-    return ci < j.Cin ? j.w[((size_t)t * j.Cin + ci) * j.Cout + co] : 0.f;
+    return ci < j.Cin ? (long long)(((size_t)t * j.Cin + ci) * j.Cout + co) : -1;
 }
 
 // tensor-core layout: out[nb][c][t][kh][n][j] = src(t, k = c*16+kh*8+j, col = nb*NCTA+n)
@@ -39,7 +40,7 @@ __device__ __forceinline__ float pack_elem_mma_dgrad(const vg_pack_job& j, size_
 // dgrad: src(t',k,col) = w[tap(t')][col][k]      (K = Cout, cols = Cin), taps restricted to one stride-parity class
 // fwd stride 2 (dgrad == 2): chunk c = (parity class a,b,c ; 16-channel chunk), taps t' in 2x2x2, src = w[2t'+a][k][col] (0 if >= K)
 // dgrad == 3: fused stride-2 parity classes -- columns are (class, ci), every class padded to 2x2x2 taps
-__device__ __forceinline__ float pack_elem_tc(const vg_pack_job& q, size_t i) {
+__device__ __forceinline__ long long pack_src_tc(const vg_pack_job& q, size_t i) {
     const int K = q.K, stride = q.stride, Cin = q.Cin, Cout = q.Cout, dgrad = q.dgrad, td = q.td, th = q.th, tw = q.tw, ncta = q.ncta;
     const int T = q.dsplit ? th * tw : td * th * tw;
     const int Kt = (dgrad == 1 || dgrad == 3) ? Cout : Cin, ncols = dgrad == 1 ? Cin : (dgrad == 3 ? 8 * Cin : Cout);
@@ -83,14 +84,17 @@ __device__ __forceinline__ float pack_elem_tc(const vg_pack_job& q, size_t i) {
         kd = ((cls >> 2) & 1) + 2 * d_; kh2 = ((cls >> 1) & 1) + 2 * h_; kw = (cls & 1) + 2 * w_;
     }
     int tap = (kd * K + kh2) * K + kw;
-    float v = 0.f;
     if (col < ncols && kd < K && kh2 < K && kw < K)
-        v = (dgrad == 1 || dgrad == 3) ? q.w[((size_t)tap * Cin + ci) * Cout + k] : q.w[((size_t)tap * Cin + k) * Cout + col];
-    return v;
+        return (dgrad == 1 || dgrad == 3) ? (long long)(((size_t)tap * Cin + ci) * Cout + k) : (long long)(((size_t)tap * Cin + k) * Cout + col);
+    return -1;
 }
 
+__device__ __forceinline__ long long pack_src(const vg_pack_job& j, size_t i) {
+    return j.kind == 0 ? pack_src_mma_fwd(j, i) : (j.kind == 1 ? pack_src_mma_dgrad(j, i) : pack_src_tc(j, i));
+}
 __device__ __forceinline__ float pack_elem(const vg_pack_job& j, size_t i) {
-    return j.kind == 0 ? pack_elem_mma_fwd(j, i) : (j.kind == 1 ? pack_elem_mma_dgrad(j, i) : pack_elem_tc(j, i));
+    const long long s = pack_src(j, i);
+    return s < 0 ? 0.f : j.w[s];
 }
 
 // host side of the tcgen05 pack: fills the job for one (layer, class); returns false when the shape has no tcgen05 layout

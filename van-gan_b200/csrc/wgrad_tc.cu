@@ -68,7 +68,7 @@ struct WgParams {
     int XDb, XHb, XHu, XWb, YDb, nB;         // XHu: rows that carry useful taps (<= XHb)
     int x_sd, x_sc, x_spar, x_sh, x_nw;      // X stage strides (cells): slice, chunk, w-parity plane set (stride 2), row; voxels per row
     uint32_t x_bytes, stage_bytes, tmem_cols;
-    int stages;
+    int stages, ca;
 };
 
 // One gathered region: cells of 16 bytes (8 channels of one voxel).  A region row is (slice d, channel chunk c, row h);
@@ -80,6 +80,7 @@ struct Region {
     int nd, nc, nh, nw;   // extents: slices, chunks, rows, voxels per row
     int lgp;              // log2(planes per chunk)
     int s2, spar;         // stride-2 source: voxel w goes to parity plane set (w & 1) at index w >> 1
+    int ca;               // cp.async.ca (through L1: the second 16-byte half of a 32-byte sector hits) instead of .cg
     int sd, sc, sh, sp;   // shared-memory strides in cells: slice, chunk, row, plane (voxel stride = 1)
     FastDiv by_cnh, by_nh;
 };
@@ -107,7 +108,8 @@ __device__ __forceinline__ void gather_region(const Region& r, uint32_t dst_base
         if (rowok && w_inside) {
 #pragma unroll 2
             for (int w = wl; w < r.nw; w += wps) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+                if (r.ca) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+                else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
                 src += wstep_src;
                 dst += dst_step;
             }
@@ -242,6 +244,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
         int lgx = 0, lgy = 0;
         while ((1 << lgx) < p.PLC) lgx++;
         while ((1 << lgy) < p.NPLy) lgy++;
+        rx.ca = ry.ca = p.ca;
         rx.GD = p.XD; rx.GH = p.XH; rx.GW = p.XW; rx.C = p.Cx;
         rx.nd = p.XDb; rx.nc = p.NCH; rx.nh = p.XHu; rx.nw = p.x_nw; rx.lgp = lgx;
         rx.sd = p.x_sd; rx.sc = p.x_sc; rx.sh = p.x_sh; rx.sp = p.XWb; rx.s2 = p.st == 2; rx.spar = p.x_spar;
@@ -500,6 +503,12 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
     if (cols > 512) return VG_ERR_UNSUPPORTED;
     p.tmem_cols = cols;
 
+    static int ca = -1;   // VG_CPASYNC=ca: gather through L1 (A/B testing)
+    if (ca < 0) {
+        const char* e = getenv("VG_CPASYNC");
+        ca = (e && e[0] == 'c' && e[1] == 'a') ? 1 : 0;
+    }
+    p.ca = ca;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return VG_ERR_CUDA;
