@@ -294,14 +294,129 @@ skel_level_fwd_march_kernel(const float* __restrict__ e_in, float* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------ 4 voxels per thread
+// Same separable evaluation as skel_level_fwd_march_kernel with a thread owning FOUR consecutive x of one row (128-bit global and
+// shared accesses): the x neighbours of the two inner voxels are the thread's own registers, only the outer two come from shuffles,
+// and one barrier / six LDS.128 / three STS.128 serve four voxels.  A warp spans 128 x: a row of W <= 128 voxels needs no x halo at
+// all (outside the volume = +-inf), wider volumes use tiles of 120 outputs with one float4 of halo per side.  Requires W % 4 == 0.
+constexpr int V4_ROWS = 20, V4_OUT = V4_ROWS - 4, V4_THREADS = 32 * V4_ROWS;
+
+struct f4 {
+    float a, b, c, d;
+};
+__device__ __forceinline__ f4 f4_set(float v) { return f4{v, v, v, v}; }
+__device__ __forceinline__ f4 f4_min(const f4& p, const f4& q) { return f4{fminf(p.a, q.a), fminf(p.b, q.b), fminf(p.c, q.c), fminf(p.d, q.d)}; }
+__device__ __forceinline__ f4 f4_max(const f4& p, const f4& q) { return f4{fmaxf(p.a, q.a), fmaxf(p.b, q.b), fmaxf(p.c, q.c), fmaxf(p.d, q.d)}; }
+// min / max over the x window {-1, 0, +1} of every element; L / R: the neighbouring lanes' adjacent elements
+__device__ __forceinline__ f4 f4_min3x(const f4& v, float L, float R) {
+    return f4{fminf(L, fminf(v.a, v.b)), fminf(v.a, fminf(v.b, v.c)), fminf(v.b, fminf(v.c, v.d)), fminf(v.c, fminf(v.d, R))};
+}
+__device__ __forceinline__ f4 f4_max3x(const f4& v, float L, float R) {
+    return f4{fmaxf(L, fmaxf(v.a, v.b)), fmaxf(v.a, fmaxf(v.b, v.c)), fmaxf(v.b, fmaxf(v.c, v.d)), fmaxf(v.c, fmaxf(v.d, R))};
+}
+__device__ __forceinline__ f4 f4_lds(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    return f4{t.x, t.y, t.z, t.w};
+}
+__device__ __forceinline__ void f4_sts(float* p, const f4& v) { *reinterpret_cast<float4*>(p) = make_float4(v.a, v.b, v.c, v.d); }
+
+__global__ void __launch_bounds__(V4_THREADS, 1)
+skel_level_fwd_v4_kernel(const float* __restrict__ e_in, float* __restrict__ e_out, const float* __restrict__ skel_in,
+                         float* __restrict__ skel_out, Vol v, int tiles_x, int tiles_y, int zchunks, int ZL, int first, int two, int hx) {
+    extern __shared__ __align__(16) float v4_smem[];
+    typedef float (*plane_t)[V4_ROWS + 2][128];
+    plane_t sV = reinterpret_cast<plane_t>(v4_smem), sRX = sV + 2, sMX = sV + 4;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    int t = blockIdx.x;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y; t /= tiles_y;
+    const int zc = t % zchunks;
+    const int n = t / zchunks;
+    const int gx = tx * two - hx + 4 * lane, gy = ty * V4_OUT - 2 + wy;        // first of the thread's four x
+    const int z0 = zc * ZL, zend = min(z0 + ZL, v.D);
+    const bool col_in = gx >= 0 && gx < v.W && (unsigned)gy < (unsigned)v.H;   // W % 4 == 0: the four voxels are in or out together
+    const bool x_out = hx == 0 || (lane >= 1 && lane < 31);
+    const bool out_thread = col_in && x_out && wy >= 2 && wy < V4_ROWS - 2;
+    const size_t HW = (size_t)v.H * v.W;
+    const size_t col = (size_t)n * v.D * HW + (size_t)(col_in ? gy : 0) * v.W + (col_in ? gx : 0);
+    if (wy == 0) {
+        for (int b = 0; b < 2; b++)
+            for (int k = 0; k < 4; k++) {
+                sV[b][0][4 * lane + k] = INFINITY; sV[b][V4_ROWS + 1][4 * lane + k] = INFINITY;
+                sRX[b][0][4 * lane + k] = INFINITY; sRX[b][V4_ROWS + 1][4 * lane + k] = INFINITY;
+                sMX[b][0][4 * lane + k] = -INFINITY; sMX[b][V4_ROWS + 1][4 * lane + k] = -INFINITY;
+            }
+    }
+    auto loadv = [&](int pz) -> f4 {
+        if (col_in && pz >= 0 && pz < v.D && pz < zend + 2) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(e_in + col + (size_t)pz * HW));
+            return f4{q.x, q.y, q.z, q.w};
+        }
+        return f4_set(INFINITY);
+    };
+    const unsigned FULL = 0xffffffffu;
+    f4 vnext = loadv(z0 - 2);
+    f4 v1 = f4_set(INFINITY), v2 = v1, v3 = v1;
+    f4 rx1 = v1, rx2 = v1, ry1 = v1, ry2 = v1, rxy1 = v1;
+    f4 e1_1 = f4_set(-INFINITY), e1_2 = e1_1, mxy3 = e1_1, mxy4 = e1_1, mx_prev = e1_1;
+    for (int i = 0; i < ZL + 5; i++) {
+        const int pz = z0 - 2 + i, buf = i & 1, zo = pz - 3;
+        const f4 vA = vnext;
+        vnext = loadv(pz + 1);
+        const bool out_ok = out_thread && zo >= z0 && zo < zend;
+        f4 sp = f4_set(0.f);
+        if (out_ok && !first) {
+            const float4 q = *reinterpret_cast<const float4*>(skel_in + col + (size_t)zo * HW);
+            sp = f4{q.x, q.y, q.z, q.w};
+        }
+        // lane 0 / 31 have no neighbour lane: outside the tile (and, without x halo, outside the volume) = +inf
+        float L = __shfl_up_sync(FULL, vA.d, 1), R = __shfl_down_sync(FULL, vA.a, 1);
+        if (lane == 0) L = INFINITY;
+        if (lane == 31) R = INFINITY;
+        const f4 rxA = f4_min3x(vA, L, R);
+        f4_sts(&sV[buf][wy + 1][4 * lane], vA);
+        f4_sts(&sRX[buf][wy + 1][4 * lane], rxA);
+        f4_sts(&sMX[buf][wy + 1][4 * lane], mx_prev);
+        __syncthreads();
+        const f4 ryA = f4_min(vA, f4_min(f4_lds(&sV[buf][wy][4 * lane]), f4_lds(&sV[buf][wy + 2][4 * lane])));
+        const f4 rxyA = f4_min(rxA, f4_min(f4_lds(&sRX[buf][wy][4 * lane]), f4_lds(&sRX[buf][wy + 2][4 * lane])));
+        const f4 mxyC = f4_max(mx_prev, f4_max(f4_lds(&sMX[buf][wy][4 * lane]), f4_lds(&sMX[buf][wy + 2][4 * lane])));   // plane pz-2
+        // eroded image at plane pz-1 (out-of-volume voxels must not take part in the dilation)
+        f4 e1b = f4_min(rxy1, f4_min(f4_min(rx2, f4_min(rx1, rxA)), f4_min(ry2, f4_min(ry1, ryA))));
+        if (!(col_in && pz - 1 >= 0 && pz - 1 < v.D)) e1b = f4_set(-INFINITY);
+        float Lm = __shfl_up_sync(FULL, e1b.d, 1), Rm = __shfl_down_sync(FULL, e1b.a, 1);
+        if (lane == 0) Lm = -INFINITY;
+        if (lane == 31) Rm = -INFINITY;
+        const f4 mxb = f4_max3x(e1b, Lm, Rm);
+        if (out_ok) {
+            const f4 o = f4_max(mxy4, f4_max(mxy3, mxyC));
+            const float ev[4] = {v3.a, v3.b, v3.c, v3.d}, ov[4] = {o.a, o.b, o.c, o.d}, spv[4] = {sp.a, sp.b, sp.c, sp.d};
+            float sk[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float delta = fmaxf(__fsub_rn(ev[k], ov[k]), 0.f);
+                sk[k] = first ? delta : __fadd_rn(spv[k], fmaxf(__fsub_rn(delta, __fmul_rn(spv[k], delta)), 0.f));
+            }
+            const size_t g = col + (size_t)zo * HW;
+            *reinterpret_cast<float4*>(skel_out + g) = make_float4(sk[0], sk[1], sk[2], sk[3]);
+            *reinterpret_cast<float4*>(e_out + g) = make_float4(e1_2.a, e1_2.b, e1_2.c, e1_2.d);
+        }
+        v3 = v2; v2 = v1; v1 = vA;
+        rx2 = rx1; rx1 = rxA; ry2 = ry1; ry1 = ryA; rxy1 = rxyA;
+        e1_2 = e1_1; e1_1 = e1b;
+        mxy4 = mxy3; mxy3 = mxyC;
+        mx_prev = mxb;
+    }
+}
+
 // chunk length along z for the marching kernels: fill the resident-block slots evenly (2 blocks per SM) at a small halo cost
-inline int pick_zl(int D, long long columns, int halo_iters) {
+inline int pick_zl(int D, long long columns, int halo_iters, int slots = 296) {
     int best = D;
     double best_eff = 0.0;
     for (int zl = 8; zl <= D; zl += 4) {
         const long long blocks = columns * ((D + zl - 1) / zl);
-        const long long waves = (blocks + 295) / 296;
-        const double eff = ((double)blocks / (double)(waves * 296)) * ((double)zl / (double)(zl + halo_iters));
+        const long long waves = (blocks + slots - 1) / slots;
+        const double eff = ((double)blocks / (double)(waves * slots)) * ((double)zl / (double)(zl + halo_iters));
         if (eff > best_eff + 1e-9) { best_eff = eff; best = zl; }
     }
     if (D < 8) best = D;
@@ -312,7 +427,7 @@ inline bool skel_march() {
     static int m = -1;
     if (m < 0) {
         const char* e = getenv("VG_SKEL");
-        m = (e && e[0] == 't') ? 0 : 1;
+        m = (e && e[0] == 't') ? 0 : 1;   // "tile": shared-memory tile kernels; "march": scalar marching kernel; default: 4 voxels per thread
     }
     return m == 1;
 }
@@ -342,8 +457,28 @@ int vg_soft_skel_fwd(const float* x, float* E, float* S, int N, int D, int H, in
     int blocks = tx * ty * tz * N;
     const int mtx = vg_cdiv(W, MW_OUT), mty = vg_cdiv(H, MH_OUT);
     const int ZL = pick_zl(D, (long long)N * mtx * mty, 5), zch = vg_cdiv(D, ZL);
+    // 4-voxels-per-thread kernel: W % 4 == 0 (VG_SKEL=march keeps the scalar marching kernel)
+    static int v4on = -1;
+    if (v4on < 0) {
+        const char* e = getenv("VG_SKEL");
+        v4on = (e && (e[0] == 't' || e[0] == 'm')) ? 0 : 1;
+    }
+    // measured (profiles/r02_skel_v4_call30.txt): 1 x 128^3 0.374 -> 0.243 ms, but with one 640-thread block per SM (94 registers) it
+    // is barrier- and latency-bound once the grid exceeds one wave (8 x 128^3: 194 vs 162 us per level against the scalar kernel, which
+    // ncu shows ISSUE-bound at 73 %), so it serves the small volumes only
+    const bool v4 = v4on && W % 4 == 0 && (long long)N * D * H * W <= (4LL << 20);
+    const int hx = W <= 128 ? 0 : 4, two = W <= 128 ? 128 : 120;
+    const int vtx = vg_cdiv(W, two), vty = vg_cdiv(H, V4_OUT);
+    const int ZL4 = pick_zl(D, (long long)N * vtx * vty, 5, 148), zch4 = vg_cdiv(D, ZL4);
+    constexpr size_t V4_SMEM = (size_t)6 * (V4_ROWS + 2) * 128 * sizeof(float);
+    if (v4 && cudaFuncSetAttribute(skel_level_fwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM) != cudaSuccess)
+        return VG_ERR_CUDA;
     for (int j = 0; j <= iters; j++) {
-        if (skel_march()) {
+        if (v4) {
+            skel_level_fwd_v4_kernel<<<N * vtx * vty * zch4, V4_THREADS, V4_SMEM, st>>>(E + (size_t)j * nv, E + (size_t)(j + 1) * nv,
+                                                                                 j ? S + (size_t)(j - 1) * nv : nullptr, S + (size_t)j * nv,
+                                                                                 v, vtx, vty, zch4, ZL4, j == 0, two, hx);
+        } else if (skel_march()) {
             skel_level_fwd_march_kernel<<<N * mtx * mty * zch, M_THREADS, 0, st>>>(E + (size_t)j * nv, E + (size_t)(j + 1) * nv,
                                                                                   j ? S + (size_t)(j - 1) * nv : nullptr,
                                                                                   S + (size_t)j * nv, v, mtx, mty, zch, ZL, j == 0);
