@@ -42,7 +42,7 @@ class DiscriminatorModel(E.Network):
         self.convo = E.Conv3D(self, "dout.conv", 3, 1, 8 * f, 1)
         self.rng_step = 0
         if seed is not None:
-            self.load(E.default_init({n: p.shape for n, p in self.params.items()}, seed))
+            self.load(E.default_init({n: p.shape for n, p in self.params.items()}, seed, glorot=tuple(n for n in self.params if n.endswith(".in.gamma"))))
 
     def stage(self, k, tape, h, training=True, noise=None, masks=None, seed=0, seed_dev=None):
         """Stage k = 0..4: everything between the raw output of convolution k-1 (the network input for k = 0) and the raw

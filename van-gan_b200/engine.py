@@ -309,11 +309,29 @@ def he_normal(rng, shape):
     return (z * std).astype(np.float32)
 
 
-def default_init(shapes, seed):
+def glorot_uniform(rng, shape):
+    """Keras' default initializer (what a layer built WITHOUT kernel_initializer / with gamma_initializer=None gets):
+    uniform(-l, l), l = sqrt(6 / (fan_in + fan_out)); a 1-D variable of length C has fan_in = fan_out = C."""
+    if len(shape) == 1:
+        fan_in = fan_out = shape[0]
+    else:
+        rf = int(np.prod(shape[:-2]))
+        fan_in, fan_out = rf * shape[-2], rf * shape[-1]
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+def default_init(shapes, seed, glorot=()):
+    """Initial values by the reference's initializers: he_normal kernels, zero biases / betas, unit gammas; the variables named in
+    `glorot` (name or name prefix) are the ones the reference builds with Keras' default glorot_uniform -- the ResUNet stem convolutions
+    and head (resunet_model.py:90,92,96,245), the PatchGAN's InstanceNormalization gammas (gamma_initializer=None, discriminator.py:70,
+    building_blocks.py:190), the V-Net head and Conv3DTranspose kernels (vnet_model.py:245,264)."""
     rng = np.random.default_rng(seed)
     out = {}
     for n, shp in shapes.items():
-        if n.endswith(".w"):
+        if any(n == g or n.startswith(g) for g in glorot) and (n.endswith(".w") or n.endswith(".gamma")):
+            out[n] = glorot_uniform(rng, shp)
+        elif n.endswith(".w"):
             out[n] = he_normal(rng, shp)
         elif n.endswith(".gamma"):
             out[n] = np.ones(shp, np.float32)

@@ -81,7 +81,7 @@ class ResUNetModel(E.Network):
         self.dec = {d: _ResBlock(self, "dec%d" % d, f[d + 1] + f[d], f[d], 1) for d in range(num_layers)}
         self.head = E.Conv3D(self, "head", 1, 1, f[0], 1, act=ACT_TANH)
         if seed is not None:
-            self.load(E.default_init({n: p.shape for n, p in self.params.items()}, seed))
+            self.load(E.default_init({n: p.shape for n, p in self.params.items()}, seed, glorot=("stem.conv0.w", "stem.short.conv.w", "head.w")))
 
     def forward(self, tape, x, taps=None):
         """x: Var holding an (N,D,H,W,1) fp32 volume.  Returns the (N,D,H,W,1) fp32 tanh output.

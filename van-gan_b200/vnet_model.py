@@ -96,7 +96,7 @@ class VNetModel(E.Network):
         self.head = E.Conv3D(self, "head", 1, 1, f, 1, act=ACT_TANH)
         self.rng_step = 0
         if seed is not None:
-            self.load(E.default_init({n: p.shape for n, p in self.params.items()}, seed))
+            self.load(E.default_init({n: p.shape for n, p in self.params.items()}, seed, glorot=("head.w",) + tuple(n for n in self.params if n.endswith(".up.w"))))
 
     def drop_channels(self):
         """channel widths of the SpatialDropout3D layers, in call order (encoder blocks, then the bottleneck)."""
