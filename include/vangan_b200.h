@@ -112,6 +112,12 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
 int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, const float* drop, void* dx, int accumulate_dx, void* dres,
                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+/* the same + the bias gradients of the convolutions that PRODUCED x and the residual: dx of the norm is dy of that convolution, so
+ * dbias_x[c] += sum over (n, voxels) of the stored dx and dbias_res[c] += sum of the stored dres are taken in the same pass instead of a
+ * pass of their own over dy inside vg_conv3d_wgrad (call that with dbias = NULL then).  Either may be NULL; dbias_x excludes accumulate_dx. */
+int vg_instnorm_bwd_sinks(const vg_instnorm_desc* d, const void* dy, const void* x, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta, const float* drop, void* dx, int accumulate_dx, void* dres,
+                          float* dgamma, float* dbeta, float* dbias_x, float* dbias_res, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout helpers around the convolutions: UpSampling3D(2)+concatenate (resunet_model.py:176,181),

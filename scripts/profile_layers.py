@@ -8,7 +8,8 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 b = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 I, Sg = synth_batch(b, S, 3)
 gan = VanGan(Args(S, b, 1), gen_i2s='resUnet', gen_s2i='resUnet')
-gan.use_graph = False   # CUDA events around every ABI call need eager launches
+gan.use_graph = False   # CUDA events around every ABI call need eager launches ...
+gan._side = gan._wg_side = None   # ... on ONE stream (side streams would add other branches' kernels to every event pair)
 dI, dS = torch.tensor(I).cuda(), torch.tensor(Sg).cuda()
 for i in range(2):
     gan.train_step(dI, dS)

@@ -58,6 +58,7 @@ SIGNATURES = {
     "vg_instnorm_stats": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "vg_instnorm_apply": (_I, [_ID, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vg_instnorm_bwd": (_I, [_ID, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    "vg_instnorm_bwd_sinks": (_I, [_ID, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "vg_upsample_concat": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vg_upsample_concat_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_gather_pad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

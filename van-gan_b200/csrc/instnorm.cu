@@ -387,13 +387,41 @@ __global__ void bn_expand_kernel(const float* __restrict__ mean_c, const float* 
     }
 }
 
+// ------------------------------------------------------------------ bias-gradient sinks
+// dx of a norm IS dy of the convolution that produced x (and dres is dy of the convolution that produced the residual), so the
+// per-channel sums those convolutions need for their bias gradients (a pass of its own over dy otherwise: channel_sum_kernel) are
+// taken here from the values as they are STORED (bf16-rounded).  Per-thread partial sums -> shared-memory tree over the block's
+// voxel lanes -> one atomicAdd per channel per block.
+struct Sinks {
+    float* dx;     // fp32[C] += sum over (n, voxels) of the stored dx, or NULL
+    float* dres;   // same for dres
+};
+template <typename T> __device__ __forceinline__ float stored(float v);
+template <> __device__ __forceinline__ float stored<bf16>(float v) { return __bfloat162float(__float2bfloat16(v)); }
+template <> __device__ __forceinline__ float stored<float>(float v) { return v; }
+
+__device__ __forceinline__ void sink_flush(const float* acc, float* sink, int C, int c8, int vl, int nvl, float* sm) {
+    // sm: [nvl][C] floats (dynamic shared memory of the apply kernels when a sink is requested)
+#pragma unroll
+    for (int k = 0; k < 8; k++) sm[(size_t)vl * C + c8 * 8 + k] = acc[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int l = 0; l < nvl; l++) t += sm[(size_t)l * C + c];
+        atomicAdd(sink + c, t);
+    }
+    __syncthreads();
+}
+
 // dx = gamma*rstd*(g - S1/V - xhat*S2/V) with g = fold(dy)*drop*act'(z); dres = fold(dy) (optional).
 // fold: REFLECT -> every padded position whose mirror is this voxel (1 for interior voxels, up to 8 on the
 // shell); ZERO -> the interior only.
 template <typename T>
 __global__ void __launch_bounds__(NT, 2) in_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g, BwdArgs a,
                                                           const float* __restrict__ sums, T* __restrict__ dx,
-                                                          T* __restrict__ dres, int accumulate_dx) {
+                                                          T* __restrict__ dres, int accumulate_dx, Sinks sk) {
+    extern __shared__ float sink_sm[];
+    float sx[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int n = blockIdx.y, C = g.C, cg = C / 8;
     const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
     const int PH = g.H + g.pad_lo + g.pad_hi, PW = g.W + g.pad_lo + g.pad_hi, PD = g.D + g.pad_lo + g.pad_hi;
@@ -460,7 +488,13 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_kernel(const T* __restrict
                             for (int k = 0; k < 8; k++) gy[k] += t[k];
                         }
             }
-            if (drn) store8<T>(drn + (size_t)vv * C, gy);
+            if (drn) {
+                store8<T>(drn + (size_t)vv * C, gy);
+                if (sk.dres) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) sr[k] += stored<T>(gy[k]);
+                }
+            }
             float o[8];
             if (accumulate_dx) load8<T>(dxn + (size_t)vv * C, o);
 #pragma unroll
@@ -472,8 +506,14 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_kernel(const T* __restrict
                 o[k] = accumulate_dx ? o[k] + val : val;
             }
             store8<T>(dxn + (size_t)vv * C, o);
+            if (sk.dx) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) sx[k] += stored<T>(o[k]);
+            }
         }
     }
+    if (sk.dx) sink_flush(sx, sk.dx, C, c8, vl, nvl, sink_sm);
+    if (sk.dres) sink_flush(sr, sk.dres, C, c8, vl, nvl, sink_sm);
 }
 
 // ================================================================== specialised instances (generator hot path)
@@ -676,7 +716,9 @@ __device__ __noinline__ void shell_fold(const T* __restrict__ dyn, const Geo& g,
 template <typename T, int SP, bool FOLDED>
 __global__ void __launch_bounds__(NT, 2) in_bwd_apply_sp_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g, BwdArgs a,
                                                           const float* __restrict__ sums, T* __restrict__ dx,
-                                                          T* __restrict__ dres, int accumulate_dx) {
+                                                          T* __restrict__ dres, int accumulate_dx, Sinks sk) {
+    extern __shared__ float sink_sm[];
+    float sx[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int act = SP == 0 ? a.act : (SP == 1 ? VG_ACT_RELU : VG_ACT_NONE);
     const int pad_lo = SP == 0 ? g.pad_lo : (SP == 1 ? 1 : 0), pad_hi = SP == 0 ? g.pad_hi : (SP == 1 ? 1 : 0);
     const int pad_mode = SP == 0 ? pad_mode : VG_PAD_REFLECT;
@@ -729,7 +771,13 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_sp_kernel(const T* __restr
             const int d = cd[u], h = ch[u], w = cw[u];
             if (!FOLDED && refl && (d == 1 || d == g.D - 2 || h == 1 || h == g.H - 2 || w == 1 || w == g.W - 2))
                 shell_fold<T>(dyn, g, PH, PW, C, d, h, w, gy);   // shell voxel: add the mirrored halo positions (rare, not inlined)
-            if (drn) store8<T>(drn + (size_t)vv * C, gy);
+            if (drn) {
+                store8<T>(drn + (size_t)vv * C, gy);
+                if (sk.dres) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) sr[k] += stored<T>(gy[k]);
+                }
+            }
             float o[8];
             if (accumulate_dx) load8<T>(dxn + (size_t)vv * C, o);
 #pragma unroll
@@ -741,8 +789,14 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_apply_sp_kernel(const T* __restr
                 o[k] = accumulate_dx ? o[k] + val : val;
             }
             store8<T>(dxn + (size_t)vv * C, o);
+            if (sk.dx) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) sx[k] += stored<T>(o[k]);
+            }
         }
     }
+    if (sk.dx) sink_flush(sx, sk.dx, C, c8, vl, nvl, sink_sm);
+    if (sk.dres) sink_flush(sr, sk.dres, C, c8, vl, nvl, sink_sm);
 }
 
 // ------------------------------------------------------------------ forward fast path: interior pass + halo pass
@@ -1041,7 +1095,19 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
 int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, const float* drop, void* dx, int accumulate_dx, void* dres,
                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
+    return vg_instnorm_bwd_sinks(d, dy, x, mean, rstd, gamma, beta, drop, dx, accumulate_dx, dres, dgamma, dbeta, nullptr, nullptr, ws,
+                                 ws_bytes, stream);
+}
+
+// vg_instnorm_bwd + the bias gradients of the convolutions that produced x / the residual: dbias_x[c] += sum of the stored dx,
+// dbias_res[c] += sum of the stored dres (either may be NULL).  Not combinable with accumulate_dx (the sum must be of the
+// producer's whole gradient).
+int vg_instnorm_bwd_sinks(const vg_instnorm_desc* d, const void* dy, const void* x, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta, const float* drop, void* dx, int accumulate_dx, void* dres,
+                          float* dgamma, float* dbeta, float* dbias_x, float* dbias_res, void* ws, size_t ws_bytes, void* stream) {
     VG_REQUIRE(d && dy && x && mean && rstd && gamma && beta && dx && ws);
+    VG_REQUIRE(!(dbias_x && accumulate_dx) && !(dbias_res && !dres));
+    const Sinks sk{dbias_x, dbias_res};
     VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT);
     const int dtype = d->dtype & ~(VG_IN_RELU_INPUT | VG_IN_BATCH_STATS | VG_IN_DY_SCRATCH);
     const int batch = (d->dtype & VG_IN_BATCH_STATS) ? 1 : 0;
@@ -1057,6 +1123,7 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
     float* sums = (float*)((char*)ws + need_p);
     const int nthr = block_threads(d->C);
     size_t smem = (size_t)(nthr / (d->C / 8)) * d->C * 2 * sizeof(float);
+    const size_t sink_smem = (dbias_x || dbias_res) ? (size_t)(nthr / (d->C / 8)) * d->C * sizeof(float) : 0;
     dim3 grid2(pick_grid((long long)d->D * d->H * d->W, d->N, d->C), d->N);
     cudaStream_t st = (cudaStream_t)stream;
     int sp = 0;
@@ -1085,28 +1152,28 @@ int vg_instnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, co
         in_fold_inplace_kernel<bf16><<<dim3(vg_cdiv(faces, 256), d->N), 256, 0, st>>>((bf16*)const_cast<void*>(dy), g);
         in_bwd_partial_folded_kernel<bf16><<<dim3(nblk2, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk2, d->N, d->C, sums, dgamma, dbeta, batch);
-        in_bwd_apply_sp_kernel<bf16, 1, true><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
+        in_bwd_apply_sp_kernel<bf16, 1, true><<<grid2, nthr, sink_smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx, sk);
         VG_LAUNCHED(4);
     } else if (sp == 1) {
         in_bwd_partial_sp_kernel<bf16, 1><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta, batch);
-        in_bwd_apply_sp_kernel<bf16, 1, false><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
+        in_bwd_apply_sp_kernel<bf16, 1, false><<<grid2, nthr, sink_smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx, sk);
         VG_LAUNCHED(3);
     } else if (sp == 2) {
         in_bwd_partial_sp_kernel<bf16, 2><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta, batch);
-        in_bwd_apply_sp_kernel<bf16, 2, false><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx);
+        in_bwd_apply_sp_kernel<bf16, 2, false><<<grid2, nthr, sink_smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres, accumulate_dx, sk);
         VG_LAUNCHED(3);
     } else if (dtype == VG_BF16) {
         in_bwd_partial_kernel<bf16><<<dim3(nblk, d->N), nthr, smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, partial); VG_LAUNCHED(1);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta, batch); VG_LAUNCHED(1);
-        in_bwd_apply_kernel<bf16><<<grid2, nthr, 0, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres,
-                                                         accumulate_dx); VG_LAUNCHED(1);
+        in_bwd_apply_kernel<bf16><<<grid2, nthr, sink_smem, st>>>((const bf16*)dy, (const bf16*)x, g, a, sums, (bf16*)dx, (bf16*)dres,
+                                                                 accumulate_dx, sk); VG_LAUNCHED(1);
     } else if (dtype == VG_F32) {
         in_bwd_partial_kernel<float><<<dim3(nblk, d->N), nthr, smem, st>>>((const float*)dy, (const float*)x, g, a, partial); VG_LAUNCHED(1);
         in_bwd_final_kernel<<<vg_cdiv(d->N * d->C, 8), 256, 0, st>>>(partial, nblk, d->N, d->C, sums, dgamma, dbeta, batch); VG_LAUNCHED(1);
-        in_bwd_apply_kernel<float><<<grid2, nthr, 0, st>>>((const float*)dy, (const float*)x, g, a, sums, (float*)dx, (float*)dres,
-                                                          accumulate_dx); VG_LAUNCHED(1);
+        in_bwd_apply_kernel<float><<<grid2, nthr, sink_smem, st>>>((const float*)dy, (const float*)x, g, a, sums, (float*)dx, (float*)dres,
+                                                                  accumulate_dx, sk); VG_LAUNCHED(1);
     } else {
         return VG_ERR_INVALID;
     }

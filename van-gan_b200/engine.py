@@ -17,17 +17,21 @@ from . import _lib
 from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH, PAD_REFLECT, PAD_ZERO, ConvDesc, InDesc, call, dtype_code
 
 DEV = "cuda"
+BIAS_SINKS = __import__("os").environ.get("VG_BIAS_SINKS", "1") != "0"   # conv bias gradients taken inside the consuming norm's backward
 
 
 # ----------------------------------------------------------------------------- tape
 class Var:
     """A tensor on the tape.  `data`: torch CUDA tensor; `grad`: accumulated gradient or None."""
-    __slots__ = ("data", "grad", "src")
+    __slots__ = ("data", "grad", "src", "ncons", "bias_sink", "bias_done")
 
     def __init__(self, data, src=None):
         self.data = data
         self.grad = None
         self.src = src
+        self.ncons = 0           # number of recorded consumers
+        self.bias_sink = None    # bias Param of the convolution that produced this tensor (its gradient is the channel sum of ours)
+        self.bias_done = False   # that channel sum was already taken by the consumer's backward kernel in this sweep
 
     @property
     def shape(self):
@@ -55,6 +59,7 @@ class Tape:
     def __init__(self, enabled=True):
         self.nodes = []
         self.enabled = enabled
+        self.wrt = set()          # ids of the Params the running sweep differentiates
         self.wg_stream = None     # optional sibling stream of the current backward sweep for the weight-gradient kernels
         self._keep, self._keep_bytes = [], 0
 
@@ -88,6 +93,8 @@ class Tape:
             node = Node(inputs, outputs, params, bwd, name)
             for o in outputs:
                 o.src = node
+            for v in inputs:
+                v.ncons += 1
             self.nodes.append(node)
 
     def clear(self):
@@ -106,6 +113,7 @@ class Tape:
         (+=) the gradients; wrt_vars: leaf Vars whose .grad is wanted as well (kept after the sweep).
         One reverse sweep; gradients of intermediate Vars are released as soon as they are consumed."""
         wrt = set(id(p) for p in wrt_params)
+        self.wrt = wrt
         needs = set(id(v) for v in wrt_vars)
         keep = set(needs)
         for node in self.nodes:
@@ -380,6 +388,8 @@ class Conv3D:
         call("vg_conv3d_fwd", desc, x.data, self.w.w if self.cin == 1 else self.wf, self.b.w if self.b else None, y,
              work=flops)
         out = Var(y)
+        if self.b is not None and self.act == ACT_NONE and self.cout > 1:
+            out.bias_sink = self.b      # a single consumer that is a norm takes the bias gradient in its own backward pass
 
         def bwd(in_needs, p_needs):
             dy = out.grad
@@ -388,8 +398,9 @@ class Conv3D:
                 call("vg_tanh_bwd", dy, out.data, t, dy.numel())
                 dy = t
             if p_needs:
-                tape.side_call((dy,), lambda: call("vg_conv3d_wgrad", desc, x.data, dy, self.w.grad, self.b.grad if self.b else None,
-                                                   work=flops))
+                dbias = self.b.grad if (self.b is not None and not out.bias_done) else None
+                tape.side_call((dy,), lambda: call("vg_conv3d_wgrad", desc, x.data, dy, self.w.grad, dbias, work=flops))
+            out.bias_done = False
             if in_needs[0]:
                 dx = torch.empty_like(x.data)
                 call("vg_conv3d_dgrad", desc, dy, self.w.w if self.cout == 1 else self.wd, dx, work=flops)
@@ -442,8 +453,17 @@ class InstanceNorm:
             need_res = residual is not None and in_needs[1]
             dres = torch.empty_like(x.data) if need_res else None
             ws2 = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
-            call("vg_instnorm_bwd", desc_b, dy, x.data, mean, rstd, self.gamma.w, self.beta.w, drop, dx, 1 if fuse else 0, dres,
-                 self.gamma.grad if p_needs else None, self.beta.grad if p_needs else None, ws2, ws_bytes,
+
+            def sink(v, ok):
+                """bias gradient of the convolution that produced v, when this norm is v's only consumer and the sweep wants it"""
+                if ok and v.bias_sink is not None and v.ncons == 1 and id(v.bias_sink) in tape.wrt and BIAS_SINKS:
+                    v.bias_done = True
+                    return v.bias_sink.grad
+                return None
+            sink_x = sink(x, in_needs[0] and not fuse)
+            sink_r = sink(residual, need_res) if residual is not None else None
+            call("vg_instnorm_bwd_sinks", desc_b, dy, x.data, mean, rstd, self.gamma.w, self.beta.w, drop, dx, 1 if fuse else 0, dres,
+                 self.gamma.grad if p_needs else None, self.beta.grad if p_needs else None, sink_x, sink_r, ws2, ws_bytes,
                  work=float(es * (2 * (nin + y.numel()) + nin * (2 if need_res else 1))))
             if in_needs[0] and not fuse:
                 accumulate(x, dx)
