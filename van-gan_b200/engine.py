@@ -18,12 +18,13 @@ from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH, PAD_REFLECT, PAD_ZERO
 
 DEV = "cuda"
 BIAS_SINKS = __import__("os").environ.get("VG_BIAS_SINKS", "1") != "0"   # conv bias gradients taken inside the consuming norm's backward
+STATS_REUSE = __import__("os").environ.get("VG_STATS_REUSE", "1") != "0"   # InstanceNorm statistics cached per tensor / derived for concats
 
 
 # ----------------------------------------------------------------------------- tape
 class Var:
     """A tensor on the tape.  `data`: torch CUDA tensor; `grad`: accumulated gradient or None."""
-    __slots__ = ("data", "grad", "src", "ncons", "bias_sink", "bias_done")
+    __slots__ = ("data", "grad", "src", "ncons", "bias_sink", "bias_done", "stats")
 
     def __init__(self, data, src=None):
         self.data = data
@@ -32,6 +33,7 @@ class Var:
         self.ncons = 0           # number of recorded consumers
         self.bias_sink = None    # bias Param of the convolution that produced this tensor (its gradient is the channel sum of ours)
         self.bias_done = False   # that channel sum was already taken by the consumer's backward kernel in this sweep
+        self.stats = None        # (mean, rstd) per (n, c) of this tensor once an InstanceNorm has computed them (re-used, see upsample_concat)
 
     @property
     def shape(self):
@@ -432,7 +434,12 @@ class InstanceNorm:
         rstd = torch.empty(n * c, dtype=torch.float32, device=DEV)
         # algorithmic HBM bytes: forward = read x twice (statistics, apply) + write y; backward = read x and dy twice + write dx
         es, nin = x.data.element_size(), x.data.numel()
-        call("vg_instnorm_stats", x.data, dt, n, d, h, w, c, mean, rstd, ws, ws_bytes, work=float(es * nin))
+        if x.stats is not None and not relu_input and STATS_REUSE:
+            mean, rstd = x.stats           # already known: the tensor was normalised before, or is a concat of tensors that were
+        else:
+            call("vg_instnorm_stats", x.data, dt, n, d, h, w, c, mean, rstd, ws, ws_bytes, work=float(es * nin))
+            if not relu_input:
+                x.stats = (mean, rstd)
         desc = InDesc(n, d, h, w, c, dt, act, slope, pad[0], pad[1], pad[2], noise_std if noise is None else 0.0, seed,
                       seed_dev.data_ptr() if seed_dev is not None else None)
         pp = pad[0] + pad[1]
@@ -569,6 +576,19 @@ def upsample_concat(tape, lo, skip):
     y = torch.empty((n, 2 * d, 2 * h, 2 * w, c0 + c1), dtype=torch.bfloat16, device=DEV)
     call("vg_upsample_concat", lo.data, skip.data, y, n, d, h, w, c0, c1)
     out = Var(y)
+    # InstanceNorm statistics of the concat without reading it: nearest-neighbour upsampling repeats every value 8 times, so the
+    # per-(n, c) mean and variance of the upsampled half are those of `lo` (1/8 of the voxels), and the skip half was normalised on
+    # the encoder side already (its statistics are cached on the Var)
+    if STATS_REUSE and skip.stats is not None:
+        if lo.stats is None:
+            ws_bytes = _lib.lib().vg_instnorm_workspace_bytes(n, d, h, w, c0)
+            ws = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
+            m0 = torch.empty(n * c0, dtype=torch.float32, device=DEV)
+            r0 = torch.empty(n * c0, dtype=torch.float32, device=DEV)
+            call("vg_instnorm_stats", lo.data, dtype_code(lo.data), n, d, h, w, c0, m0, r0, ws, ws_bytes,
+                 work=float(lo.data.element_size() * lo.data.numel()))
+            lo.stats = (m0, r0)
+        out.stats = tuple(torch.cat([a.view(n, c0), b.view(n, c1)], dim=1).reshape(-1).contiguous() for a, b in zip(lo.stats, skip.stats))
 
     def bwd(in_needs, p_needs):
         dlo = torch.empty_like(lo.data)
