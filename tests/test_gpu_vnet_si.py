@@ -102,10 +102,10 @@ def test_conv3d_transpose_k2s2(cuda, Cin, Cout, S, N):
     assert rel_l2(net.params["up.w"].grad, 2 * wr.grad) < 1e-4
 
 
-def _si_case(S, filters, L, N, seed=1):
+def _si_case(S, filters, L, N, seed=1, si=True):
     from oracle import nets as ON
     rng = np.random.default_rng(seed)
-    shapes = ON.vnet_param_shapes(filters, L, 1, use_batch_norm=True, deconv=True)
+    shapes = ON.vnet_param_shapes(filters, L, 1, use_batch_norm=si, deconv=si)
     init = ON.init_params(shapes, 5, 0.05)
     x = torch.tensor(rng.standard_normal((N, S, S, S, 1)), dtype=torch.float32).clamp(-1, 1)
     masks = ON.make_vnet_masks(rng, N, filters, L)
@@ -123,19 +123,21 @@ def test_param_shapes_match_oracle(cuda):
     assert sum(int(np.prod(s)) for s in vnet_param_shapes(32, 4, 1, False, 'upsample').values()) == 25888737   # gen_IS variant
 
 
-@pytest.mark.parametrize("S,filters,L,N", [(32, 16, 4, 2)])
-def test_vnet_si_blocks_teacher_forced(cuda, S, filters, L, N):
-    """Every stage of custom_vnet(use_batch_norm=True, upsample_mode='deconv') fed the CUDA path's own input to that stage: forward
-    at 2e-2, and -- with a given upstream gradient -- the input gradient and the stage's parameter gradients against the fp32 oracle."""
+@pytest.mark.parametrize("S,filters,L,N,si", [(32, 16, 4, 2, True), (32, 16, 4, 2, False)])
+def test_vnet_si_blocks_teacher_forced(cuda, S, filters, L, N, si):
+    """Every stage of custom_vnet -- si=True: the gen_SI variant (use_batch_norm=True, upsample_mode='deconv'); si=False: the gen_IS
+    variant (InstanceNormalization, UpSampling3D + Conv3D) -- fed the CUDA path's own input to that stage: forward at 2e-2, and, with a
+    given upstream gradient, the input gradient and the stage's parameter gradients against the fp32 oracle and against the oracle with
+    bf16 storage emulation (the per-stage gradient evidence the whole-network test of tests/test_gpu_vnet.py cannot give)."""
     import torch.nn.functional as F
     from oracle import nets as ON
     from van_gan_b200.vnet_model import custom_vnet
     from van_gan_b200 import engine as E
     from van_gan_b200._lib import PAD_REFLECT
-    rng, shapes, init, x, masks = _si_case(S, filters, L, N)
+    rng, shapes, init, x, masks = _si_case(S, filters, L, N, si=si)
     P = ON.to_torch(init)
-    net = custom_vnet((S, S, S, 1), use_batch_norm=True, upsample_mode='deconv', dropout=0.5, filters=filters, num_layers=L,
-                      output_activation='tanh')
+    net = custom_vnet((S, S, S, 1), use_batch_norm=si, upsample_mode='deconv' if si else 'upsample', dropout=0.5, filters=filters,
+                      num_layers=L, output_activation='tanh')
     net.load(init)
     taps = {}
     out = net.forward(E.Tape(enabled=False), E.Var(x.cuda()), training=True, masks=[m.cuda() for m in masks], taps=taps)
@@ -178,12 +180,15 @@ def test_vnet_si_blocks_teacher_forced(cuda, S, filters, L, N):
     prev = T["bridge"]
     for l in reversed(range(L)):
         with torch.no_grad():
-            u = ON.conv3d_transpose_k2s2(prev, P["dec%d.up.w" % l], P["dec%d.up.b" % l])
+            if si:
+                u = ON.conv3d_transpose_k2s2(prev, P["dec%d.up.w" % l], P["dec%d.up.b" % l])
+            else:
+                u = ON.conv3d(ON.upsample2(prev), P["dec%d.up.conv.w" % l], P["dec%d.up.conv.b" % l], padding="same")
         check_block("dec%d" % l, net.dec[l], torch.cat([bf(u), T["enc%d" % l]], dim=-1), None)
         prev = T["dec%d" % l]
     for r in report:
-        print("vnet gen_SI block %-7s fwd %.2e  dx %.2e  params %.2e   (bf16-storage oracle vs fp32 oracle: dx %.2e params %.2e;"
-              " CUDA vs bf16-storage oracle: dx %.2e params %.2e)" % r)
+        print("vnet %s block %-7s fwd %.2e  dx %.2e  params %.2e   (bf16-storage oracle vs fp32 oracle: dx %.2e params %.2e;"
+              " CUDA vs bf16-storage oracle: dx %.2e params %.2e)" % (("gen_SI" if si else "gen_IS",) + r))
     for name, e_f, e_x, e_p, f_x, f_p, v_x, v_p in report:
         assert v_x < LAYER_TOL and v_p < LAYER_TOL, (name, v_x, v_p)      # same arithmetic, same storage points: north_star's 2e-2
         # bound: the per-block figures of tests/test_gpu_parity_r2.py, or -- for the small deep stages, where a block holds only a few
@@ -196,6 +201,8 @@ def test_vnet_si_blocks_teacher_forced(cuda, S, filters, L, N):
     with torch.no_grad():
         ref = torch.tanh(ON.conv3d(prev, P["head.w"], P["head.b"], padding="same"))
     assert rel_l2(out.data, ref) < 2e-2, "head"
+    if not si:
+        return
     # the CUDA network's moving statistics after ONE training forward == the oracle's after one whole-network training forward
     state2 = ON.vnet_bn_state(filters, L)
     with torch.no_grad():
