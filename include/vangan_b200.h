@@ -228,6 +228,11 @@ int vg_batchnorm_bwd(const vg_instnorm_desc* d, const void* dy, const void* x, c
 int vg_conv3d_transpose_k2s2_scatter(const void* t, const float* bias, void* y, int N, int D, int H, int W, int Cout, void* stream);
 /* dt = space_to_depth(dy); dbias (optional, fp32[Cout]) += sum dy */
 int vg_conv3d_transpose_k2s2_gather(const void* dy, void* dt, float* dbias, int N, int D, int H, int W, int Cout, void* stream);
+/* 'resnet' generator (generator.py:7-73): UpSampling3D(2) + the zero padding of the Conv3D(k4, s1, 'same') that follows it
+ * (building_blocks.py:240-280; TF pads 1 before / 2 after): out[N, 2D+lo+hi, 2H+lo+hi, 2W+lo+hi, C] bf16, and its adjoint.  The 7x7x7
+ * convolutions of that generator (generator.py:38,67: one side has a single channel) go through vg_conv3d_fwd / dgrad / wgrad with K = 7. */
+int vg_upsample_pad(const void* a, void* out, int N, int D, int H, int W, int C, int lo, int hi, void* stream);
+int vg_upsample_pad_bwd(const void* dout, void* da, int N, int D, int H, int W, int C, int lo, int hi, void* stream);
 /* dir 0: gemm[Cin][8*Cout] = permute(keras[2][2][2][Cout][Cin]); dir 1: keras_grad += permute(gemm_grad) */
 int vg_conv3d_transpose_k2s2_weights(const float* src, float* dst, int Cin, int Cout, int dir, void* stream);
 

@@ -419,3 +419,87 @@ def vnet_forward(p, x, num_layers=4, masks=None, taps=None, bn_state=None, train
         if taps is not None:
             taps["dec%d" % l] = x
     return torch.tanh(conv3d(x, p["head.w"], p["head.b"], padding="same"))
+
+
+# --------------------------------------------------------------------------- 3D ResNet generator ('resnet', VanGan's default)
+def resnet_param_shapes(filters=32, num_downsampling_blocks=3, num_residual_blocks=6, num_upsample_blocks=3, cin=1):
+    """Trainable variables of get_resnet_generator (generator.py:7-73) in call order, with VanGan's arguments (vangan.py:88-95: three
+    downsampling and three upsampling blocks).  No convolution but the last has a bias (use_bias=False: generator.py:38,
+    building_blocks.py:77,135,248)."""
+    P = OrderedDict()
+
+    def inorm(name, c):
+        P[name + ".gamma"] = (c,); P[name + ".beta"] = (c,)
+
+    f = filters
+    P["c0.conv.w"] = (7, 7, 7, cin, f); inorm("c0.in", f)
+    for i in range(num_downsampling_blocks):
+        P["down%d.conv.w" % i] = (3, 3, 3, f, 2 * f); inorm("down%d.in" % i, 2 * f)
+        f *= 2
+    for j in range(num_residual_blocks):
+        for k in (1, 2):
+            P["res%d.c%d.conv.w" % (j, k)] = (3, 3, 3, f, f); inorm("res%d.c%d.in" % (j, k), f)
+    for i in range(num_upsample_blocks):
+        P["up%d.conv.w" % i] = (4, 4, 4, f, f // 2); inorm("up%d.in" % i, f // 2)
+        f //= 2
+    P["out.conv.w"] = (7, 7, 7, f, 1); P["out.conv.b"] = (1,)
+    return P
+
+
+def make_resnet_masks(rng, n, filters=32, num_downsampling_blocks=3, dtype=torch.float32):
+    """SpatialDropout3D masks in call order: rate 0.5 after the first block (generator.py:42), 0.2 inside every downsample block
+    (building_blocks.py:192-195), scaled by 1/(1-rate)."""
+    rates = [0.5] + [0.2] * num_downsampling_blocks
+    return [torch.tensor((rng.random((n, 1, 1, 1, filters * 2 ** i)) >= r) / (1.0 - r), dtype=dtype) for i, r in enumerate(rates)]
+
+
+def resnet_stage_c0(p, x, mask=None):
+    """generator.py:35-42: ReflectionPadding3D(1) -> Conv3D(7, valid) -> InstanceNorm -> ReLU -> SpatialDropout3D(0.5)"""
+    h = torch.relu(instance_norm(conv3d(reflect_pad(x), p["c0.conv.w"]), p["c0.in.gamma"], p["c0.in.beta"]))
+    return _qa(h if mask is None else h * mask)
+
+
+def resnet_stage_down(p, i, x, mask=None):
+    """building_blocks.downsample as called at generator.py:45-50: pad -> Conv3D(k3, s2, valid) -> IN -> ReLU -> SpatialDropout3D(0.2)"""
+    h = conv3d(reflect_pad(x), p["down%d.conv.w" % i], stride=2)
+    h = torch.relu(instance_norm(h, p["down%d.in.gamma" % i], p["down%d.in.beta" % i]))
+    return _qa(h if mask is None else h * mask)
+
+
+def resnet_stage_res(p, j, x):
+    """building_blocks.residual_block (:68-123)"""
+    h = conv3d(reflect_pad(x), p["res%d.c1.conv.w" % j])
+    h = _qa(torch.relu(instance_norm(h, p["res%d.c1.in.gamma" % j], p["res%d.c1.in.beta" % j])))
+    h = conv3d(reflect_pad(h), p["res%d.c2.conv.w" % j])
+    return _qa(x + instance_norm(h, p["res%d.c2.in.gamma" % j], p["res%d.c2.in.beta" % j]))
+
+
+def resnet_stage_up(p, i, x):
+    """building_blocks.upsample (:240-280): UpSampling3D(2) -> Conv3D(k4, s1, 'same') -> IN -> ReLU"""
+    h = conv3d(_qa(upsample2(x)), p["up%d.conv.w" % i], padding="same")
+    return _qa(torch.relu(instance_norm(h, p["up%d.in.gamma" % i], p["up%d.in.beta" % i])))
+
+
+def resnet_stage_out(p, x):
+    """generator.py:66-69 (num_downsampling_blocks == 3: no extra padding): Conv3D(1, 7, 'same') -> tanh"""
+    return torch.tanh(conv3d(x, p["out.conv.w"], p["out.conv.b"], padding="same"))
+
+
+def resnet_forward(p, x, nd=3, nr=6, nu=3, masks=None, taps=None):
+    """get_resnet_generator(num_downsampling_blocks=3, num_upsample_blocks=3) (generator.py:7-73).  masks=None: inference."""
+    h = resnet_stage_c0(p, x, None if masks is None else masks[0])
+    if taps is not None:
+        taps["c0"] = h
+    for i in range(nd):
+        h = resnet_stage_down(p, i, h, None if masks is None else masks[i + 1])
+        if taps is not None:
+            taps["down%d" % i] = h
+    for j in range(nr):
+        h = resnet_stage_res(p, j, h)
+        if taps is not None:
+            taps["res%d" % j] = h
+    for i in range(nu):
+        h = resnet_stage_up(p, i, h)
+        if taps is not None:
+            taps["up%d" % i] = h
+    return resnet_stage_out(p, h)

@@ -56,4 +56,4 @@ def test_seed_offsets_are_unique_per_step_and_replica():
             off = VanGan.seed_offset(1234, step, 8, rank)
             assert off % 64 == 0 and off not in seen
             seen.add(off)
-    assert VanGan.seed_offset(1234, 3, 1, 0) == (1234 * 1000003 + 3) * 64
+    assert VanGan.seed_offset(1234, 3, 1, 0) == (1234 * 1000003 + 3) * 128

@@ -177,6 +177,10 @@ CONV_CASES = [
     (16, 16, 3, 1, (34, 34, 66), 3), (32, 32, 3, 1, (34, 34, 34), 5),
     # fused parity-class stride-2 dgrad (Cin 16 / 32): two N blocks, k4 taps, odd extents
     (32, 64, 3, 2, (11, 9, 13), 1), (16, 32, 4, 2, (10, 12, 14), 1), (16, 32, 3, 2, (34, 18, 35), 2), (128, 256, 3, 2, (9, 7, 11), 2),
+    # 7^3 convolutions of the 'resnet' generator (generator.py:38,67): single-channel input / single-channel output (csrc/conv_k7.cu)
+    (1, 32, 7, 1, (14, 13, 16), 2), (32, 1, 7, 1, (13, 14, 15), 1), (16, 1, 7, 1, (9, 9, 12), 2),
+    # k4 s1 after UpSampling3D (building_blocks.upsample) at the resnet generator's widths
+    (256, 128, 4, 1, (7, 7, 7), 1), (128, 64, 4, 1, (11, 11, 11), 1), (64, 32, 4, 1, (19, 11, 13), 2), (32, 64, 3, 2, (15, 15, 17), 1),
 ]
 
 

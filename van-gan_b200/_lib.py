@@ -70,6 +70,8 @@ SIGNATURES = {
     "vg_batchnorm_bwd": (_I, [_ID, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
     "vg_conv3d_transpose_k2s2_scatter": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vg_conv3d_transpose_k2s2_gather": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vg_upsample_pad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vg_upsample_pad_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vg_conv3d_transpose_k2s2_weights": (_I, [_P, _P, _I, _I, _I, _P]),
     "vg_comm_available": (_I, []),
     "vg_comm_nccl_version": (_I, []),

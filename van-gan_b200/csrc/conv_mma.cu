@@ -23,6 +23,12 @@
 #include "pack_elem.cuh"
 #include "common.cuh"
 
+// conv_k7.cu
+int vg_k7_many_to_one(const bf16* M, const bf16* w, int w_tstride, const float* bias, float* y, int N, int MD, int MH, int MW, int C, int YD,
+                      int YH, int YW, int K, int sgn, int act, cudaStream_t st);
+int vg_k7_wgrad_one(const bf16* M, const float* S, float* dw, int N, int MD, int MH, int MW, int C, int SD, int SH, int SW, int K, int sgn,
+                    int off, cudaStream_t st);
+
 namespace {
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -777,7 +783,8 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
 
 inline bool desc_ok(const vg_conv3d_desc* d) {
     if (!d || d->N <= 0 || d->Cin <= 0 || d->Cout <= 0) return false;
-    if (!(d->K == 1 || d->K == 3 || d->K == 4)) return false;
+    if (!(d->K == 1 || d->K == 3 || d->K == 4 || d->K == 7)) return false;
+    if (d->K == 7 && !(d->stride == 1 && (d->Cin == 1 || d->Cout == 1))) return false;   // 'resnet' generator: conv_k7.cu
     if (!(d->stride == 1 || d->stride == 2)) return false;
     if (d->ID < d->K || d->IH < d->K || d->IW < d->K) return false;
     if (d->Cin == 1 ? d->x_dtype != VG_F32 : (d->x_dtype != VG_BF16 || d->Cin % 16)) return false;
@@ -969,9 +976,17 @@ int vg_conv3d_fwd(const vg_conv3d_desc* d, const void* x, const void* w_fwd, con
         else if (d->K == 4 && d->stride == 2) VG_CIN1_FWD(4, 2);
         else if (d->K == 3 && d->stride == 2) VG_CIN1_FWD(3, 2);
         else if (d->K == 4 && d->stride == 1) VG_CIN1_FWD(4, 1);
+        else if (d->K == 7 && d->stride == 1) VG_CIN1_FWD(7, 1);
         else return VG_ERR_UNSUPPORTED;
 #undef VG_CIN1_FWD
         VG_LAUNCHED(1);
+        VG_CHECK_LAUNCH();
+        return VG_OK;
+    }
+    if (d->K == 7) {   // Cout == 1 (Cin == 1 returned above): direct kernel on the bf16 forward pack [T][Np][Cin], column 0
+        int rc = vg_k7_many_to_one((const bf16*)x, (const bf16*)w_fwd, rup(d->Cout, NPAD) * d->Cin, bias, (float*)y, d->N, d->ID, d->IH, d->IW,
+                                   d->Cin, OD, OH, OW, d->K, +1, d->act, st);
+        if (rc != VG_OK) return rc;
         VG_CHECK_LAUNCH();
         return VG_OK;
     }
@@ -1025,6 +1040,13 @@ int vg_conv3d_dgrad(const vg_conv3d_desc* d, const void* dy, const void* w_dgrad
         return VG_OK;
     }
     const int s = d->stride;
+    if (d->K == 7) {   // Cin == 1 (Cout == 1 returned above): dx = sum over taps and channels of dy, on the bf16 dgrad pack [T][Np][Cout], row 0
+        int rc = vg_k7_many_to_one((const bf16*)dy, (const bf16*)w_dgrad, rup(d->Cin, NPAD) * d->Cout, nullptr, (float*)dx, d->N, OD, OH, OW,
+                                   d->Cout, d->ID, d->IH, d->IW, d->K, -1, VG_ACT_NONE, st);
+        if (rc != VG_OK) return rc;
+        VG_CHECK_LAUNCH();
+        return VG_OK;
+    }
     if (small_enabled() && d->Cin == 1 && s == 2 && d->x_dtype == VG_F32) {
         int rc = vg_small_cin1_dgrad_s2((const bf16*)dy, (const bf16*)w_dgrad, (float*)dx, d->N, d->ID, d->IH, d->IW, OD, OH, OW, d->Cout, d->K, st);
         if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
@@ -1088,6 +1110,21 @@ int vg_conv3d_wgrad(const vg_conv3d_desc* d, const void* x, const void* dy, floa
     cudaStream_t st = (cudaStream_t)stream;
     const int OD = odim(d->ID, d->K, d->stride), OH = odim(d->IH, d->K, d->stride), OW = odim(d->IW, d->K, d->stride);
     const size_t rows = (size_t)d->N * OD * OH * OW;
+    if (d->K == 7) {
+        if (dbias) {
+            if (d->Cout == 1) {
+                channel_sum_kernel<float><<<vg_grid_for(rows, 256, 2), 256, 32 * sizeof(float), st>>>((const float*)dy, rows, 1, dbias); VG_LAUNCHED(1);
+            } else {
+                channel_sum_kernel<bf16><<<vg_grid_for(rows, 32 * 4, 4), 256, (size_t)(256 / (d->Cout / 8)) * d->Cout * sizeof(float), st>>>(
+                    (const bf16*)dy, rows, d->Cout, dbias); VG_LAUNCHED(1);
+            }
+        }
+        int rc = d->Cin == 1 ? vg_k7_wgrad_one((const bf16*)dy, (const float*)x, dw, d->N, OD, OH, OW, d->Cout, d->ID, d->IH, d->IW, d->K, +1, 0, st)
+                             : vg_k7_wgrad_one((const bf16*)x, (const float*)dy, dw, d->N, d->ID, d->IH, d->IW, d->Cin, OD, OH, OW, d->K, -1, 0, st);
+        if (rc != VG_OK) return rc;
+        VG_CHECK_LAUNCH();
+        return VG_OK;
+    }
     if (d->Cin == 1) {
         VG_REQUIRE(d->Cout % 16 == 0);
         if (small_enabled()) {

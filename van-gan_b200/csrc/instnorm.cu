@@ -1027,8 +1027,9 @@ int stats_impl(const T* x, int N, int D, int H, int W, int C, float* mean, float
 extern "C" {
 
 size_t vg_instnorm_workspace_bytes(int N, int D, int H, int W, int C) {
-    // partials of the widest pass (the backward reduction walks the padded volume: up to (D+3)(H+3)(W+3)) + per-(n,c) sums
-    size_t nblk = (size_t)pick_grid((long long)(D + 3) * (H + 3) * (W + 3), N, C);
+    // partials of the widest pass (the backward reduction walks the padded volume: up to 3 + 3 voxels of padding per axis, the zeros
+    // of a 7^3 'same' convolution) + per-(n,c) sums
+    size_t nblk = (size_t)pick_grid((long long)(D + 6) * (H + 6) * (W + 6), N, C);
     return (size_t)N * nblk * C * 2 * sizeof(float) + (size_t)N * C * 2 * sizeof(float);
 }
 
@@ -1047,7 +1048,7 @@ int vg_instnorm_apply(const vg_instnorm_desc* d, const void* x, const void* resi
                       const float* rstd, const float* gamma, const float* beta, const float* drop, const float* noise,
                       void* stream) {
     VG_REQUIRE(d && x && y && mean && rstd && gamma && beta);
-    VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT && d->pad_lo >= 0 && d->pad_hi >= 0);
+    VG_REQUIRE(d->C % 8 == 0 && d->C <= 8 * NT && d->pad_lo >= 0 && d->pad_hi >= 0 && d->pad_lo <= 3 && d->pad_hi <= 3);
     if (d->pad_mode == VG_PAD_REFLECT && (d->pad_lo || d->pad_hi))
         VG_REQUIRE(d->pad_lo == 1 && d->pad_hi == 1 && d->D >= 2 && d->H >= 2 && d->W >= 2);
     const int dtype = d->dtype & ~(VG_IN_RELU_INPUT | VG_IN_BATCH_STATS | VG_IN_DY_SCRATCH);

@@ -270,6 +270,49 @@ __global__ void ct_weights_kernel(const float* __restrict__ src, float* __restri
     }
 }
 
+
+// UpSampling3D(2) followed by the zero padding of a TF-'same' convolution with an even kernel (k4 s1: 1 before, 2 after --
+// building_blocks.upsample, building_blocks.py:240-280): out[N, 2D+lo+hi, 2H+lo+hi, 2W+lo+hi, C] in one pass; and its adjoint
+// (da = sum of the 2x2x2 block of the interior of dout).
+__global__ void __launch_bounds__(NT) upsample_pad_kernel(const bf16* __restrict__ a, bf16* __restrict__ out, int N, int D, int H, int W, int C,
+                                                          int lo, int hi) {
+    const int cg = C / 8, PD = 2 * D + lo + hi, PH = 2 * H + lo + hi, PW = 2 * W + lo + hi;
+    const size_t total = (size_t)N * PD * PH * PW * cg;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        const int c8 = (int)(i % cg);
+        size_t v = i / cg;
+        const int pw = (int)(v % PW); v /= PW;
+        const int ph = (int)(v % PH); v /= PH;
+        const int pd = (int)(v % PD);
+        const int n = (int)(v / PD);
+        const int d = pd - lo, h = ph - lo, w = pw - lo;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)d < (unsigned)(2 * D) && (unsigned)h < (unsigned)(2 * H) && (unsigned)w < (unsigned)(2 * W))
+            val = *reinterpret_cast<const uint4*>(a + ((((size_t)n * D + (d >> 1)) * H + (h >> 1)) * W + (w >> 1)) * C + c8 * 8);
+        *reinterpret_cast<uint4*>(out + i * 8) = val;
+    }
+}
+
+__global__ void __launch_bounds__(NT) upsample_pad_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ da, int N, int D, int H, int W,
+                                                              int C, int lo, int hi) {
+    const int cg = C / 8, PH = 2 * H + lo + hi, PW = 2 * W + lo + hi, PD = 2 * D + lo + hi;
+    const size_t total = (size_t)N * D * H * W * cg;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        const int c8 = (int)(i % cg);
+        size_t v = i / cg;
+        const int w = (int)(v % W); v /= W;
+        const int h = (int)(v % H); v /= H;
+        const int d = (int)(v % D);
+        const int n = (int)(v / D);
+        float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int a = 0; a < 2; a++)
+            for (int b = 0; b < 2; b++)
+                for (int c = 0; c < 2; c++)
+                    add8(g, dout + ((((size_t)n * PD + 2 * d + a + lo) * PH + 2 * h + b + lo) * PW + 2 * w + c + lo) * C + c8 * 8);
+        store8<bf16>(da + i * 8, g);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -338,6 +381,22 @@ int vg_conv3d_transpose_k2s2_gather(const void* dy, void* dt, float* dbias, int 
 int vg_conv3d_transpose_k2s2_weights(const float* src, float* dst, int Cin, int Cout, int dir, void* stream) {
     VG_REQUIRE(src && dst && Cin > 0 && Cout > 0 && (dir == 0 || dir == 1));
     ct_weights_kernel<<<vg_cdiv(8 * Cin * Cout, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, Cin, Cout, dir); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_upsample_pad(const void* a, void* out, int N, int D, int H, int W, int C, int lo, int hi, void* stream) {
+    VG_REQUIRE(a && out && N > 0 && D > 0 && H > 0 && W > 0 && C % 8 == 0 && lo >= 0 && hi >= 0);
+    const long long total = (long long)N * (2 * D + lo + hi) * (2 * H + lo + hi) * (2 * W + lo + hi) * (C / 8);
+    upsample_pad_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>((const bf16*)a, (bf16*)out, N, D, H, W, C, lo, hi); VG_LAUNCHED(1);
+    VG_CHECK_LAUNCH();
+    return VG_OK;
+}
+
+int vg_upsample_pad_bwd(const void* dout, void* da, int N, int D, int H, int W, int C, int lo, int hi, void* stream) {
+    VG_REQUIRE(dout && da && N > 0 && D > 0 && H > 0 && W > 0 && C % 8 == 0 && lo >= 0 && hi >= 0);
+    const long long total = (long long)N * D * H * W * (C / 8);
+    upsample_pad_bwd_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>((const bf16*)dout, (bf16*)da, N, D, H, W, C, lo, hi); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }

@@ -331,7 +331,7 @@ def glorot_uniform(rng, shape):
     return rng.uniform(-lim, lim, size=shape).astype(np.float32)
 
 
-def default_init(shapes, seed, glorot=()):
+def default_init(shapes, seed, glorot=(), he_gamma=False):
     """Initial values by the reference's initializers: he_normal kernels, zero biases / betas, unit gammas; the variables named in
     `glorot` (name or name prefix) are the ones the reference builds with Keras' default glorot_uniform -- the ResUNet stem convolutions
     and head (resunet_model.py:90,92,96,245), the PatchGAN's InstanceNormalization gammas (gamma_initializer=None, discriminator.py:70,
@@ -344,7 +344,8 @@ def default_init(shapes, seed, glorot=()):
         elif n.endswith(".w"):
             out[n] = he_normal(rng, shp)
         elif n.endswith(".gamma"):
-            out[n] = np.ones(shp, np.float32)
+            # gamma_initializer='he_normal' (generator.py:14): a 1-D variable has fan_in = its length
+            out[n] = he_normal(rng, (shp[0], shp[0]))[0].copy() if he_gamma else np.ones(shp, np.float32)
         else:
             out[n] = np.zeros(shp, np.float32)
     return out
@@ -649,6 +650,24 @@ def gather_pad(tape, a, b, up=1, pad=0, mode=PAD_ZERO):
             accumulate(b, db)
 
     tape.record(ins, [out], [], bwd, "gather_pad")
+    return out
+
+
+def upsample_pad(tape, x, lo, hi):
+    """UpSampling3D(2) + the zero padding (lo before / hi after) of the 'same' convolution that follows (building_blocks.py:240-280)."""
+    n, d, h, w, c = x.shape
+    pp = lo + hi
+    y = torch.empty((n, 2 * d + pp, 2 * h + pp, 2 * w + pp, c), dtype=torch.bfloat16, device=DEV)
+    call("vg_upsample_pad", x.data, y, n, d, h, w, c, lo, hi)
+    out = Var(y)
+
+    def bwd(in_needs, p_needs):
+        if in_needs[0]:
+            dx = torch.empty_like(x.data)
+            call("vg_upsample_pad_bwd", out.grad, dx, n, d, h, w, c, lo, hi)
+            accumulate(x, dx)
+
+    tape.record([x], [out], [], bwd, "upsample_pad")
     return out
 
 

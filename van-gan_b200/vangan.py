@@ -3,8 +3,8 @@
 Kept from the reference: the constructor signature, the attribute names the loss functions read,
 `compute_losses`, `train_step`, `test_step`, `distributed_train_step`, `distributed_test_step`,
 `reduce_dict`, the ten result-dict keys (vangan.py:338-351) and the order of the four optimizer
-updates (vangan.py:426-438).  Only the LSGAN / resUnet configuration that main.py runs
-(main.py:196-200) is built; the other branches raise.
+updates (vangan.py:426-438).  Built: the LSGAN branch with any of the three generator families ('resnet' -- the constructor's
+default --, 'resUnet' -- what main.py:196-200 runs --, 'vnet'); the Wasserstein / gradient-penalty branch raises.
 """
 import os
 
@@ -16,6 +16,7 @@ from .discriminator import get_discriminator
 from .distribute import Strategy
 from .loss_functions import (LossContext, cycle_loss, cycle_reconstruction, cycle_seg_loss, discriminator_loss_fn,
                              generator_loss_fn)
+from .generator import ResNetGenerator, get_resnet_generator
 from .resunet_model import ResUNet
 from .vnet_model import VNetModel, custom_vnet
 
@@ -67,10 +68,12 @@ class VanGan:
         self.keep_last = False   # tests set this to inspect fake/cycled volumes after a step
 
         with self.strategy.scope():
-            if gen_i2s not in ('resUnet', 'vnet') or gen_s2i not in ('resUnet', 'vnet'):
-                raise NotImplementedError("generators: 'resUnet' (what main.py:196-200 selects) and 'vnet' (vangan.py:97-110 for "
-                                          "gen_i2s, :135-149 for gen_s2i) are built; 'resnet' is listed under next steps in DESIGN.md")
-            if gen_i2s == 'vnet':
+            if gen_i2s not in ('resUnet', 'vnet', 'resnet') or gen_s2i not in ('resUnet', 'vnet', 'resnet'):
+                raise ValueError('Generator type not recognised')      # vangan.py:124,164
+            if gen_i2s == 'resnet':
+                self.gen_IS = get_resnet_generator(input_img_size=self.subvol_patch_size, batch_size=self.global_batch_size,
+                                                   name='generator_IS', num_downsampling_blocks=3, num_upsample_blocks=3, seed=seed)
+            elif gen_i2s == 'vnet':
                 self.gen_IS = custom_vnet(input_shape=self.subvol_patch_size, activation='relu', use_batch_norm=False,
                                           upsample_mode='upsample', dropout=0.5, dropout_change_per_layer=0.0,
                                           dropout_type='spatial', use_dropout_on_upsampling=False, use_attention_gate=False,
@@ -79,7 +82,10 @@ class VanGan:
                 self.gen_IS = ResUNet(input_shape=self.subvol_patch_size, upsample_mode='simple', dropout=0.1,
                                       dropout_change_per_layer=0.1, dropout_type='none', use_attention_gate=False,
                                       filters=16, num_layers=4, name='generator_IS', seed=seed)
-            if gen_s2i == 'vnet':
+            if gen_s2i == 'resnet':
+                self.gen_SI = get_resnet_generator(input_img_size=self.subvol_patch_size, batch_size=self.global_batch_size,
+                                                   name='generator_SI', num_downsampling_blocks=3, num_upsample_blocks=3, seed=seed + 1)
+            elif gen_s2i == 'vnet':
                 self.gen_SI = custom_vnet(input_shape=self.subvol_patch_size, activation='relu', use_batch_norm=True,
                                           upsample_mode='deconv', dropout=0.5, dropout_change_per_layer=0.0,
                                           dropout_type='spatial', use_dropout_on_upsampling=False, use_attention_gate=False,
@@ -136,6 +142,8 @@ class VanGan:
         """One generator application; the V-Net variant draws its SpatialDropout3D masks per (step, application)."""
         if isinstance(net, VNetModel):
             return net.forward(tape, x, training=training, seed=self.step * 4 + app)
+        if isinstance(net, ResNetGenerator):      # SpatialDropout3D masks: per-application key + the per-step device offset (graph-safe)
+            return net.forward(tape, x, training=training, seed=4 + app, seed_dev=self._seed_dev)
         return net.forward(tape, x)
 
     def _disc(self, net, tape, x, training, rand, key, app):
@@ -240,11 +248,12 @@ class VanGan:
 
     @staticmethod
     def seed_offset(seed, step, world=1, rank=0):
-        """Offset added to every in-kernel Philox key of one step.  A (step, replica) pair owns a block of 64 keys (the four
-        discriminator applications use key = application * 16 + layer), so draws differ per step AND per replica --
+        """Offset added to every in-kernel Philox key of one step.  A (step, replica) pair owns a block of 128 keys (the four
+        discriminator applications use key = application * 16 + layer, the 'resnet' generator applications (4 + application) * 16 +
+        dropout layer), so draws differ per step AND per replica --
         MirroredStrategy draws GaussianNoise / SpatialDropout3D independently on every replica -- while `seed` itself, which
         also initialises the weights, stays shared across ranks."""
-        return ((seed * 1000003 + step) * world + rank) * 64
+        return ((seed * 1000003 + step) * world + rank) * 128
 
     def _upload_step_state(self):
         """Seed offset and the four Adam step sizes of THIS step -> device (async copies on the current stream)."""
