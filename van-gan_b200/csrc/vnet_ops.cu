@@ -266,7 +266,7 @@ __global__ void ct_weights_kernel(const float* __restrict__ src, float* __restri
         const int ci = i % Cin, co = (i / Cin) % Cout, pos = i / (Cin * Cout);        // i indexes the Keras layout
         const int j = ci * (8 * Cout) + pos * Cout + co;                               // the GEMM layout
         if (dir == 0) dst[j] = src[i];
-        else dst[i] += src[j];
+        else atomicAdd(dst + i, src[j]);   // sub-sweeps of one network may fold their kernel gradients concurrently
     }
 }
 

@@ -82,6 +82,11 @@ class Scalar:
 
     __rmul__ = __mul__
 
+    def part(self, *idx):
+        """The same scalar restricted (for the BACKWARD pass only) to the gradient terms idx of its sum: backward is linear in the
+        seeds, so a loss may be swept as several independent parts (vangan._sweeps runs them on separate streams)."""
+        return Scalar(self.ctx, self.value_fn, [self.grad_fns[i] for i in idx])
+
     def __float__(self):
         return float(self.value_fn(self.ctx.values()))
 

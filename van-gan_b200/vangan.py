@@ -119,9 +119,13 @@ class VanGan:
         # side streams forked from / joined to the caller's stream by events, so small kernels of one branch fill the SMs another
         # leaves idle (per-GPU batch 1 on 8 GPUs); VG_STREAMS=0 keeps everything on one stream
         self.use_streams = os.environ.get("VG_STREAMS", "1") != "0"
-        self._side = [torch.cuda.Stream() for _ in range(4)] if self.use_streams else None
+        self._side = [torch.cuda.Stream() for _ in range(8)] if self.use_streams else None
         # one more stream per sweep for the weight-gradient kernels (VG_WG_STREAM=0 disables)
-        self._wg_side = [torch.cuda.Stream() for _ in range(4)] if (self.use_streams and os.environ.get("VG_WG_STREAM", "1") != "0") else None
+        self._wg_side = [torch.cuda.Stream() for _ in range(8)] if (self.use_streams and os.environ.get("VG_WG_STREAM", "1") != "0") else None
+        # VG_SPLIT_SWEEPS=1: every loss swept as its independent parts (8 sweeps side by side).  Measured (call 38): b=8 175.0 -> 176.6
+        # ms, b=1 32.3 -> 31.5 ms -- the SMs are already busy with four sweeps, and the extra concurrent atomics widen the run-to-run
+        # spread of the gradients -- so the default stays one sweep per network.
+        self.split_sweeps = self.use_streams and os.environ.get("VG_SPLIT_SWEEPS", "0") == "1"
         # CUDA graph of one full train step (captured on the third eligible call; VG_GRAPH=0 disables)
         self.use_graph = os.environ.get("VG_GRAPH", "1") != "0" and not isinstance(self.gen_IS, VNetModel) and not isinstance(self.gen_SI, VNetModel)
         self._graph = None
@@ -164,9 +168,9 @@ class VanGan:
         # C = disc_S (real, then fake), D = disc_I.  They meet only where one consumes another's generated volume.
         main = torch.cuda.current_stream()
         par = self._side is not None and rand is None
-        sA, sB, sC, sD = self._side if par else (main, main, main, main)
+        sA, sB, sC, sD = self._side[:4] if par else (main, main, main, main)
         if par:
-            self._fork(main, self._side)
+            self._fork(main, self._side[:4])
         with torch.cuda.stream(sA):
             fake_S = self._gen(self.gen_IS, tape, real_I, training, 0)
         with torch.cuda.stream(sB):
@@ -197,7 +201,7 @@ class VanGan:
             gen_SI_loss = self.generator_loss_fn(self, disc_fake_I, from_logits=True)
             disc_I_loss = self.discriminator_loss_fn(self, disc_real_I, disc_fake_I, from_logits=True)
         if par:
-            self._join(main, self._side)
+            self._join(main, self._side[:4])
 
         total_loss_I = gen_IS_loss + cycle_loss_I + seg_loss
         total_loss_S = gen_SI_loss + cycle_loss_S + reconstruction_loss
@@ -225,26 +229,46 @@ class VanGan:
             main.wait_event(ev)
 
     def _sweeps(self, pairs, overlap_allreduce):
-        """Backward sweeps of `pairs` = [(net, loss), ...], one side stream each (they share only read-only activations and
-        weights; every sweep writes its own network's gradient buffer and its own temporaries).  Returns the all-reduce handles."""
+        """Backward sweeps of `pairs` = [(net, [loss part, ...]), ...].  Every PART is swept on its own side stream: the parts of one
+        loss seed different tensors (a generator's adversarial term reaches it through the discriminator and its first application, its
+        cycle terms through the second application; a discriminator's real and fake terms through its two applications), backward is
+        linear in the seeds, parts share only read-only activations and weights, and every parameter-gradient kernel accumulates with
+        atomics -- so they run side by side.  A network's all-reduce is enqueued once all of its parts are done."""
         main = torch.cuda.current_stream()
-        sides = self._side[:len(pairs)] if (self._side is not None and len(pairs) > 1) else None
+        nparts = sum(len(parts) for _net, parts in pairs)
+        sides = self._side[:nparts] if (self._side is not None and nparts > 1) else None
         handles = []
+        for net, _parts in pairs:
+            net.zero_grad()
         if sides is not None:
             self._fork(main, sides)
-        for i, (net, loss) in enumerate(pairs):
-            with torch.cuda.stream(sides[i] if sides is not None else main):
-                self.tape.wg_stream = self._wg_side[i] if self._wg_side is not None else None
-                self._sweep(net, loss)
-                self.tape.wg_stream = None
-                # MirroredStrategy's gradient all-reduce: enqueued on the communication stream as soon as this sweep ends
+        k = 0
+        for net, parts in pairs:
+            first = k
+            for part in parts:
+                with torch.cuda.stream(sides[k] if sides is not None else main):
+                    self.tape.wg_stream = self._wg_side[k] if (self._wg_side is not None and sides is not None) else None
+                    self.tape.backward(part.seeds(), net.trainable_variables)
+                    self.tape.wg_stream = None
+                k += 1
+            with torch.cuda.stream(sides[first] if sides is not None else main):
+                if sides is not None and k - first > 1:
+                    self._join(torch.cuda.current_stream(), sides[first + 1:k])
+                # MirroredStrategy's gradient all-reduce: enqueued on the communication stream as soon as this network's sweeps end
                 handles.append(self.strategy.all_reduce_async(net.g) if overlap_allreduce else None)
         if sides is not None:
             self._join(main, sides)
         return handles
 
     def _plan(self, total_I, total_S, dI, dS):
-        return ((self.gen_IS, total_I), (self.gen_SI, total_S), (self.disc_I, dI), (self.disc_S, dS))
+        """(network, parts of the loss its `minimize` differentiates) in the reference's order (vangan.py:426-438).  total_loss_I =
+        gen_IS_loss + cycle_loss_I + seg_loss: the first term seeds disc_S(fake_S), the other two seed cycled_S; the discriminator
+        losses are MSE(1, D(real)) + MSE(0, D(fake)), one term per application."""
+        if not self.split_sweeps:
+            return ((self.gen_IS, [total_I]), (self.gen_SI, [total_S]), (self.disc_I, [dI]), (self.disc_S, [dS]))
+        assert len(total_I.grad_fns) == 3 and len(total_S.grad_fns) == 3 and len(dI.grad_fns) == 2 and len(dS.grad_fns) == 2
+        return ((self.gen_IS, [total_I.part(0), total_I.part(1, 2)]), (self.gen_SI, [total_S.part(0), total_S.part(1, 2)]),
+                (self.disc_I, [dI.part(0), dI.part(1)]), (self.disc_S, [dS.part(0), dS.part(1)]))
 
     @staticmethod
     def seed_offset(seed, step, world=1, rank=0):
@@ -394,6 +418,10 @@ class VanGan:
     def _sweep(self, net, loss):
         net.zero_grad()
         self.tape.backward(loss.seeds(), net.trainable_variables)
+
+    def backward_of(self, net, loss):
+        """one sweep of `loss` w.r.t. the variables of `net` on the current stream (tests)"""
+        self._sweep(net, loss)
 
     def _replay(self, real_I, real_S):
         g = self._graph
