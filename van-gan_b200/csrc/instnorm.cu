@@ -1001,7 +1001,12 @@ inline int block_threads(int C) { int cg = C / 8; return (NT / cg) * cg; }
 // blocks per sample for a pass over `vox` voxels: ~8 waves of 148 SMs over the whole batch, at least U voxels per lane
 inline int pick_grid(long long vox, int N, int C) {
     long long nvl = block_threads(C) / (C / 8);
-    long long want = (148 * 8 + N - 1) / N;
+    // ~8 k voxels per block: between one resident round (2 blocks per SM) for small batches -- a block's prologue (per-channel
+    // constants) and epilogue (block reduction) cost ~3 us, as much as streaming 4 k voxels -- and 8 waves for the large ones
+    long long total = vox * N / 8192;
+    if (total < 148 * 2) total = 148 * 2;
+    if (total > 148 * 8) total = 148 * 8;
+    long long want = (total + N - 1) / N;
     long long maxb = (vox + nvl * U - 1) / (nvl * U);
     if (want > maxb) want = maxb;
     return want < 1 ? 1 : (int)want;
