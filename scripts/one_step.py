@@ -5,7 +5,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import Args, synth_batch
 from van_gan_b200.vangan import VanGan
-S, b = 128, 8
+S, b = 128, (int(sys.argv[1]) if len(sys.argv) > 1 else 8)
 I, Sg = synth_batch(b, S, 100)
 gan = VanGan(Args(S, b, 1), gen_i2s='resUnet', gen_s2i='resUnet', seed=1234)
 gan.use_graph = False

@@ -353,8 +353,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgParams 
                     const int r = blk / p.NW, tw = p.NW > 1 ? blk - r * p.NW : twq;
                     const int td = fold ? p.K - 1 - r : tdq;
                     float* o = p.dw + ((size_t)((td * p.K + th) * p.K + tw) * p.Cx + ci) * p.Cy + cob * p.CO + col;
+                    // 16-byte vector reductions (sm_90+): a quarter of the atomic requests -- the epilogue's ksplit x |dW| atomics are
+                    // a FIXED cost per call (the deep layers at b = 1 spent most of their ~75 us there)
 #pragma unroll
-                    for (int e = 0; e < 16; e++) atomicAdd(o + e, __uint_as_float(v[e]));
+                    for (int e = 0; e < 16; e += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(o + e), "f"(__uint_as_float(v[e])),
+                                     "f"(__uint_as_float(v[e + 1])), "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
+                                     : "memory");
                 }
             }
         }
