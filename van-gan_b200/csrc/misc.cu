@@ -164,27 +164,40 @@ __device__ __forceinline__ int find_seg(const long long* __restrict__ off, int n
     return lo;
 }
 
-// per-variable squared norms: flat grid-stride pass; a warp that sits inside one variable issues one atomic
+// per-variable squared norms: a warp owns runs of 4096 consecutive elements and keeps its partial sum while it stays inside one
+// variable -- one double atomic per (run, variable) instead of one per 128 elements (the large variables serialised ~80 k atomics on
+// a handful of addresses: 0.125 ms per network for 40 MB of reads)
 __global__ void __launch_bounds__(NT) seg_sqnorm_kernel(const float* __restrict__ g, const long long* __restrict__ off, int nseg,
                                                         double* __restrict__ norms, long long total) {
-    for (long long base = ((long long)blockIdx.x * NT + (threadIdx.x & ~31)) * 4; base < total; base += (long long)gridDim.x * NT * 4) {
-        // each warp owns 128 consecutive elements
-        int s0 = find_seg(off, nseg, base);
-        long long end = base + 128 < total ? base + 128 : total;
-        bool uniform = off[s0 + 1] >= end;
+    constexpr long long CH = 4096;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * NT + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * NT) >> 5;
+    for (long long chunk = warp * CH; chunk < total; chunk += nwarps * CH) {
+        const long long cend = chunk + CH < total ? chunk + CH : total;
+        int cur = -1;
         double acc = 0;
-        for (int k = 0; k < 4; k++) {
-            long long i = base + k * 32 + (threadIdx.x & 31);
-            if (i < total) {
-                float v = g[i];
-                if (uniform) acc += (double)v * v;
-                else atomicAdd(norms + find_seg(off, nseg, i), (double)v * v);
+        for (long long base = chunk; base < cend; base += 128) {
+            const int s0 = find_seg(off, nseg, base);
+            const long long end = base + 128 < cend ? base + 128 : cend;
+            const bool uniform = off[s0 + 1] >= end;     // warp-uniform
+            if (uniform && s0 != cur) {
+                acc = warp_sum_d(acc);
+                if (lane == 0 && cur >= 0 && acc != 0.0) atomicAdd(norms + cur, acc);
+                cur = s0;
+                acc = 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const long long i = base + k * 32 + lane;
+                if (i < end) {
+                    const float v = g[i];
+                    if (uniform) acc += (double)v * v;
+                    else atomicAdd(norms + find_seg(off, nseg, i), (double)v * v);
+                }
             }
         }
-        if (uniform) {
-            acc = warp_sum_d(acc);
-            if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(norms + s0, acc);
-        }
+        acc = warp_sum_d(acc);
+        if (lane == 0 && cur >= 0 && acc != 0.0) atomicAdd(norms + cur, acc);
     }
 }
 
@@ -487,7 +500,7 @@ static int clip_adam_impl(float* w, const float* g, float* m, float* v, const lo
     VG_REQUIRE(w && g && m && v && seg_offsets && nseg > 0 && total > 0 && norm_ws);
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(norm_ws, 0, (size_t)nseg * sizeof(double), st) != cudaSuccess) return VG_ERR_CUDA;
-    seg_sqnorm_kernel<<<vg_grid_for(total / 4 + 1, NT, 8), NT, 0, st>>>(g, seg_offsets, nseg, norm_ws, total); VG_LAUNCHED(1);
+    seg_sqnorm_kernel<<<vg_grid_for(total / 128 + 1, NT, 8), NT, 0, st>>>(g, seg_offsets, nseg, norm_ws, total); VG_LAUNCHED(1);
     clip_adam_kernel<<<vg_grid_for((total + 3) / 4, NT, 16), NT, 0, st>>>(w, g, m, v, seg_offsets, nseg, norm_ws, lr_t, beta1, beta2, eps,
                                                                clipnorm, total, lr_t_dev); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
