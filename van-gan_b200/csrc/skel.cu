@@ -409,6 +409,138 @@ skel_level_fwd_v4_kernel(const float* __restrict__ e_in, float* __restrict__ e_o
     }
 }
 
+// ------------------------------------------------------------------------------------------ z-marching routing kernel (backward)
+// Same result as skel_bwd_route_kernel up to the order of the floating-point additions:
+//   D_j[q] = a_j[q] + sum_{p: argmin over N19(p) of e_j is q} D_{j+1}[p] - sum_{p: argmax over N27(p) of e_j is q} a_{j-1}[p]
+// with "arg" = FIRST extreme in the scan order (dz, dy, dx) (the pooling gradient's tie rule).  The first extreme over a box is found
+// separably -- first over dx inside a row, then the first row over dy, then the first plane over dz; a strict comparison keeps the
+// earlier candidate, so the lexicographic order survives every stage.  The 19-neighbourhood is the cross {(-1,0),(0,-1),(0,0),(0,1),
+// (1,0)} in the planes dz = -1, +1 and the full 3x3 in the plane dz = 0; in scan order the cross is: row-above centre, the row's own
+// three, row-below centre.  A thread owns an (x, y) column and marches along z (x neighbours by shuffle, y neighbours through one
+// shared-memory row exchange per plane, z windows in registers); every window then SCATTERS its two values to its two winners with
+// shared-memory atomics into a 4-plane ring of accumulators, and a plane is written out once the windows of its three neighbouring
+// planes have scattered.  ~90 instructions per voxel and level instead of the ~130 shared-memory loads of the tile kernel.
+struct Cand {
+    float v;
+    int code;   // (dy + 1) * 3 + (dx + 1), or -1 = none
+};
+__device__ __forceinline__ void first_min(Cand& best, float v, int code) {
+    if (v < best.v) { best.v = v; best.code = code; }
+}
+__device__ __forceinline__ void first_max(Cand& best, float v, int code) {
+    if (v > best.v) { best.v = v; best.code = code; }
+}
+
+constexpr int RM_ROWS = 20, RM_OUT = RM_ROWS - 4, RM_THREADS = 32 * RM_ROWS;
+
+__global__ void __launch_bounds__(RM_THREADS, 2)
+skel_bwd_route_march_kernel(const float* __restrict__ ej, const float* __restrict__ a_j, const float* __restrict__ D_next,
+                            const float* __restrict__ a_prev, float* __restrict__ D_out, Vol v, int tiles_x, int tiles_y, int zchunks,
+                            int ZL) {
+    __shared__ float sV[2][RM_ROWS + 2][32], sMinV[2][RM_ROWS + 2][32], sMaxV[2][RM_ROWS + 2][32];
+    __shared__ int sIdx[2][RM_ROWS + 2][32];
+    __shared__ float sAcc[4][RM_ROWS + 2][34];
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    int t = blockIdx.x;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y; t /= tiles_y;
+    const int zc = t % zchunks;
+    const int n = t / zchunks;
+    const int gx = tx * MW_OUT - 2 + lane, gy = ty * RM_OUT - 2 + wy;
+    const int z0 = zc * ZL, zend = min(z0 + ZL, v.D);
+    const bool col_in = (unsigned)gx < (unsigned)v.W && (unsigned)gy < (unsigned)v.H;
+    const bool win_thread = col_in && lane >= 1 && lane < 31 && wy >= 1 && wy < RM_ROWS - 1;     // window centres: halo 1
+    const bool out_thread = col_in && lane >= 2 && lane < 30 && wy >= 2 && wy < RM_ROWS - 2;
+    const size_t HW = (size_t)v.H * v.W;
+    const size_t col = (size_t)n * v.D * HW + (size_t)(col_in ? gy : 0) * v.W + (col_in ? gx : 0);
+    const float QNAN = __int_as_float(0x7fc00000);
+    for (int i = threadIdx.x; i < 4 * (RM_ROWS + 2) * 34; i += RM_THREADS) (&sAcc[0][0][0])[i] = 0.f;
+    if (wy == 0) {
+        for (int b = 0; b < 2; b++) {
+            sV[b][0][lane] = QNAN; sV[b][RM_ROWS + 1][lane] = QNAN;
+            sMinV[b][0][lane] = QNAN; sMinV[b][RM_ROWS + 1][lane] = QNAN;
+            sMaxV[b][0][lane] = QNAN; sMaxV[b][RM_ROWS + 1][lane] = QNAN;
+            sIdx[b][0][lane] = 0; sIdx[b][RM_ROWS + 1][lane] = 0;
+        }
+    }
+    __syncthreads();
+    auto loadv = [&](int pz) -> float {   // NaN outside the volume: never wins a strict comparison
+        return (col_in && pz >= 0 && pz < v.D) ? __ldg(ej + col + (size_t)pz * HW) : QNAN;
+    };
+    const unsigned FULL = 0xffffffffu;
+    // per-plane candidates of the last three planes (index 0 = oldest): cross minimum, 3x3 minimum, 3x3 maximum
+    Cand c5[3], m9n[3], m9x[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        c5[k] = Cand{INFINITY, -1}; m9n[k] = Cand{INFINITY, -1}; m9x[k] = Cand{-INFINITY, -1};
+    }
+    float vnext = loadv(z0 - 2);
+    for (int i = 0; i < ZL + 4; i++) {
+        const int pz = z0 - 2 + i, buf = i & 1;
+        const float vA = vnext;
+        vnext = loadv(pz + 1);
+        // window centre plane c = pz - 1 and output plane o = pz - 2: fetch their values early
+        const int c = pz - 1, o = pz - 2;
+        const bool win_ok = win_thread && c >= 0 && c < v.D && c >= z0 - 1 && c <= zend;
+        float Dn = 0.f, ap = 0.f, aj = 0.f;
+        if (win_ok) {
+            const size_t g = col + (size_t)c * HW;
+            if (D_next) Dn = __ldg(D_next + g);
+            if (a_prev) ap = __ldg(a_prev + g);
+        }
+        const bool out_ok = out_thread && o >= z0 && o < zend;
+        if (out_ok && a_j) aj = __ldg(a_j + col + (size_t)o * HW);
+        // ---- x stage of plane pz: first minimum / maximum over dx = -1, 0, +1
+        const float L = __shfl_up_sync(FULL, vA, 1), R = __shfl_down_sync(FULL, vA, 1);
+        Cand rn{INFINITY, -1}, rx{-INFINITY, -1};
+        if (lane > 0) { first_min(rn, L, 0); first_max(rx, L, 0); }
+        first_min(rn, vA, 1); first_max(rx, vA, 1);
+        if (lane < 31) { first_min(rn, R, 2); first_max(rx, R, 2); }
+        sV[buf][wy + 1][lane] = vA;
+        sMinV[buf][wy + 1][lane] = rn.code >= 0 ? rn.v : QNAN;
+        sMaxV[buf][wy + 1][lane] = rx.code >= 0 ? rx.v : QNAN;
+        sIdx[buf][wy + 1][lane] = (rn.code & 3) | ((rx.code & 3) << 2);
+        __syncthreads();
+        // ---- y stage of plane pz
+        const float vU = sV[buf][wy][lane], vD = sV[buf][wy + 2][lane];
+        const float nU = sMinV[buf][wy][lane], nD = sMinV[buf][wy + 2][lane];
+        const float xU = sMaxV[buf][wy][lane], xD = sMaxV[buf][wy + 2][lane];
+        const int iU = sIdx[buf][wy][lane], iD = sIdx[buf][wy + 2][lane];
+        Cand cross{INFINITY, -1}, mn{INFINITY, -1}, mx{-INFINITY, -1};
+        first_min(cross, vU, 0 * 3 + 1);                       // (dy, dx) = (-1, 0)
+        if (rn.code >= 0) first_min(cross, rn.v, 1 * 3 + rn.code);   // row y: its first minimum over dx
+        first_min(cross, vD, 2 * 3 + 1);                       // (+1, 0)
+        first_min(mn, nU, 0 * 3 + (iU & 3));
+        if (rn.code >= 0) first_min(mn, rn.v, 1 * 3 + rn.code);
+        first_min(mn, nD, 2 * 3 + (iD & 3));
+        first_max(mx, xU, 0 * 3 + ((iU >> 2) & 3));
+        if (rx.code >= 0) first_max(mx, rx.v, 1 * 3 + rx.code);
+        first_max(mx, xD, 2 * 3 + ((iD >> 2) & 3));
+        c5[0] = c5[1]; c5[1] = c5[2]; c5[2] = cross;
+        m9n[0] = m9n[1]; m9n[1] = m9n[2]; m9n[2] = mn;
+        m9x[0] = m9x[1]; m9x[1] = m9x[2]; m9x[2] = mx;
+        // ---- z stage: window centred at plane c = pz - 1 (planes pz-2, pz-1, pz = indices 0, 1, 2), then scatter
+        if (win_ok && (Dn != 0.f || ap != 0.f)) {
+            Cand bn{INFINITY, -1}, bx{-INFINITY, -1};
+            int dzn = 0, dzx = 0;
+            if (c5[0].code >= 0 && c5[0].v < bn.v) { bn = c5[0]; dzn = -1; }
+            if (m9n[1].code >= 0 && m9n[1].v < bn.v) { bn = m9n[1]; dzn = 0; }
+            if (c5[2].code >= 0 && c5[2].v < bn.v) { bn = c5[2]; dzn = 1; }
+            if (m9x[0].code >= 0 && m9x[0].v > bx.v) { bx = m9x[0]; dzx = -1; }
+            if (m9x[1].code >= 0 && m9x[1].v > bx.v) { bx = m9x[1]; dzx = 0; }
+            if (m9x[2].code >= 0 && m9x[2].v > bx.v) { bx = m9x[2]; dzx = 1; }
+            if (Dn != 0.f && bn.code >= 0)
+                atomicAdd(&sAcc[(c + dzn) & 3][wy + 1 + bn.code / 3 - 1][lane + 1 + bn.code % 3 - 1], Dn);
+            if (ap != 0.f && bx.code >= 0)
+                atomicAdd(&sAcc[(c + dzx) & 3][wy + 1 + bx.code / 3 - 1][lane + 1 + bx.code % 3 - 1], -ap);
+        }
+        __syncthreads();
+        // ---- plane o = pz - 2 has received the windows of planes o-1, o, o+1
+        if (out_ok) D_out[col + (size_t)o * HW] = aj + sAcc[o & 3][wy + 1][lane + 1];
+        sAcc[o & 3][wy + 1][lane + 1] = 0.f;                   // every (row, lane) cell has exactly one owner thread
+    }
+}
+
 // chunk length along z for the marching kernels: fill the resident-block slots evenly (2 blocks per SM) at a small halo cost
 inline int pick_zl(int D, long long columns, int halo_iters, int slots = 296) {
     int best = D;
@@ -522,10 +654,24 @@ int vg_soft_skel_bwd(const float* E, const float* S, const float* gskel, float* 
         skel_bwd_coeff_kernel<<<blocks, NTHREADS, 0, st>>>(Gin, sprev, e0, e1, aout, gout, v, tx, ty, tz, first);
         VG_LAUNCHED(1);
     };
+    // VG_SKEL_BWD=tile keeps the shared-memory tile routing kernel (A/B testing and cross-checks)
+    static int bmarch = -1;
+    if (bmarch < 0) {
+        const char* e = getenv("VG_SKEL_BWD");
+        bmarch = (e && e[0] == 't') ? 0 : 1;
+    }
+    const int rtx = vg_cdiv(W, MW_OUT), rty = vg_cdiv(H, RM_OUT);
+    const int RZL = pick_zl(D, (long long)N * rtx * rty, 4), rzch = vg_cdiv(D, RZL);
+    auto route = [&](const float* e, const float* aj, const float* dnext, const float* aprev, float* out) {
+        if (bmarch)
+            skel_bwd_route_march_kernel<<<N * rtx * rty * rzch, RM_THREADS, 0, st>>>(e, aj, dnext, aprev, out, v, rtx, rty, rzch, RZL);
+        else
+            skel_bwd_route_kernel<<<blocks, NTHREADS, ROUTE_SMEM, st>>>(e, aj, dnext, aprev, out, v, tx, ty, tz);
+        VG_LAUNCHED(1);
+    };
     coeff(Gcur, k ? S + (size_t)(k - 1) * nv : nullptr, Ej(k), Ej(k + 1), Ab[k & 1], Gb[(k + 1) & 1], k == 0);
     Gcur = Gb[(k + 1) & 1];  // now holds G_{k-1}
-    skel_bwd_route_kernel<<<blocks, NTHREADS, ROUTE_SMEM, st>>>(Ej(k + 1), nullptr, nullptr, Ab[k & 1], Db[(k + 1) & 1], v, tx, ty,
-                                                       tz); VG_LAUNCHED(1);
+    route(Ej(k + 1), nullptr, nullptr, Ab[k & 1], Db[(k + 1) & 1]);
     for (int j = k; j >= 0; j--) {
         if (j >= 1) {
             int jj = j - 1;
@@ -533,8 +679,7 @@ int vg_soft_skel_bwd(const float* E, const float* S, const float* gskel, float* 
             Gcur = Gb[(jj + 1) & 1];
         }
         float* out = j == 0 ? dx : Db[j & 1];
-        skel_bwd_route_kernel<<<blocks, NTHREADS, ROUTE_SMEM, st>>>(Ej(j), Ab[j & 1], Db[(j + 1) & 1], j >= 1 ? Ab[(j - 1) & 1] : nullptr,
-                                                           out, v, tx, ty, tz); VG_LAUNCHED(1);
+        route(Ej(j), Ab[j & 1], Db[(j + 1) & 1], j >= 1 ? Ab[(j - 1) & 1] : nullptr, out);
     }
     VG_CHECK_LAUNCH();
     return VG_OK;
