@@ -135,6 +135,8 @@ def run_sliding(gen=None, strategy=None, cases=((False, "stride 64, complete=Fal
                     "seconds": round(best, 4), "Mvoxel_per_s": round(vol.size / best / 1e6, 1),
                     "window_Mvoxel_per_s": round(st["windows"] * 128 ** 3 / best / 1e6, 1),
                     "gen_fwd_TFLOPs": round(st["windows"] * 299.31e9 / best / 1e12, 1)})
+        if "phases_ms" in st:                        # VG_STITCH_PROFILE=1 (synchronising marks: the total above is then not a bench value)
+            out[-1]["phases_ms"] = st["phases_ms"]
     return out
 
 

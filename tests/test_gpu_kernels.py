@@ -47,6 +47,31 @@ def test_soft_skel_backward(cuda, shape, iters):
     assert float((dx - x.grad).abs().max()) < 1e-5 * float(x.grad.abs().max()) + 1e-6
 
 
+@pytest.mark.parametrize("shape,iters,levels", [((2, 37, 21, 45), 4, 4), ((1, 70, 18, 30), 6, 2), ((3, 9, 40, 33), 3, 8)])
+def test_soft_skel_backward_with_ties(cuda, shape, iters, levels, monkeypatch):
+    """Quantised volumes (segmentation-like plateaus): almost every min / max window holds several equal extrema, so the gradient
+    routing is decided by the tie rule in every level.  The policy (oracle/__init__.py: one winner, the first extremum in the window's
+    scan order) is implemented twice -- the z-marching routing kernel (separable first-extremum search, shared-memory scatter) and the
+    tile kernel (VG_SKEL_BWD=tile: explicit window scans, gather form) -- and the two must agree; the forward has no tie ambiguity and
+    is compared with the oracle.  Ragged tile / z-chunk extents."""
+    from oracle import losses as OL
+    from van_gan_b200 import clDice_func as K
+    rng = np.random.default_rng(18)
+    xq = np.round(rng.random(shape + (1,)) * levels) / levels
+    x = torch.tensor(xq, dtype=torch.float32)
+    g = torch.tensor(rng.standard_normal(shape + (1,)), dtype=torch.float32).cuda()
+    skel, bwd = K.soft_skel_with_grad(x.cuda(), iters)
+    assert torch.equal(skel.cpu(), OL.soft_skel(x, iters))
+    monkeypatch.delenv("VG_SKEL_BWD", raising=False)
+    dx_march = bwd(g).clone()
+    monkeypatch.setenv("VG_SKEL_BWD", "tile")
+    dx_tile = bwd(g).clone()
+    assert float(dx_tile.abs().max()) > 0
+    assert rel_l2(dx_march.cpu(), dx_tile.cpu()) < 1e-6
+    # conservation: every level routes each incoming gradient to exactly one voxel, so no gradient mass is created or lost by ties
+    assert float((dx_march - dx_tile).abs().max()) < 1e-5 * float(dx_tile.abs().max())
+
+
 # ----------------------------------------------------------------------------- losses
 class _Cfg:
     def __init__(self, G=2, nd=1):

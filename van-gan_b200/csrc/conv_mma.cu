@@ -1052,6 +1052,13 @@ int vg_conv3d_dgrad(const vg_conv3d_desc* d, const void* dy, const void* w_dgrad
         if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
         if (rc != VG_ERR_UNSUPPORTED) return rc;
     }
+    if (small_enabled() && d->K == 1 && s == 1 && d->x_dtype == VG_BF16 && d->y_dtype == VG_BF16 && !d->dx_lo && !d->dx_hi) {
+        // 1x1x1 shortcut: dx[v][ci] = sum_co dy[v][co] w[ci][co] is the streaming forward kernel with the channel roles swapped; the
+        // mma.sync dgrad pack [Np(ci)][Cout] is exactly its operand layout (one pass over dy and dx instead of K = 1-tap MMAs)
+        int rc = vg_small_k1_fwd((const bf16*)dy, (const bf16*)w_dgrad, nullptr, (bf16*)dx, (long long)d->N * OD * OH * OW, d->Cout, d->Cin, st);
+        if (rc == VG_OK) { VG_CHECK_LAUNCH(); return VG_OK; }
+        if (rc != VG_ERR_UNSUPPORTED) return rc;
+    }
     if (d->K < s) {  // k1 s2: odd-parity classes receive nothing
         size_t bytes = (size_t)d->N * d->ID * d->IH * d->IW * d->Cin * (d->x_dtype == VG_F32 ? 4 : 2);
         if (cudaMemsetAsync(dx, 0, bytes, st) != cudaSuccess) return VG_ERR_CUDA;

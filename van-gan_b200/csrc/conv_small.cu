@@ -645,6 +645,8 @@ int vg_small_k1_fwd(const bf16* x, const bf16* wp, const float* bias, bf16* y, l
     else if (Cin == 96 && Cout == 32) k1_fwd_kernel<6, 4><<<148 * 2, 256, 0, st>>>(x, wp, bias, y, nvox);
     else if (Cin == 16 && Cout == 16) k1_fwd_kernel<1, 2><<<grid, 256, 0, st>>>(x, wp, bias, y, nvox);
     else if (Cin == 32 && Cout == 32) k1_fwd_kernel<2, 4><<<grid, 256, 0, st>>>(x, wp, bias, y, nvox);
+    else if (Cin == 16 && Cout == 48) k1_fwd_kernel<1, 6><<<grid, 256, 0, st>>>(x, wp, bias, y, nvox);        // input gradients of the
+    else if (Cin == 32 && Cout == 96) k1_fwd_kernel<2, 12><<<148 * 2, 256, 0, st>>>(x, wp, bias, y, nvox);    // decoder shortcuts
     else return VG_ERR_UNSUPPORTED;
     VG_LAUNCHED(1);
     return VG_OK;

@@ -655,11 +655,8 @@ int vg_soft_skel_bwd(const float* E, const float* S, const float* gskel, float* 
         VG_LAUNCHED(1);
     };
     // VG_SKEL_BWD=tile keeps the shared-memory tile routing kernel (A/B testing and cross-checks)
-    static int bmarch = -1;
-    if (bmarch < 0) {
-        const char* e = getenv("VG_SKEL_BWD");
-        bmarch = (e && e[0] == 't') ? 0 : 1;
-    }
+    const char* ebwd = getenv("VG_SKEL_BWD");   // read per call: the tie-rule test runs both kernels in one process
+    const int bmarch = (ebwd && ebwd[0] == 't') ? 0 : 1;
     const int rtx = vg_cdiv(W, MW_OUT), rty = vg_cdiv(H, RM_OUT);
     const int RZL = pick_zl(D, (long long)N * rtx * rty, 4), rzch = vg_cdiv(D, RZL);
     auto route = [&](const float* e, const float* aj, const float* dnext, const float* aprev, float* out) {
