@@ -332,7 +332,8 @@ def run_gpu(args):
         if m:
             kind, ci, co, kk, st = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4)), int(m.group(5))
             k1_small = (ci, co) in ((48, 16), (96, 32), (16, 16), (32, 32))     # 1x1x1 forward shapes served by conv_small.cu
-            on_tc = kind == "dgrad" or kk >= 3 or (kk == 1 and st == 1 and not k1_small)
+            # tcgen05 path: every k3 / k4 layer; 1x1x1: stride-2 input gradients and the stride-1 shapes without a streaming kernel
+            on_tc = kk >= 3 or (kk == 1 and not (st == 1 and k1_small) and (kind == "dgrad" or st == 1))
             if ci % 16 == 0 and co % 16 == 0 and on_tc:
                 tc_ms += v["ms"]; tc_flop += v["work"]; tc_calls += v["calls"]
     achieved = tc_flop / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None

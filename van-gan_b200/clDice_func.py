@@ -41,7 +41,10 @@ def soft_skel_with_grad(img, iters):
         nb = lib().vg_soft_skel_bwd_workspace_bytes(n, d, h, w)
         ws = torch.empty(nb // 4, dtype=torch.float32, device=E.DEV)
         dx = torch.empty_like(img)
-        call("vg_soft_skel_bwd", Eb, Sb, gskel.contiguous(), dx, ws, nb, n, d, h, w, iters, work=16.0 * img.numel() * (iters + 1))
+        call("vg_soft_skel_bwd", Eb, Sb, gskel.contiguous(), dx, ws, nb, n, d, h, w, iters,
+             # HBM bytes of this formulation per voxel and level: coefficient pass reads G, S_{j-1}, E_j, E_{j+1} and writes a_j, G_{j-1};
+             # routing pass reads E_j, a_j, D_{j+1}, a_{j-1} and writes D_j -> 11 floats
+             work=44.0 * img.numel() * (iters + 1))
         return dx
 
     return Sb[iters].view(img.shape), backward
