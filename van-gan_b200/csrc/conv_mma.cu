@@ -498,8 +498,8 @@ inline int class_taps(int K, int stride, int a) { return K <= a ? 0 : (K - a + s
 // broadcast from shared memory) feeds 16*VW FMAs.  The VW voxels of a thread are 32 apart in the flattened (oh, ow) plane, so
 // the 32 lanes of a warp always touch consecutive voxels: input loads are coalesced and each output voxel row (16 channels =
 // one 32-byte sector) leaves as a single 256-bit store, 1 KB contiguous per warp instruction when Cout == 16.
-template <int K, int S>
-__global__ void __launch_bounds__(128) cin1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+template <int K, int S, bool PF = false>
+__global__ void __launch_bounds__(128, PF ? 3 : 1) cin1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, bf16* __restrict__ y, int N, int ID,
                                                        int IH, int IW, int OD, int OH, int OW, int Cout) {
     constexpr int VW = 4, T = K * K * K;
@@ -532,31 +532,50 @@ __global__ void __launch_bounds__(128) cin1_fwd_kernel(const float* __restrict__
 #pragma unroll
             for (int k = 0; k < 16; k++) acc[v][k] = sw[T * Cout + cg * 16 + k];
         const float* xb = x + ((size_t)n * ID + od * S) * IH * IW;
-#pragma unroll 1
-        for (int kd = 0; kd < K; kd++)
-#pragma unroll 1
-            for (int kh = 0; kh < K; kh++) {
-                const float* xr = xb + ((size_t)kd * IH + kh) * IW;
-                float xv[VW][K];
+        auto load_row = [&](int q, float (&xv)[VW][K]) {   // the K inputs along w of every owned voxel for tap row q = (kd, kh)
+            const float* xr = xb + ((size_t)(q / K) * IH + (q % K)) * IW;
+#pragma unroll
+            for (int v = 0; v < VW; v++)
+#pragma unroll
+                for (int kw = 0; kw < K; kw++) xv[v][kw] = __ldg(xr + xoff[v] + kw);
+        };
+        auto fma_row = [&](int q, const float (&xv)[VW][K]) {
+            const float* wr = sw + (q * K) * Cout + cg * 16;
+#pragma unroll
+            for (int kw = 0; kw < K; kw++) {
+                float wv[16];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(wr + kw * Cout + j * 4);
+                    wv[4 * j] = t4.x; wv[4 * j + 1] = t4.y; wv[4 * j + 2] = t4.z; wv[4 * j + 3] = t4.w;
+                }
 #pragma unroll
                 for (int v = 0; v < VW; v++)
 #pragma unroll
-                    for (int kw = 0; kw < K; kw++) xv[v][kw] = __ldg(xr + xoff[v] + kw);
-                const float* wr = sw + ((kd * K + kh) * K) * Cout + cg * 16;
-#pragma unroll
-                for (int kw = 0; kw < K; kw++) {
-                    float wv[16];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(wr + kw * Cout + q * 4);
-                        wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
-                    }
-#pragma unroll
-                    for (int v = 0; v < VW; v++)
-#pragma unroll
-                        for (int k = 0; k < 16; k++) acc[v][k] = fmaf(xv[v][kw], wv[k], acc[v][k]);
+                    for (int k = 0; k < 16; k++) acc[v][k] = fmaf(xv[v][kw], wv[k], acc[v][k]);
+            }
+        };
+        if (PF) {
+            // software pipeline over the K*K tap rows: the loads of row q+1 are in flight while row q feeds the FMA pipe
+            float xa[VW][K], xb2[VW][K];
+            load_row(0, xa);
+#pragma unroll 1
+            for (int q = 0; q < K * K; q += 2) {
+                if (q + 1 < K * K) load_row(q + 1, xb2);
+                fma_row(q, xa);
+                if (q + 1 < K * K) {
+                    if (q + 2 < K * K) load_row(q + 2, xa);
+                    fma_row(q + 1, xb2);
                 }
             }
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < K * K; q++) {
+                float xv[VW][K];
+                load_row(q, xv);
+                fma_row(q, xv);
+            }
+        }
         bf16* yo = y + (((size_t)n * OD + od) * plane + (size_t)fb * 32 * VW + lane) * Cout + cg * 16;
 #pragma unroll
         for (int v = 0; v < VW; v++)
@@ -968,9 +987,19 @@ int vg_conv3d_fwd(const vg_conv3d_desc* d, const void* x, const void* w_fwd, con
         size_t smem = ((size_t)T * d->Cout + d->Cout) * sizeof(float);
         size_t total = (size_t)d->N * OD * ((OH * OW + 127) / 128) * (d->Cout / 16);   // warp items
         int grid = vg_grid_for(total, 4, 8);
+        // k4 layers (PatchGAN d0, 1 -> 64): the software-pipelined tap loop, 0.598 -> 0.553 ms at 8x130^3; k3 (stem, 1 -> 16) measured
+        // 0.549 -> 0.560 ms and keeps the plain loop.  VG_CIN1_PF=0: plain loop everywhere (A/B testing)
+        const char* epf = getenv("VG_CIN1_PF");
+        const bool pf = !(epf && epf[0] == '0') && d->K == 4;
 #define VG_CIN1_FWD(KK, SS)                                                                                                       \
-    cin1_fwd_kernel<KK, SS><<<grid, 128, smem, st>>>((const float*)x, (const float*)w_fwd, bias, (bf16*)y, d->N, d->ID, d->IH, d->IW, \
-                                                     OD, OH, OW, d->Cout)
+    do {                                                                                                                          \
+        if (pf && KK == 4)                                                                                                        \
+            cin1_fwd_kernel<KK, SS, (KK == 4)><<<grid, 128, smem, st>>>((const float*)x, (const float*)w_fwd, bias, (bf16*)y, d->N,         \
+                                                                                d->ID, d->IH, d->IW, OD, OH, OW, d->Cout);            \
+        else                                                                                                                      \
+            cin1_fwd_kernel<KK, SS, false><<<grid, 128, smem, st>>>((const float*)x, (const float*)w_fwd, bias, (bf16*)y, d->N, d->ID, d->IH, \
+                                                                  d->IW, OD, OH, OW, d->Cout);                                        \
+    } while (0)
         if (d->K == 1 && d->stride == 1) VG_CIN1_FWD(1, 1);
         else if (d->K == 3 && d->stride == 1) VG_CIN1_FWD(3, 1);
         else if (d->K == 4 && d->stride == 2) VG_CIN1_FWD(4, 2);

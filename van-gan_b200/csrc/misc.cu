@@ -26,9 +26,20 @@ __global__ void __launch_bounds__(NT) upsample_concat_kernel(const bf16* __restr
         const uint4* lrow = reinterpret_cast<const uint4*>(lo + (((size_t)n * D + (d >> 1)) * H + (h >> 1)) * W * C0);
         const uint4* srow = reinterpret_cast<const uint4*>(skip + (size_t)row * W2 * C1);
         uint4* orow = reinterpret_cast<uint4*>(out + (size_t)row * W2 * C);
-        for (int i = threadIdx.x; i < per_row; i += NT) {
-            const int w = i / cg, c8 = i - w * cg;
-            orow[i] = c8 < cg0 ? __ldg(lrow + (w >> 1) * cg0 + c8) : __ldg(srow + w * cg1 + (c8 - cg0));
+        // 4 independent 16-byte packets per thread in flight (a 128-voxel row of 48 channels is 768 packets = 3 per thread)
+        for (int i0 = threadIdx.x; i0 < per_row; i0 += 4 * NT) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * NT;
+                if (i < per_row) {
+                    const int w = i / cg, c8 = i - w * cg;
+                    v[u] = c8 < cg0 ? __ldg(lrow + (w >> 1) * cg0 + c8) : __ldg(srow + w * cg1 + (c8 - cg0));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i0 + u * NT < per_row) orow[i0 + u * NT] = v[u];
         }
     }
 }
@@ -73,10 +84,10 @@ __global__ void __launch_bounds__(NT) upsample_concat_bwd_lo_kernel(const bf16* 
 __global__ void __launch_bounds__(NT) upsample_concat_bwd_skip_kernel(const bf16* __restrict__ dcat, bf16* __restrict__ dskip,
                                                                       size_t V2, int C0, int C1, int accumulate) {
     const int C = C0 + C1, cg1 = C1 / 8;
-    // voxel-major walk with 32-bit arithmetic inside chunks of 2^20 voxels
     const size_t total = V2 * cg1;
+    const bool small = total <= 0xffffffffull;   // 32-bit division on the packet index (a 64-bit one costs more than the 16-byte copy)
     for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
-        const size_t v = i / (unsigned)cg1;
+        const size_t v = small ? (size_t)((unsigned)i / (unsigned)cg1) : i / (unsigned)cg1;
         const int c8 = (int)(i - v * cg1);
         uint4 p = __ldg(reinterpret_cast<const uint4*>(dcat + v * C + C0 + c8 * 8));
         if (accumulate) {
@@ -91,25 +102,43 @@ __global__ void __launch_bounds__(NT) upsample_concat_bwd_skip_kernel(const bf16
     }
 }
 
+// A warp owns padded rows (n, pd, ph): three 32-bit divisions per ROW instead of four 64-bit ones per voxel; lanes walk pw.
 __global__ void __launch_bounds__(NT) pad_noise_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int D, int H,
                                                        int W, const float* __restrict__ noise, float noise_std,
                                                        unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
     if (seed_dev) seed += *seed_dev;   // per-step offset kept in device memory (CUDA-graph replays draw fresh noise)
     const int PD = D + 2, PH = H + 2, PW = W + 2;
-    size_t total = (size_t)N * PD * PH * PW;
-    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
-        int pw = (int)(i % PW), ph = (int)((i / PW) % PH), pd = (int)((i / ((size_t)PW * PH)) % PD);
-        int n = (int)(i / ((size_t)PW * PH * PD));
-        int d = reflect1(pd - 1, D), h = reflect1(ph - 1, H), w = reflect1(pw - 1, W);
-        float v = x[(((size_t)n * D + d) * H + h) * W + w];
-        if (noise) {
-            v += noise[i];
-        } else if (noise_std > 0.f) {
-            uint4 r = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 2u, 0x56414e47u),
-                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-            v += noise_std * box_muller(r.x, r.y).x;
+    const unsigned rows = (unsigned)N * PD * PH;   // < 2^31 (checked by the caller)
+    const int lane = threadIdx.x & 31;
+    const unsigned nwarps = gridDim.x * (NT / 32);
+    for (unsigned row = blockIdx.x * (NT / 32) + (threadIdx.x >> 5); row < rows; row += nwarps) {
+        const unsigned ph = row % PH, r = row / PH;
+        const unsigned pd = r % PD, n = r / PD;
+        const int d = reflect1((int)pd - 1, D), h = reflect1((int)ph - 1, H);
+        const float* xr = x + (((size_t)n * D + d) * H + h) * W;
+        const size_t i0 = (size_t)row * PW;
+        for (int pw0 = lane; pw0 < PW; pw0 += 128) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {   // four independent loads in flight per lane
+                const int pw = pw0 + 32 * u;
+                v[u] = pw < PW ? xr[reflect1(pw - 1, W)] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int pw = pw0 + 32 * u;
+                if (pw >= PW) continue;
+                const size_t i = i0 + pw;   // flat index of the padded voxel: also the Philox counter (unchanged stream)
+                if (noise) {
+                    v[u] += noise[i];
+                } else if (noise_std > 0.f) {
+                    uint4 rr = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 2u, 0x56414e47u),
+                                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+                    v[u] += noise_std * box_muller(rr.x, rr.y).x;
+                }
+                y[i] = v[u];
+            }
         }
-        y[i] = v;
     }
 }
 
@@ -456,8 +485,9 @@ int vg_upsample_concat_bwd(const void* dcat, void* dlo, void* dskip, int accumul
 int vg_pad_noise(const float* x, float* y, int N, int D, int H, int W, const float* noise, float noise_std,
                  unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
     VG_REQUIRE(x && y && D >= 2 && H >= 2 && W >= 2);
-    size_t total = (size_t)N * (D + 2) * (H + 2) * (W + 2);
-    pad_noise_kernel<<<vg_grid_for(total, NT, 16), NT, 0, (cudaStream_t)stream>>>(x, y, N, D, H, W, noise, noise_std, seed, seed_dev); VG_LAUNCHED(1);
+    const long long rows = (long long)N * (D + 2) * (H + 2);
+    VG_REQUIRE(rows < 0x7fffffffLL);
+    pad_noise_kernel<<<vg_grid_for(rows, NT / 32, 16), NT, 0, (cudaStream_t)stream>>>(x, y, N, D, H, W, noise, noise_std, seed, seed_dev); VG_LAUNCHED(1);
     VG_CHECK_LAUNCH();
     return VG_OK;
 }

@@ -102,12 +102,31 @@ skel_level_fwd_kernel(const float* __restrict__ e_in, float* __restrict__ e_out,
     }
 }
 
+// max over the block of a non-negative per-thread value -> atomicMax into *dst (bit pattern of a non-negative float orders like the
+// float).  Deterministic: a maximum does not depend on the order.  `scratch`: >= 32 floats of shared memory, free after a barrier.
+__device__ __forceinline__ void block_absmax(float v, unsigned* dst, float* scratch) {
+    if (!dst) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        float m = threadIdx.x < nw ? scratch[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0 && m > 0.f && __float_as_uint(m) > *dst) atomicMax(dst, __float_as_uint(m));
+    }
+}
+
 // a_j and G_{j-1} from G_j, skel_{j-1}, e_j, e_{j+1} (see header comment / DESIGN.md)
 __global__ void __launch_bounds__(NTHREADS)
 skel_bwd_coeff_kernel(const float* __restrict__ G, const float* __restrict__ skel_prev, const float* __restrict__ ej,
                       const float* __restrict__ ej1, float* __restrict__ a_out, float* __restrict__ G_out, Vol v,
-                      int tiles_x, int tiles_y, int tiles_z, int first) {
+                      int tiles_x, int tiles_y, int tiles_z, int first, unsigned* __restrict__ amax) {
     __shared__ float sB[H1Z * H1Y * H1X];
+    float my_max = 0.f;   // max |a_j| of this thread's voxels (the routing kernel's fixed-point scale, see block_absmax)
     int t = blockIdx.x;
     int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = (t / (tiles_x * tiles_y)) % tiles_z;
     int n = t / (tiles_x * tiles_y * tiles_z);
@@ -144,8 +163,11 @@ skel_bwd_coeff_kernel(const float* __restrict__ G, const float* __restrict__ ske
             dd = Gj * m * (1.f - sp);
             G_out[g] = Gj * (1.f - m * delta);
         }
-        a_out[g] = diff > 0.f ? dd : 0.f;
+        const float a = diff > 0.f ? dd : 0.f;
+        a_out[g] = a;
+        my_max = fmaxf(my_max, fabsf(a));
     }
+    block_absmax(my_max, amax, sB);
 }
 
 // D_j[q] = a_j[q] + sum_{p in N19(q)} [argmin_p(e_j)==q] D_{j+1}[p] - sum_{p in N27(q)} [argmax_p(e_j)==q] a_{j-1}[p]
@@ -420,6 +442,12 @@ skel_level_fwd_v4_kernel(const float* __restrict__ e_in, float* __restrict__ e_o
 // shared-memory row exchange per plane, z windows in registers); every window then SCATTERS its two values to its two winners with
 // shared-memory atomics into a 4-plane ring of accumulators, and a plane is written out once the windows of its three neighbouring
 // planes have scattered.  ~90 instructions per voxel and level instead of the ~130 shared-memory loads of the tile kernel.
+// The ring holds FIXED-POINT sums (integer atomics): a float atomicAdd would make the result depend on the arrival order, and a
+// 1e-7 wobble of this gradient is enough to flip a bf16 rounding somewhere in the generator's backward pass, which the
+// ill-conditioned small test volumes amplify to 3e-3 -- replay == eager could then only be tested statistically.  With 2^e >
+// max(|D_{j+1}|, |a_{j-1}|) (tracked by the producing kernels with atomicMax) a value is split exactly into hi = rn(v * 2^(25-e)) and
+// lo = rn((v - hi * 2^(e-25)) * 2^(50-e)), two native 32-bit shared-memory atomics (a 64-bit add would be a CAS loop): the <= 46
+// contributions of a cell stay below 2^31, the resolution is 2^-50 of the largest value, and integer addition is exact in any order.
 struct Cand {
     float v;
     int code;   // (dy + 1) * 3 + (dx + 1), or -1 = none
@@ -436,10 +464,29 @@ constexpr int RM_ROWS = 20, RM_OUT = RM_ROWS - 4, RM_THREADS = 32 * RM_ROWS;
 __global__ void __launch_bounds__(RM_THREADS, 2)
 skel_bwd_route_march_kernel(const float* __restrict__ ej, const float* __restrict__ a_j, const float* __restrict__ D_next,
                             const float* __restrict__ a_prev, float* __restrict__ D_out, Vol v, int tiles_x, int tiles_y, int zchunks,
-                            int ZL) {
+                            int ZL, const unsigned* __restrict__ max_dnext, const unsigned* __restrict__ max_aprev,
+                            unsigned* __restrict__ max_out) {
     __shared__ float sV[2][RM_ROWS + 2][32], sMinV[2][RM_ROWS + 2][32], sMaxV[2][RM_ROWS + 2][32];
     __shared__ int sIdx[2][RM_ROWS + 2][32];
-    __shared__ float sAcc[4][RM_ROWS + 2][34];
+    __shared__ int sAccH[4][RM_ROWS + 2][34], sAccL[4][RM_ROWS + 2][34];
+    // fixed-point scales of this call (uniform over the grid)
+    float fx_hi, fx_hi_inv, fx_lo_inv;
+    {
+        const unsigned mb = max(max_dnext ? *max_dnext : 0u, max_aprev ? *max_aprev : 0u);
+        int sh = mb ? 25 - ((int)((mb >> 23) & 0xff) - 126) : 0;   // largest value = f * 2^e, f in [0.5, 1): exponent field = e + 126
+        sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+        fx_hi = __int_as_float((127 + sh) << 23);
+        fx_hi_inv = __int_as_float((127 - sh) << 23);
+        fx_lo_inv = __int_as_float((127 - sh - 25) << 23);
+    }
+    constexpr float FX_LO = 33554432.f;   // 2^25
+    auto fx_add = [&](int slot, int row, int colx, float val) {
+        const float hs = rintf(val * fx_hi);                         // |hs| <= 2^25
+        const float rem = fmaf(-hs, fx_hi_inv, val) * fx_hi;         // exact low part of val, in units of 2^-sh: |rem| <= 1/2
+        atomicAdd(&sAccH[slot][row][colx], (int)hs);
+        atomicAdd(&sAccL[slot][row][colx], __float2int_rn(rem * FX_LO));
+    };
+    float my_max = 0.f;
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
     int t = blockIdx.x;
     const int tx = t % tiles_x; t /= tiles_x;
@@ -454,7 +501,10 @@ skel_bwd_route_march_kernel(const float* __restrict__ ej, const float* __restric
     const size_t HW = (size_t)v.H * v.W;
     const size_t col = (size_t)n * v.D * HW + (size_t)(col_in ? gy : 0) * v.W + (col_in ? gx : 0);
     const float QNAN = __int_as_float(0x7fc00000);
-    for (int i = threadIdx.x; i < 4 * (RM_ROWS + 2) * 34; i += RM_THREADS) (&sAcc[0][0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < 4 * (RM_ROWS + 2) * 34; i += RM_THREADS) {
+        (&sAccH[0][0][0])[i] = 0;
+        (&sAccL[0][0][0])[i] = 0;
+    }
     if (wy == 0) {
         for (int b = 0; b < 2; b++) {
             sV[b][0][lane] = QNAN; sV[b][RM_ROWS + 1][lane] = QNAN;
@@ -529,16 +579,21 @@ skel_bwd_route_march_kernel(const float* __restrict__ ej, const float* __restric
             if (m9x[0].code >= 0 && m9x[0].v > bx.v) { bx = m9x[0]; dzx = -1; }
             if (m9x[1].code >= 0 && m9x[1].v > bx.v) { bx = m9x[1]; dzx = 0; }
             if (m9x[2].code >= 0 && m9x[2].v > bx.v) { bx = m9x[2]; dzx = 1; }
-            if (Dn != 0.f && bn.code >= 0)
-                atomicAdd(&sAcc[(c + dzn) & 3][wy + 1 + bn.code / 3 - 1][lane + 1 + bn.code % 3 - 1], Dn);
-            if (ap != 0.f && bx.code >= 0)
-                atomicAdd(&sAcc[(c + dzx) & 3][wy + 1 + bx.code / 3 - 1][lane + 1 + bx.code % 3 - 1], -ap);
+            if (Dn != 0.f && bn.code >= 0) fx_add((c + dzn) & 3, wy + 1 + bn.code / 3 - 1, lane + 1 + bn.code % 3 - 1, Dn);
+            if (ap != 0.f && bx.code >= 0) fx_add((c + dzx) & 3, wy + 1 + bx.code / 3 - 1, lane + 1 + bx.code % 3 - 1, -ap);
         }
         __syncthreads();
         // ---- plane o = pz - 2 has received the windows of planes o-1, o, o+1
-        if (out_ok) D_out[col + (size_t)o * HW] = aj + sAcc[o & 3][wy + 1][lane + 1];
-        sAcc[o & 3][wy + 1][lane + 1] = 0.f;                   // every (row, lane) cell has exactly one owner thread
+        if (out_ok) {
+            const float acc = fmaf((float)sAccL[o & 3][wy + 1][lane + 1], fx_lo_inv, (float)sAccH[o & 3][wy + 1][lane + 1] * fx_hi_inv);
+            const float d = aj + acc;
+            D_out[col + (size_t)o * HW] = d;
+            my_max = fmaxf(my_max, fabsf(d));
+        }
+        sAccH[o & 3][wy + 1][lane + 1] = 0;                    // every (row, lane) cell has exactly one owner thread
+        sAccL[o & 3][wy + 1][lane + 1] = 0;
     }
+    block_absmax(my_max, max_out, &sV[0][0][0]);
 }
 
 // chunk length along z for the marching kernels: fill the resident-block slots evenly (2 blocks per SM) at a small halo cost
@@ -625,7 +680,11 @@ int vg_soft_skel_fwd(const float* x, float* E, float* S, int N, int D, int H, in
     return VG_OK;
 }
 
-size_t vg_soft_skel_bwd_workspace_bytes(int N, int D, int H, int W) { return (size_t)6 * N * D * H * W * sizeof(float); }
+// six volumes + 2 x 64 running maxima (|a_j|, |D_j| per level: the fixed-point scales of the routing kernel)
+constexpr int SKEL_MAX_SLOTS = 64;
+size_t vg_soft_skel_bwd_workspace_bytes(int N, int D, int H, int W) {
+    return (size_t)6 * N * D * H * W * sizeof(float) + 2 * SKEL_MAX_SLOTS * sizeof(unsigned);
+}
 
 // gskel: dL/d skel (same shape as x); dx: dL/dx.  E, S as written by vg_soft_skel_fwd.
 int vg_soft_skel_bwd(const float* E, const float* S, const float* gskel, float* dx, void* workspace,
@@ -650,33 +709,40 @@ int vg_soft_skel_bwd(const float* E, const float* S, const float* gskel, float* 
     const float* Gcur = gskel;
     // (a z-marching version of the coefficient kernel was measured slower than the tile kernel: 5 global accesses and one
     // barrier per plane leave nothing to amortise -- 10.8 -> 13.3 ms at 256^3, iters 15 -- and was dropped)
-    auto coeff = [&](const float* Gin, const float* sprev, const float* e0, const float* e1, float* aout, float* gout, int first) {
-        skel_bwd_coeff_kernel<<<blocks, NTHREADS, 0, st>>>(Gin, sprev, e0, e1, aout, gout, v, tx, ty, tz, first);
-        VG_LAUNCHED(1);
-    };
     // VG_SKEL_BWD=tile keeps the shared-memory tile routing kernel (A/B testing and cross-checks)
     const char* ebwd = getenv("VG_SKEL_BWD");   // read per call: the tie-rule test runs both kernels in one process
-    const int bmarch = (ebwd && ebwd[0] == 't') ? 0 : 1;
+    const int bmarch = ((ebwd && ebwd[0] == 't') || k + 2 > SKEL_MAX_SLOTS) ? 0 : 1;
+    // running maxima per level: mxA[j] = max |a_j|, mxD[j] = max |D_j| (the marching kernel's fixed-point scales)
+    unsigned* mxA = reinterpret_cast<unsigned*>(ws + 6 * nv);
+    unsigned* mxD = mxA + SKEL_MAX_SLOTS;
+    if (bmarch && cudaMemsetAsync(mxA, 0, 2 * SKEL_MAX_SLOTS * sizeof(unsigned), st) != cudaSuccess) return VG_ERR_CUDA;
+    auto coeff = [&](const float* Gin, const float* sprev, const float* e0, const float* e1, float* aout, float* gout, int first, int lvl) {
+        skel_bwd_coeff_kernel<<<blocks, NTHREADS, 0, st>>>(Gin, sprev, e0, e1, aout, gout, v, tx, ty, tz, first, bmarch ? mxA + lvl : nullptr);
+        VG_LAUNCHED(1);
+    };
     const int rtx = vg_cdiv(W, MW_OUT), rty = vg_cdiv(H, RM_OUT);
     const int RZL = pick_zl(D, (long long)N * rtx * rty, 4), rzch = vg_cdiv(D, RZL);
-    auto route = [&](const float* e, const float* aj, const float* dnext, const float* aprev, float* out) {
+    // lvl = level j of the output D_j; dnext = D_{j+1}, aprev = a_{j-1} (either may be absent)
+    auto route = [&](const float* e, const float* aj, const float* dnext, const float* aprev, float* out, int lvl) {
         if (bmarch)
-            skel_bwd_route_march_kernel<<<N * rtx * rty * rzch, RM_THREADS, 0, st>>>(e, aj, dnext, aprev, out, v, rtx, rty, rzch, RZL);
+            skel_bwd_route_march_kernel<<<N * rtx * rty * rzch, RM_THREADS, 0, st>>>(e, aj, dnext, aprev, out, v, rtx, rty, rzch, RZL,
+                                                                                  dnext ? mxD + lvl + 1 : nullptr,
+                                                                                  aprev ? mxA + lvl - 1 : nullptr, lvl > 0 ? mxD + lvl : nullptr);
         else
             skel_bwd_route_kernel<<<blocks, NTHREADS, ROUTE_SMEM, st>>>(e, aj, dnext, aprev, out, v, tx, ty, tz);
         VG_LAUNCHED(1);
     };
-    coeff(Gcur, k ? S + (size_t)(k - 1) * nv : nullptr, Ej(k), Ej(k + 1), Ab[k & 1], Gb[(k + 1) & 1], k == 0);
+    coeff(Gcur, k ? S + (size_t)(k - 1) * nv : nullptr, Ej(k), Ej(k + 1), Ab[k & 1], Gb[(k + 1) & 1], k == 0, k);
     Gcur = Gb[(k + 1) & 1];  // now holds G_{k-1}
-    route(Ej(k + 1), nullptr, nullptr, Ab[k & 1], Db[(k + 1) & 1]);
+    route(Ej(k + 1), nullptr, nullptr, Ab[k & 1], Db[(k + 1) & 1], k + 1);
     for (int j = k; j >= 0; j--) {
         if (j >= 1) {
             int jj = j - 1;
-            coeff(Gcur, jj ? S + (size_t)(jj - 1) * nv : nullptr, Ej(jj), Ej(jj + 1), Ab[jj & 1], Gb[(jj + 1) & 1], jj == 0);
+            coeff(Gcur, jj ? S + (size_t)(jj - 1) * nv : nullptr, Ej(jj), Ej(jj + 1), Ab[jj & 1], Gb[(jj + 1) & 1], jj == 0, jj);
             Gcur = Gb[(jj + 1) & 1];
         }
         float* out = j == 0 ? dx : Db[j & 1];
-        route(Ej(j), Ab[j & 1], Db[(j + 1) & 1], j >= 1 ? Ab[(j - 1) & 1] : nullptr, out);
+        route(Ej(j), Ab[j & 1], Db[(j + 1) & 1], j >= 1 ? Ab[(j - 1) & 1] : nullptr, out, j);
     }
     VG_CHECK_LAUNCH();
     return VG_OK;
