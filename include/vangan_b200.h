@@ -162,6 +162,7 @@ int vg_maxpool2_pad_bwd(const void* x, const void* dy, void* dx, int N, int D, i
  * E: [(iters+2)][N*D*H*W] erosion pyramid, S: [(iters+1)][N*D*H*W]; the skeleton is S[iters].
  * ------------------------------------------------------------------------------------------- */
 int vg_soft_skel_fwd(const float* x, float* E, float* S, int N, int D, int H, int W, int iters, void* stream);
+/* workspace: six fp32 volumes (G, a, D ping-pong pairs) + 2 x 64 per-level maxima (fixed-point scales of the routing kernel) */
 size_t vg_soft_skel_bwd_workspace_bytes(int N, int D, int H, int W);
 int vg_soft_skel_bwd(const float* E, const float* S, const float* gskel, float* dx, void* workspace, size_t workspace_bytes,
                      int N, int D, int H, int W, int iters, void* stream);

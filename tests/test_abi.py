@@ -63,4 +63,4 @@ def test_descriptor_struct_layouts():
     assert lib.vg_conv3d_packed_bytes(d, 1) > 27 * 16 * 16 * 2
     bad = _lib.ConvDesc(1, 10, 10, 10, 16, 16, 5, 1, _lib.VG_BF16, _lib.VG_BF16, 0)
     assert lib.vg_conv3d_packed_bytes(bad, 0) == 0
-    assert lib.vg_soft_skel_bwd_workspace_bytes(1, 8, 8, 8) == 6 * 512 * 4
+    assert lib.vg_soft_skel_bwd_workspace_bytes(1, 8, 8, 8) == 6 * 512 * 4 + 2 * 64 * 4   # six volumes + the per-level maxima

@@ -26,6 +26,19 @@ extern unsigned long long g_vg_launches;
 static inline int vg_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // grid sizing: a multiple of the SM count (148 on B200), capped by the work available
+// cudaFuncSetAttribute applies to the CURRENT device: a per-process flag would leave the second GPU of a multi-device process without
+// its shared-memory opt-in.  One bit per device ordinal.
+struct VgPerDevice {
+    unsigned long long mask = 0;
+    static unsigned long long bit() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return 1ull << (d & 63);
+    }
+    bool done() const { return (mask & bit()) != 0; }
+    void mark() { mask |= bit(); }
+};
+
 static inline int vg_grid_for(long long work_items, int per_block, int waves = 8) {
     long long blocks = (work_items + per_block - 1) / per_block;
     long long cap = 148LL * waves;

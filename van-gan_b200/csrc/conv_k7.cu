@@ -125,11 +125,11 @@ int vg_k7_many_to_one(const bf16* M, const bf16* w, int w_tstride, const float* 
     const int grid = vg_grid_for(total, NT, 8);
 #define VG_M21(CC)                                                                                                                    \
     do {                                                                                                                              \
-        static bool attr = false;                                                                                                     \
-        if (!attr) {                                                                                                                  \
+        static VgPerDevice attr;                                                                                                     \
+        if (!attr.done()) {                                                                                                                  \
             if (cudaFuncSetAttribute(many_to_one_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) \
                 return VG_ERR_CUDA;                                                                                                   \
-            attr = true;                                                                                                              \
+            attr.mark();                                                                                                              \
         }                                                                                                                             \
         many_to_one_kernel<CC><<<grid, NT, smem, st>>>(M, w, w_tstride, bias, y, N, MD, MH, MW, YD, YH, YW, K, sgn, act);            \
     } while (0)

@@ -263,11 +263,11 @@ inline bool pick_gconv_cfg(const GConv& p, int ncols, GCfg& out) {
 
 template <int CK, int NTW>
 int launch_gconv_t(const GConv& p, const GCfg& c, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static VgPerDevice attr_done;
+    if (!attr_done.done()) {
         if (cudaFuncSetAttribute(gconv_kernel<CK, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
             return VG_ERR_CUDA;
-        attr_done = true;
+        attr_done.mark();
     }
     const int gtw = (p.GW + BW - 1) / BW, gth = (p.GH + BH - 1) / BH, gtd = (p.GD + BD - 1) / BD;
     dim3 grid((unsigned)((size_t)gtw * gth * gtd * p.N), (unsigned)((p.Cy + 8 * NTW - 1) / (8 * NTW)));
@@ -421,11 +421,11 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WGrad p) {
 
 template <int TPW, int NCW>
 int launch_wgrad_t(const WGrad& p, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static VgPerDevice attr_done;
+    if (!attr_done.done()) {
         if (cudaFuncSetAttribute(wgrad_kernel<TPW, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
             return VG_ERR_CUDA;
-        attr_done = true;
+        attr_done.mark();
     }
     const int E_D = (BD - 1) * p.so + p.K, E_H = (BH - 1) * p.so + p.K, E_W = (BW - 1) * p.so + p.K;
     size_t stage = (size_t)E_D * E_H * E_W * 32 + 128 * 8 * NCW * 2;

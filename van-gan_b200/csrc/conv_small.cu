@@ -215,10 +215,10 @@ template <int KS, int NT>
 int launch_k1_wgrad(const bf16* x, const bf16* dy, float* dw, int nvox, int stride, int OD, int OH, int OW, int ID, int IH, int IW,
                     cudaStream_t st) {
     constexpr size_t smem = k1w_smem_bytes<KS, NT>();
-    static bool attr = false;
-    if (!attr) {
+    static VgPerDevice attr;
+    if (!attr.done()) {
         if (cudaFuncSetAttribute(k1_wgrad_kernel<KS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return VG_ERR_CUDA;
-        attr = true;
+        attr.mark();
     }
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm > 3) per_sm = 3;
@@ -626,11 +626,11 @@ int launch_cin1_wgrad_tc(const float* x, const bf16* dy, float* dw, float* dbias
     const size_t red = (size_t)8 * MT * 16 * 16 * 4;
     if (smem < red) smem = red;
     if (smem > 200 * 1024) return VG_ERR_UNSUPPORTED;
-    static bool attr = false;
-    if (!attr) {
+    static VgPerDevice attr;
+    if (!attr.done()) {
         if (cudaFuncSetAttribute(cin1_wgrad_tc_kernel<K, S, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return VG_ERR_CUDA;
-        attr = true;
+        attr.mark();
     }
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm > 3) per_sm = 3;
@@ -718,10 +718,10 @@ int vg_small_cin1_dgrad_s2(const bf16* dy, const bf16* wd, float* dx, int N, int
     if (K != 4 || Cout != 64) return VG_ERR_UNSUPPORTED;
     constexpr int NC = 4;
     constexpr size_t smem = (size_t)5 * 5 * 17 * (NC * 32 + 16);
-    static bool attr = false;
-    if (!attr) {
+    static VgPerDevice attr;
+    if (!attr.done()) {
         if (cudaFuncSetAttribute(cin1_dgrad_s2_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return VG_ERR_CUDA;
-        attr = true;
+        attr.mark();
     }
     const int GD = (ID + 1) / 2, GH = (IH + 1) / 2, GW = (IW + 1) / 2;
     const int nbd = (GD + 3) / 4, nbh = (GH + 3) / 4, nbw = (GW + 15) / 16;

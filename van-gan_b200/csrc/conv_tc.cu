@@ -717,14 +717,14 @@ int vg_tc_launch(const bf16* x, int Nb, int XD, int XH, int XW, int Cx, const bf
         return VG_ERR_UNSUPPORTED;
 
     const size_t smem = (size_t)p.stages * p.stage_bytes + TC_TAIL;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static VgPerDevice attr_done;
+    if (!attr_done.done()) {
         if (cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(tc_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(tc_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return VG_ERR_CUDA;
-        attr_done = true;
+        attr_done.mark();
     }
     int grid = p.nwork < 148 ? p.nwork : 148;
     if (p.BD == 8) tc_conv_kernel<8><<<grid, TC_THREADS, smem, stream>>>(tmap, p);

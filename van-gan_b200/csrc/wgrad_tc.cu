@@ -514,10 +514,10 @@ int vg_wg_tc_launch(const bf16* x, const bf16* dy, float* dw, int Nb, int XD, in
         ca = (e && e[0] == 'c' && e[1] == 'a') ? 1 : 0;
     }
     p.ca = ca;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static VgPerDevice attr_done;
+    if (!attr_done.done()) {
         if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return VG_ERR_CUDA;
-        attr_done = true;
+        attr_done.mark();
     }
     const size_t smem = (size_t)p.stages * p.stage_bytes + 256;
     wgrad_tc_kernel<<<p.tiles * p.ksplit, WG_THREADS, smem, stream>>>(p);
