@@ -153,6 +153,13 @@ def test_vnet_blocks_teacher_forced(cuda, S, filters, L, N):
     assert rel_l2(out.data, ref) < 2e-2, "head"
 
 
+# Measured (B200, deterministic): output 1.9e-2, aggregate gradient 0.19, worst variable (bridge.c2.in.beta) 0.34 against the
+# bf16-storage oracle -- the conditioning described in the docstring below, not wiring: every block of this network, teacher-forced
+# with the oracle's own activations, is within 1.5e-2 (test_vnet_blocks_teacher_forced).  A missing or mis-scaled edge gives >= 1.0
+# on the variables behind it, so both bounds still reject a wrong backward graph.
+AGG_TOL, VAR_TOL = 0.25, 0.45
+
+
 def test_vnet_whole_network(cuda):
     """End to end, output and weight gradients.  A randomly initialised V-Net (conv -> ReLU -> InstanceNorm chains without
     residual paths) amplifies ANY perturbation ~2.2x per block: the fp32 oracle itself moves 1.3e-2 when its input is
@@ -184,10 +191,15 @@ def test_vnet_whole_network(cuda):
     gg = net.export_grads()
     num = sum(float(((torch.tensor(gg[k]).double() - gref[k].double()) ** 2).sum()) for k in shapes)
     den = sum(float((gref[k].double() ** 2).sum()) for k in shapes)
-    assert (num / den) ** 0.5 < 0.35, (num / den) ** 0.5
+    agg = (num / den) ** 0.5
+    per = {k: rel_l2(torch.tensor(gg[k]), gref[k]) for k in shapes}
+    worst = max(per, key=per.get)
+    print("vnet whole network: output %.2e, gradient aggregate %.2e, worst variable %s %.2e"
+          % (rel_l2(out.data, y.detach()), agg, worst, per[worst]))
+    assert agg < AGG_TOL, agg
     # every variable receives a gradient of the right scale (a missing edge in the backward graph would give 0 or O(1) error)
     for k in shapes:
-        assert rel_l2(torch.tensor(gg[k]), gref[k]) < 0.9, k
+        assert per[k] < VAR_TOL, (k, per[k])
 
 
 def OrderedDict_zip(keys, vals):
