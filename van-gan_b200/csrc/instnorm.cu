@@ -75,6 +75,13 @@ struct VoxIter {
     }
 };
 
+// Sample order of the FIRST pass of a two-pass operation (statistics before apply, backward reduction before backward apply): last
+// sample first.  The producing convolution wrote the tensor in ascending sample order, so its tail is what the 126 MB L2 still holds;
+// the pass then ends on sample 0, which is where the second pass (ascending) begins.  The result does not depend on the order
+// (every (sample, block) partial has its own slot).  Measured at 8x128^3: statistics 4.8 -> 4.6 ms per step, backward unchanged
+// (a sample's x + dy is 137 MB, more than the L2 holds) -- kept because it is free, not because it matters.
+__device__ __forceinline__ int first_pass_sample() { return (int)(gridDim.y - 1 - blockIdx.y); }
+
 // ------------------------------------------------------------------ statistics
 // partial[(n*nblk + blk)*C*2 + c*2 + {0,1}] = sum / sumsq of (x - shift_c) over the block's voxels,
 // shift_c = x[n,0,c] (keeps E[x^2]-E[x]^2 well conditioned)
@@ -82,7 +89,7 @@ template <typename T>
 __global__ void __launch_bounds__(NT) in_stats_partial_kernel(const T* __restrict__ x, int V, int C,
                                                               float* __restrict__ partial, int relu_in) {
     extern __shared__ float sm[];  // [vlanes][C][2]
-    const int n = blockIdx.y, cg = C / 8;
+    const int n = first_pass_sample(), cg = C / 8;
     const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
     const T* xn = x + (size_t)n * V * C + c8 * 8;
     float shift[8], s1[8], s2[8];
@@ -255,7 +262,7 @@ template <typename T>
 __global__ void __launch_bounds__(NT, 2) in_bwd_partial_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g,
                                                             BwdArgs a, float* __restrict__ partial) {
     extern __shared__ float sm[];
-    const int n = blockIdx.y, C = g.C, cg = C / 8;
+    const int n = first_pass_sample(), C = g.C, cg = C / 8;
     const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
     const int PD = g.D + g.pad_lo + g.pad_hi, PH = g.H + g.pad_lo + g.pad_hi, PW = g.W + g.pad_lo + g.pad_hi;
     const int M = PD * PH * PW;
@@ -618,7 +625,7 @@ __global__ void __launch_bounds__(NT, 2) in_bwd_partial_sp_kernel(const T* __res
     const int pad_mode = SP == 0 ? pad_mode : VG_PAD_REFLECT;
     const bool relu_in = SP == 0 && relu_in;
     extern __shared__ float sm[];
-    const int n = blockIdx.y, C = g.C, cg = C / 8;
+    const int n = first_pass_sample(), C = g.C, cg = C / 8;
     const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
     const int PD = g.D + pad_lo + pad_hi, PH = g.H + pad_lo + pad_hi, PW = g.W + pad_lo + pad_hi;
     const int M = PD * PH * PW;
@@ -940,7 +947,7 @@ template <typename T>
 __global__ void __launch_bounds__(NT, 2) in_bwd_partial_folded_kernel(const T* __restrict__ dy, const T* __restrict__ x, Geo g,
                                                                    BwdArgs a, float* __restrict__ partial) {
     extern __shared__ float sm[];
-    const int n = blockIdx.y, C = g.C, cg = C / 8;
+    const int n = first_pass_sample(), C = g.C, cg = C / 8;
     const int c8 = threadIdx.x % cg, vl = threadIdx.x / cg, nvl = blockDim.x / cg;
     const int PD = g.D + 2, PH = g.H + 2, PW = g.W + 2;
     const int V = g.D * g.H * g.W;
