@@ -277,6 +277,9 @@ def run_gpu(args):
         launch_mode = ("CUDA graph replay: one graph (losses, four backward sweeps, clip+Adam, operand repack)" if world == 1 else
                        ("CUDA graph replay: one graph with the bucketed NCCL all-reduces (vg_comm) captured on the communication stream"
                         if gan._graph["mode"] == "single" else
+                        "CUDA graph replay: two graphs (forward + the four backward sweeps side by side / clip+Adam); the bucketed NCCL "
+                        "all-reduces (vg_comm) of the four networks are enqueued on the communication stream between the replays"
+                        if gan._graph["mode"] == "two" else
                         "CUDA graph replay: three graphs (forward + generator sweeps / discriminator sweeps / clip+Adam); the bucketed NCCL "
                         "all-reduces (vg_comm) are enqueued on the communication stream between the replays, the generators' overlapping the "
                         "discriminator sweeps"))

@@ -47,6 +47,26 @@ def test_soft_skel_backward(cuda, shape, iters):
     assert float((dx - x.grad).abs().max()) < 1e-5 * float(x.grad.abs().max()) + 1e-6
 
 
+@pytest.mark.parametrize("scale", [1e-20, 1e-6, 1e20])
+def test_soft_skel_backward_gradient_scale(cuda, scale):
+    """The routing kernel accumulates in fixed point with a scale taken from the largest value of each level: the result must be
+    as accurate for tiny and huge incoming gradients as for O(1) ones, and bit-identical from call to call."""
+    from oracle import losses as OL
+    from van_gan_b200 import clDice_func as K
+    shape, iters = (2, 18, 26, 34), 7
+    rng = np.random.default_rng(28)
+    x = torch.tensor(rng.random(shape + (1,)), dtype=torch.float32, requires_grad=True)
+    g = torch.tensor(rng.standard_normal(shape + (1,)), dtype=torch.float32)
+    g[0, 3, 4, 5, 0] = 300.0                                        # one dominant element sets the scale for everything else
+    OL.soft_skel(x, iters).backward(g)
+    _skel, bwd = K.soft_skel_with_grad(x.detach().cuda(), iters)
+    dx = bwd((g * scale).cuda())
+    assert torch.equal(dx, bwd((g * scale).cuda()))
+    dx = (dx.double() / scale).float().cpu()
+    assert rel_l2(dx, x.grad) < 1e-5
+    assert float((dx - x.grad).abs().max()) < 1e-5 * float(x.grad.abs().max())
+
+
 @pytest.mark.parametrize("shape,iters,levels", [((2, 37, 21, 45), 4, 4), ((1, 70, 18, 30), 6, 2), ((3, 9, 40, 33), 3, 8)])
 def test_soft_skel_backward_with_ties(cuda, shape, iters, levels, monkeypatch):
     """Quantised volumes (segmentation-like plateaus): almost every min / max window holds several equal extrema, so the gradient

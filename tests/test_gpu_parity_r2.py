@@ -303,7 +303,7 @@ def _fresh_gan(S, b, use_graph, seed=77):
     return gan
 
 
-@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("split", [False, True, 2])
 def test_graph_replay_equals_eager(cuda, split, monkeypatch):
     """split=True: the capture layout of the multi-GPU step -- forward + generator sweeps / discriminator sweeps / clip+Adam as three
     graphs with the gradient all-reduces enqueued between the replays (VG_GRAPH_SPLIT=1 selects it on one GPU).  Both layouts run the
@@ -316,14 +316,15 @@ def test_graph_replay_equals_eager(cuda, split, monkeypatch):
     from test_gpu_train_step import synth
     S, b = 32, 2
     if split:
-        monkeypatch.setenv("VG_GRAPH_SPLIT", "1")
+        monkeypatch.setenv("VG_GRAPH_SPLIT", "2" if split == 2 else "1")   # 2: forward + four sweeps / clip+Adam as two graphs
     rng = np.random.default_rng(31)
     batches = [synth(rng, b, S) for _ in range(4)]
     gan = _fresh_gan(S, b, True)
     for I, Sg in batches[:3]:
         gan.train_step(I.cuda(), Sg.cuda())
     assert gan._graph is not None and gan.launches_per_replay > 100, "the graph path did not engage"
-    assert gan._graph["mode"] == ("per-sweep" if split else "single") and len(gan._graph["graphs"]) == (3 if split else 1)
+    assert gan._graph["mode"] == {False: "single", True: "per-sweep", 2: "two"}[split]
+    assert len(gan._graph["graphs"]) == {False: 1, True: 3, 2: 2}[split]
     snap = {k: (net.w.clone(), net.m.clone(), net.v.clone(), net.step_count) for k, net in gan.networks.items()}
     step0 = gan.step
 

@@ -383,7 +383,11 @@ class VanGan:
             graphs.append(g)
             return out
 
-        split = (world > 1 and not in_graph_comm) or os.environ.get("VG_GRAPH_SPLIT") == "1"   # VG_GRAPH_SPLIT=1: per-sweep graphs at world 1 (tests)
+        gsplit = os.environ.get("VG_GRAPH_SPLIT", "0")      # "1" / "2": the multi-GPU capture layouts at world 1 (tests)
+        split = (world > 1 and not in_graph_comm) or gsplit in ("1", "2")
+        # multi-GPU layout: "per-sweep" (three graphs, the generators' all-reduces beside the discriminator sweeps) or "two" (forward +
+        # all four sweeps side by side / clip+Adam, every all-reduce between the two: full four-way concurrency, exchange exposed)
+        layout = "two" if (gsplit == "2" or (gsplit != "1" and os.environ.get("VG_GRAPH_LAYOUT", "per-sweep") == "two")) else "per-sweep"
         if not split:
             def whole():
                 result, _plan, handles = self._body_losses_and_sweeps(E.Var(gI), E.Var(gS), None, in_graph_comm)
@@ -394,6 +398,10 @@ class VanGan:
                 return result
             result = capture(whole)
             mode = "single"
+        elif layout == "two":
+            result = capture(lambda: self._body_losses_and_sweeps(E.Var(gI), E.Var(gS), None, False)[0])
+            capture(self._body_adam)
+            mode = "two"
         else:
             state = {}
 
@@ -432,6 +440,13 @@ class VanGan:
         self._upload_step_state()
         if g["mode"] == "single":
             g["graphs"][0].replay()
+        elif g["mode"] == "two":
+            g["graphs"][0].replay()
+            handles = [self.strategy.all_reduce_async(net.g) for net in (self.gen_IS, self.gen_SI, self.disc_I, self.disc_S)]
+            for h in handles:
+                if h is not None:
+                    h.wait()
+            g["graphs"][1].replay()
         else:
             handles = []
             for gr, nets in zip(g["graphs"][:2], ((self.gen_IS, self.gen_SI), (self.disc_I, self.disc_S))):
