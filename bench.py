@@ -280,9 +280,10 @@ def run_gpu(args):
                         "CUDA graph replay: two graphs (forward + the four backward sweeps side by side / clip+Adam); the bucketed NCCL "
                         "all-reduces (vg_comm) of the four networks are enqueued on the communication stream between the replays"
                         if gan._graph["mode"] == "two" else
-                        "CUDA graph replay: three graphs (forward + generator sweeps / discriminator sweeps / clip+Adam); the bucketed NCCL "
-                        "all-reduces (vg_comm) are enqueued on the communication stream between the replays, the generators' overlapping the "
-                        "discriminator sweeps"))
+                        "CUDA graph replay: four graphs (forward + generator sweeps / discriminator sweeps / clip+Adam of the generators / "
+                        "clip+Adam of the discriminators); the bucketed NCCL all-reduces (vg_comm) are enqueued on the communication stream "
+                        "between the replays: the generators' run beside the discriminator sweeps, the discriminators' beside the generators' "
+                        "update"))
         if gan.use_streams:
             launch_mode += "; the two generator chains of the forward pass and the backward sweeps run on side streams"
     comm_msgs = int(strategy._L.vg_comm_collectives(strategy.comm)) if strategy.comm is not None else 0

@@ -324,7 +324,7 @@ def test_graph_replay_equals_eager(cuda, split, monkeypatch):
         gan.train_step(I.cuda(), Sg.cuda())
     assert gan._graph is not None and gan.launches_per_replay > 100, "the graph path did not engage"
     assert gan._graph["mode"] == {False: "single", True: "per-sweep", 2: "two"}[split]
-    assert len(gan._graph["graphs"]) == {False: 1, True: 3, 2: 2}[split]
+    assert len(gan._graph["graphs"]) == {False: 1, True: 4, 2: 2}[split]   # per-sweep: gen sweeps / disc sweeps / gen update / disc update
     snap = {k: (net.w.clone(), net.m.clone(), net.v.clone(), net.step_count) for k, net in gan.networks.items()}
     step0 = gan.step
 

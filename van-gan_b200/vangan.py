@@ -295,8 +295,12 @@ class VanGan:
         handles = self._sweeps(plan, overlap_allreduce)
         return result, plan, handles
 
-    def _body_adam(self):
+    def _body_adam(self, only=None):
+        """clip + Adam + operand repack of every network, or of those in `only` (the generators' update runs beside the
+        discriminators' all-reduce in the multi-GPU layout)"""
         for i, opt in enumerate(self.optimizers.values()):
+            if only is not None and opt.net not in only:
+                continue
             opt.net.adam_step(lr_t_dev=self._lr_dev[i:i + 1], beta_1=opt.beta_1, beta_2=opt.beta_2, eps=opt.epsilon,
                               clipnorm=opt.clipnorm)
 
@@ -359,11 +363,11 @@ class VanGan:
     def _capture(self, real_I, real_S):
         """The step as CUDA graphs.
         World 1: ONE graph -- losses, the four backward sweeps, clip+Adam, operand repack.
-        World > 1: graph 1 = forward pass, losses and the two generator sweeps; graph 2 = the two discriminator sweeps; graph 3 =
-        clip+Adam.  Between the replays the bucketed gradient all-reduces of the networks just swept are enqueued on the
-        communication stream (vg_comm, ordered by events): the generators' messages run while the discriminator sweeps execute,
-        and the Adam graph is ordered after the last message.  Replays and collectives are all asynchronous: the host enqueues
-        the whole step without waiting.
+        World > 1: graph 1 = forward pass, losses and the two generator sweeps; graph 2 = the two discriminator sweeps; graphs 3 / 4 =
+        clip+Adam of the generators / of the discriminators.  Between the replays the bucketed gradient all-reduces of the networks
+        just swept are enqueued on the communication stream (vg_comm, ordered by events): the generators' messages run while the
+        discriminator sweeps execute, the discriminators' while the generators are updated, and each update graph is ordered after
+        its own messages.  Replays and collectives are all asynchronous: the host enqueues the whole step without waiting.
         VG_GRAPH_COMM=1 captures the collectives INTO a single graph instead (measured: fine at 32^3, hangs at 4x128^3 per GPU on
         2 GPUs -- kept opt-in for investigation)."""
         from . import _lib
@@ -385,7 +389,8 @@ class VanGan:
 
         gsplit = os.environ.get("VG_GRAPH_SPLIT", "0")      # "1" / "2": the multi-GPU capture layouts at world 1 (tests)
         split = (world > 1 and not in_graph_comm) or gsplit in ("1", "2")
-        # multi-GPU layout: "per-sweep" (three graphs, the generators' all-reduces beside the discriminator sweeps) or "two" (forward +
+        # multi-GPU layout: "per-sweep" (four graphs: generator sweeps / discriminator sweeps / the two updates, with the generators'
+        # all-reduces beside the discriminator sweeps and the discriminators' beside the generators' update) or "two" (forward +
         # all four sweeps side by side / clip+Adam, every all-reduce between the two: full four-way concurrency, exchange exposed)
         layout = "two" if (gsplit == "2" or (gsplit != "1" and os.environ.get("VG_GRAPH_LAYOUT", "per-sweep") == "two")) else "per-sweep"
         if not split:
@@ -413,7 +418,10 @@ class VanGan:
                 return res
             result = capture(first)
             capture(lambda: self._sweeps(state["plan"][2:], False))   # both discriminator sweeps
-            capture(self._body_adam)
+            # two update graphs: the generators' (their all-reduces finished beside the discriminator sweeps) runs while the
+            # discriminators' messages are in flight, the discriminators' after them
+            capture(lambda: self._body_adam(only=(self.gen_IS, self.gen_SI)))
+            capture(lambda: self._body_adam(only=(self.disc_I, self.disc_S)))
             mode = "per-sweep"
         self.launches_per_replay = int(_lib.lib().vg_launch_count() - l0)
         ctx = self.loss_ctx
@@ -448,14 +456,19 @@ class VanGan:
                     h.wait()
             g["graphs"][1].replay()
         else:
-            handles = []
-            for gr, nets in zip(g["graphs"][:2], ((self.gen_IS, self.gen_SI), (self.disc_I, self.disc_S))):
-                gr.replay()
-                handles += [self.strategy.all_reduce_async(net.g) for net in nets]     # run beside the next graph
-            for h in handles:
+            gens, discs = (self.gen_IS, self.gen_SI), (self.disc_I, self.disc_S)
+            g["graphs"][0].replay()                                                   # forward + generator sweeps
+            gen_h = [self.strategy.all_reduce_async(net.g) for net in gens]           # ... their messages run beside graph 1
+            g["graphs"][1].replay()                                                   # discriminator sweeps
+            disc_h = [self.strategy.all_reduce_async(net.g) for net in discs]
+            for h in gen_h:
                 if h is not None:
                     h.wait()
-            g["graphs"][2].replay()
+            g["graphs"][2].replay()                                                   # clip+Adam of the generators, beside the discriminators' messages
+            for h in disc_h:
+                if h is not None:
+                    h.wait()
+            g["graphs"][3].replay()                                                   # clip+Adam of the discriminators
         g["ctx"].host = None
         return self._finish_step(g["result"], g["ctx"], True)
 
