@@ -61,3 +61,37 @@ def test_strategy_single_process_is_a_no_op():
     assert s.num_replicas_in_sync == 1 and s.rank == 0
     t = torch.ones(4)
     assert s.all_reduce_async(t) is None and torch.equal(s.reduce("SUM", t), torch.ones(4))
+
+
+def test_skeleton_ring_fixed_point_split_is_exact_and_order_independent():
+    """The arithmetic of the soft-skeleton routing kernel's accumulator ring (csrc/skel.cu, skel_bwd_route_march_kernel), restated in
+    numpy fp32: with 2^e above the largest magnitude, v = hi * 2^-sh + lo * 2^-(sh+25) exactly (sh = 25 - e), |hi| <= 2^25,
+    |lo| <= 2^24, so 46 contributions fit an int32 and their integer sums do not depend on the order of the atomics."""
+    rng = np.random.default_rng(41)
+    f32 = np.float32
+    for scale in (1e-20, 3e-7, 1.0, 777.0, 1e20):
+        v = (rng.standard_normal(4096) * rng.choice([1e-6, 1e-3, 1.0], 4096) * scale).astype(f32)
+        m = f32(np.abs(v).max())
+        bits = np.array([m], dtype=f32).view(np.uint32)[0]
+        e = int((bits >> 23) & 0xff) - 126                     # m = f * 2^e, f in [0.5, 1)
+        assert m < 2.0 ** e and m >= 2.0 ** (e - 1)
+        sh = max(-100, min(100, 25 - e))
+        fx_hi, fx_hi_inv = f32(2.0 ** sh), f32(2.0 ** -sh)
+        hs = np.rint(v * fx_hi).astype(f32)                    # exact: power-of-two scaling, |.| <= 2^25 is an integer-valued float
+        assert np.abs(hs).max() <= 2 ** 25
+        rem = ((v.astype(np.float64) - hs.astype(np.float64) * float(fx_hi_inv)).astype(f32) * fx_hi)   # the fmaf of the kernel
+        assert np.array_equal(rem.astype(np.float64), (v.astype(np.float64) - hs.astype(np.float64) * 2.0 ** -sh) * 2.0 ** sh)
+        assert np.abs(rem).max() <= 0.5
+        lo = np.rint(rem * f32(2.0 ** 25)).astype(np.int64)
+        hi = hs.astype(np.int64)
+        assert np.abs(lo).max() <= 2 ** 24
+        back = hi.astype(np.float64) * 2.0 ** -sh + lo.astype(np.float64) * 2.0 ** -(sh + 25)
+        assert np.abs(back - v.astype(np.float64)).max() <= 2.0 ** (e - 51)          # half a unit of the low part
+        # sums of 46 contributions per cell, in two different orders, in int32
+        cells = rng.integers(0, 64, 46 * 64)
+        idx = rng.integers(0, v.size, cells.size)
+        acc_a, acc_b = np.zeros((2, 64), np.int64), np.zeros((2, 64), np.int64)
+        for order, acc in ((np.arange(cells.size), acc_a), (rng.permutation(cells.size), acc_b)):
+            np.add.at(acc[0], cells[order], hi[idx[order]])
+            np.add.at(acc[1], cells[order], lo[idx[order]])
+        assert np.array_equal(acc_a, acc_b) and np.abs(acc_a).max() < 2 ** 31
