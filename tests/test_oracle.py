@@ -264,3 +264,79 @@ def test_keras_bce_and_lsgan_known_values():
     t0 = -np.log((f(1) - f(f(1) - f(1e-7))) + f(1e-7))
     expect_flip = 10.0 * 0.5 * (float(t1) + float(t0))
     assert abs(flipped - expect_flip) < 1e-4 * expect_flip
+
+
+def test_adam_recursion_against_torch_adam_over_several_steps():
+    """Independent second opinion on the optimizer recursion (moments, bias correction, step counter): with eps -> 0 Keras' form
+    lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps) and torch.optim.Adam's lr/(1-b1^t) * m/(sqrt(v/(1-b2^t))+eps) are the same
+    update, so five steps of the oracle's Adam must follow torch's on identical gradients (clipnorm out of reach)."""
+    rng = np.random.default_rng(12)
+    w0 = torch.tensor(rng.standard_normal(64), dtype=torch.float64)
+    grads = [torch.tensor(rng.standard_normal(64), dtype=torch.float64) for _ in range(5)]
+    P = {"a": w0.clone()}
+    opt = OS.Adam(["a"], lr=2e-4, beta_1=0.5, beta_2=0.9, eps=1e-300, clipnorm=1e30)
+    wt = w0.clone().requires_grad_(True)
+    topt = torch.optim.Adam([wt], lr=2e-4, betas=(0.5, 0.9), eps=1e-300)
+    for g in grads:
+        opt.apply(P, {"a": g})
+        wt.grad = g.clone()
+        topt.step()
+        assert torch.allclose(P["a"], wt.detach(), rtol=1e-12, atol=1e-15)
+    # and the clip is per variable, on the aggregated gradient, before the moments see it (vangan.py:220-235: clipnorm=100)
+    g = torch.tensor(rng.standard_normal(64) * 1e3, dtype=torch.float64)
+    gc = OS.clip_by_norm(g, 100.0)
+    assert abs(float(gc.norm()) - 100.0) < 1e-9 and torch.allclose(gc / gc.norm(), g / g.norm())
+    assert torch.equal(OS.clip_by_norm(g * 1e-6, 100.0), g * 1e-6)
+
+
+def test_batch_norm_against_torch_functional():
+    """oracle.nets.batch_norm (Keras BatchNormalization, momentum 0.99, eps 1e-3) against torch.nn.functional.batch_norm: same
+    normalised output and gradients in training mode, same moving averages (torch momentum = 1 - Keras momentum; both use the
+    Bessel-corrected batch variance for the moving variance), same inference output."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(13)
+    C = 6
+    x = torch.tensor(rng.standard_normal((2, 3, 4, 5, C)) * 2 + 0.5, dtype=torch.float64, requires_grad=True)
+    gamma = torch.tensor(rng.random(C) + 0.5, dtype=torch.float64, requires_grad=True)
+    beta = torch.tensor(rng.standard_normal(C), dtype=torch.float64, requires_grad=True)
+    gy = torch.tensor(rng.standard_normal((2, 3, 4, 5, C)), dtype=torch.float64)
+    state = {"k.moving_mean": torch.zeros(C, dtype=torch.float64), "k.moving_variance": torch.ones(C, dtype=torch.float64)}
+    y = ON.batch_norm(x, gamma, beta, state, "k", training=True)
+    g_o = torch.autograd.grad((y * gy).sum(), [x, gamma, beta])
+    rm, rv = torch.zeros(C, dtype=torch.float64), torch.ones(C, dtype=torch.float64)
+    xt = x.detach().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    gt, bt = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    yt = F.batch_norm(xt, rm, rv, gt, bt, training=True, momentum=1.0 - ON.BN_MOMENTUM, eps=ON.BN_EPS)
+    g_t = torch.autograd.grad((yt * gy.permute(0, 4, 1, 2, 3)).sum(), [xt, gt, bt])
+    assert torch.allclose(y, yt.permute(0, 2, 3, 4, 1), rtol=1e-10, atol=1e-12)
+    assert torch.allclose(g_o[0], g_t[0].permute(0, 2, 3, 4, 1), rtol=1e-9, atol=1e-12)
+    assert torch.allclose(g_o[1], g_t[1], rtol=1e-9) and torch.allclose(g_o[2], g_t[2], rtol=1e-9)
+    assert torch.allclose(state["k.moving_mean"], rm, rtol=1e-12) and torch.allclose(state["k.moving_variance"], rv, rtol=1e-12)
+    yi = ON.batch_norm(x.detach(), gamma.detach(), beta.detach(), state, "k", training=False)
+    yti = F.batch_norm(xt.detach(), rm, rv, gt.detach(), bt.detach(), training=False, eps=ON.BN_EPS)
+    assert torch.allclose(yi, yti.permute(0, 2, 3, 4, 1), rtol=1e-10, atol=1e-12)
+
+
+def test_instance_norm_and_transposed_conv_against_torch_functional():
+    """tfa InstanceNormalization (eps 1e-3, biased variance) == torch instance_norm with the same eps; Conv3DTranspose k2 s2
+    'same' == conv_transpose3d stride 2 with the Keras kernel (kd,kh,kw,Cout,Cin) permuted, checked by explicit index arithmetic."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(14)
+    x = torch.tensor(rng.standard_normal((2, 4, 5, 6, 8)), dtype=torch.float64)
+    gamma, beta = torch.tensor(rng.random(8) + 0.5, dtype=torch.float64), torch.tensor(rng.standard_normal(8), dtype=torch.float64)
+    y = ON.instance_norm(x, gamma, beta)
+    yt = F.instance_norm(x.permute(0, 4, 1, 2, 3), weight=gamma, bias=beta, eps=1e-3).permute(0, 2, 3, 4, 1)
+    assert torch.allclose(y, yt, rtol=1e-10, atol=1e-12)
+    xs = torch.tensor(rng.standard_normal((1, 2, 3, 2, 3)), dtype=torch.float64)
+    w = torch.tensor(rng.standard_normal((2, 2, 2, 4, 3)), dtype=torch.float64)     # (kd, kh, kw, Cout, Cin)
+    b = torch.tensor(rng.standard_normal(4), dtype=torch.float64)
+    yc = ON.conv3d_transpose_k2s2(xs, w, b)
+    ref = torch.zeros((1, 4, 6, 4, 4), dtype=torch.float64)
+    for d in range(2):
+        for h in range(3):
+            for ww in range(2):
+                for a in range(2):
+                    for bb in range(2):
+                        for c in range(2):
+                            ref[0, 2 * d + a, 2 * h + bb, 2 * ww + c] = w[a, bb, c] @ xs[0, d, h, ww] + b
+    assert torch.allclose(yc, ref, rtol=1e-12, atol=1e-12)
